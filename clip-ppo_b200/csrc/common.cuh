@@ -1,0 +1,68 @@
+// Shared helpers for the sm_100a kernels of the CLIP-PPO observation path.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+#include "../../include/clipppo_b200.h"
+
+namespace clipppo {
+
+// cudaError_t of the most recent failing runtime/driver call on this host thread.
+int& last_cuda_error_ref();
+
+inline int record_cuda(cudaError_t e) {
+    if (e == cudaSuccess) return CLIPPPO_OK;
+    last_cuda_error_ref() = static_cast<int>(e);
+    return CLIPPPO_ERR_CUDA;
+}
+
+#define CLIPPPO_CUDA_TRY(expr)                                         \
+    do {                                                               \
+        cudaError_t e__ = (expr);                                      \
+        if (e__ != cudaSuccess) return ::clipppo::record_cuda(e__);    \
+    } while (0)
+
+// Launch-error check that never synchronises.
+#define CLIPPPO_CHECK_LAUNCH() CLIPPPO_CUDA_TRY(cudaGetLastError())
+
+inline cudaStream_t as_stream(clipppo_stream_t s) { return static_cast<cudaStream_t>(s); }
+
+constexpr int kNumSMs = 148;   // B200: 2 dies x 74 SMs
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Block-wide sum; `scratch` needs >= 32 floats of shared memory.  Every thread gets the total.
+__device__ __forceinline__ float block_sum(float v, float* scratch) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    v = warp_sum(v);
+    __syncthreads();                       // scratch may still be in use by a previous call
+    if (lane == 0) scratch[warp] = v;
+    __syncthreads();
+    const int nwarps = (blockDim.x + 31) >> 5;
+    float t = (lane < nwarps) ? scratch[lane] : 0.0f;
+    return warp_sum(t);
+}
+
+__device__ __forceinline__ uint32_t ptx_smem(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+// Streaming 128-bit accesses: read-once / write-once data should not pollute L1.
+__device__ __forceinline__ float4 ld_stream_f4(const float* p) {
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void st_stream_f4(float* p, float4 v) {
+    asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};"
+                 :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+}  // namespace clipppo

@@ -1,0 +1,350 @@
+// D1 - fused visual disturbance: noise -> contrast -> blur -> cutout, one launch, one HBM pass.
+//
+// Replaces DisturbanceWrapperGPU.apply_disturbances (reference shared/disturbances_gpu.py:66-73)
+// and, through the `stages` mask, each of its four stage methods.  Numerical spec: SURVEY.md
+// Appendix A (torchvision gaussian_noise_image / adjust_contrast / gaussian_blur + the
+// reference's own cutout).
+//
+// Data layout.  An image is split into S horizontal stripes; the S CTAs that own them form one
+// thread-block cluster.  Each CTA keeps its stripe (all channels, plus 2*(k/2) halo rows) in
+// shared memory, so x and noise are read from HBM exactly once and `out` is written once:
+// 12 algorithmic bytes per element.  The only cross-stripe dependencies - the per-image gray
+// mean of the contrast stage and the halo rows of the vertical blur - travel over distributed
+// shared memory inside the cluster, not through HBM.
+//
+//   phase 1  load x (+ sigma*noise, clamp) -> smem, accumulate the gray sum      [HBM read]
+//   phase 2  block reduce, cluster reduce over DSMEM -> per-image mean
+//   phase 3  contrast blend in place in smem
+//   phase 4  halo rows (reflect at the image border) copied from the owning CTA's smem
+//   phase 5  separable blur: horizontal taps from smem, vertical taps from a register ring;
+//            cutout predicate on the store                                         [HBM write]
+#include <cooperative_groups.h>
+
+#include "common.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace clipppo {
+
+struct DisturbParams {
+    const void* x;
+    const float* noise;
+    void* out;
+    long long xs[4], ns[4];
+    int B, C, H, W;
+    int stages;
+    float sigma_n, c, omc;
+    float taps[CLIPPPO_MAX_BLUR_TAPS];
+    int sh, sw, ph, pw;
+    int S, R;       // stripes per image (= cluster size), rows per stripe
+    int fast;       // x / noise contiguous NCHW fp32, W % 4 == 0, 16-byte aligned
+    int io_mode;    // 0: fp32 strided in, fp32 NCHW out.  1: u8 NHWC in / u8 NHWC out.
+                    // 2: fp32 (0..255) NHWC in / u8 NHWC out.
+};
+
+constexpr int kDisturbThreads = 256;
+constexpr int kSmemHeaderFloats = 64;   // [0,32) reduction scratch, [32] cluster partial
+
+__device__ __forceinline__ float clamp01(float v) { return fminf(fmaxf(v, 0.0f), 1.0f); }
+
+// [tv] gaussian_noise_image: clamp(x + (0.0 + n*sigma), 0, 1); no FMA contraction so the
+// result is bit-identical to the eager mul / add / clamp sequence.
+__device__ __forceinline__ float noisy(float x, float n, float sigma) {
+    return clamp01(__fadd_rn(x, __fmul_rn(n, sigma)));
+}
+
+template <int K>
+__global__ void __launch_bounds__(kDisturbThreads)
+disturb_kernel(const __grid_constant__ DisturbParams p) {
+    constexpr int P = K / 2;
+    extern __shared__ __align__(16) float smem[];
+    float* red = smem;
+    float* partial = smem + 32;
+    float* tile = smem + kSmemHeaderFloats;
+
+    cg::cluster_group cluster = cg::this_cluster();
+    const int S = p.S, R = p.R, C = p.C, H = p.H, W = p.W;
+    const int b = blockIdx.x / S, s = blockIdx.x % S;
+    const int r0 = min(s * R, H), r1 = min(r0 + R, H), rows = r1 - r0;
+    const int RS = R + 2 * P;                 // smem rows per channel
+    const int tid = threadIdx.x, nth = blockDim.x;
+    const bool do_noise = (p.stages & CLIPPPO_STAGE_NOISE) != 0;
+    const bool do_contrast = (p.stages & CLIPPPO_STAGE_CONTRAST) != 0;
+    const bool do_cut = (p.stages & CLIPPPO_STAGE_CUTOUT) != 0;
+    const float sigma = p.sigma_n;
+
+    // ---- phase 1: stripe -> smem -----------------------------------------------------------
+    float gsum = 0.0f;
+    if (p.fast) {
+        const int W4 = W >> 2;
+        const int n4 = rows * W4;             // float4 per channel
+        const int total4 = C * n4;
+        const float* xb = static_cast<const float*>(p.x) + (size_t)b * C * H * W;
+        const float* nb = p.noise ? p.noise + (size_t)b * C * H * W : nullptr;
+        constexpr int UNR = 4;
+        for (int i0 = tid; i0 < total4; i0 += nth * UNR) {
+            float4 xv[UNR], nv[UNR];
+#pragma unroll
+            for (int u = 0; u < UNR; ++u) {
+                const int i = i0 + u * nth;
+                if (i < total4) {
+                    const int c_ = i / n4, rem = i - c_ * n4;
+                    const size_t g = ((size_t)c_ * H + r0) * W + (size_t)rem * 4;
+                    xv[u] = ld_stream_f4(xb + g);
+                    if (do_noise) nv[u] = ld_stream_f4(nb + g);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < UNR; ++u) {
+                const int i = i0 + u * nth;
+                if (i < total4) {
+                    const int c_ = i / n4, rem = i - c_ * n4;
+                    float4 v = xv[u];
+                    if (do_noise) {
+                        v.x = noisy(v.x, nv[u].x, sigma);
+                        v.y = noisy(v.y, nv[u].y, sigma);
+                        v.z = noisy(v.z, nv[u].z, sigma);
+                        v.w = noisy(v.w, nv[u].w, sigma);
+                    }
+                    const float wc = (C == 3) ? (c_ == 0 ? 0.2989f : (c_ == 1 ? 0.587f : 0.114f)) : 1.0f;
+                    gsum += wc * ((v.x + v.y) + (v.z + v.w));
+                    *reinterpret_cast<float4*>(tile + ((size_t)c_ * RS + P) * W + (size_t)rem * 4) = v;
+                }
+            }
+        }
+    } else {
+        const int n = rows * W;
+        const int total = C * n;
+        const bool chan_fastest = p.xs[1] < p.xs[3];     // NHWC-like memory order
+        for (int i = tid; i < total; i += nth) {
+            int c_, r, j;
+            if (chan_fastest) { c_ = i % C; const int q = i / C; j = q % W; r = q / W; }
+            else              { j = i % W;  const int q = i / W; r = q % rows; c_ = q / rows; }
+            const long long xo = (long long)b * p.xs[0] + c_ * p.xs[1] + (long long)(r0 + r) * p.xs[2] + j * p.xs[3];
+            float v;
+            if (p.io_mode == 0)      v = static_cast<const float*>(p.x)[xo];
+            else if (p.io_mode == 1) v = static_cast<float>(static_cast<const uint8_t*>(p.x)[xo]) / 255.0f;
+            else                     v = static_cast<const float*>(p.x)[xo] / 255.0f;
+            if (do_noise) {
+                const long long no = (long long)b * p.ns[0] + c_ * p.ns[1] + (long long)(r0 + r) * p.ns[2] + j * p.ns[3];
+                v = noisy(v, p.noise[no], sigma);
+            }
+            const float wc = (C == 3) ? (c_ == 0 ? 0.2989f : (c_ == 1 ? 0.587f : 0.114f)) : 1.0f;
+            gsum += wc * v;
+            tile[((size_t)c_ * RS + P + r) * W + j] = v;
+        }
+    }
+
+    // ---- phase 2 + 3: per-image gray mean, contrast blend in place -------------------------
+    if (do_contrast) {
+        float tot = block_sum(gsum, red);
+        if (S > 1) {
+            if (tid == 0) *partial = tot;
+            cluster.sync();
+            tot = 0.0f;
+            for (int q = 0; q < S; ++q) tot += *cluster.map_shared_rank(partial, q);
+        }
+        const float m = tot / static_cast<float>(H * W);
+        const float cm = __fmul_rn(p.omc, m);
+        const int n = rows * W;
+        __syncthreads();
+        for (int i = tid; i < C * n; i += nth) {
+            const int c_ = i / n, rem = i - c_ * n;
+            float* q = tile + ((size_t)c_ * RS + P) * W + rem;
+            *q = clamp01(__fadd_rn(__fmul_rn(p.c, *q), cm));
+        }
+    }
+
+    // ---- phase 4: halo rows over DSMEM -----------------------------------------------------
+    if (K > 1) {
+        if (S > 1) cluster.sync(); else __syncthreads();
+        if (rows > 0) {
+            const int hn = 2 * P * W;
+            for (int i = tid; i < C * hn; i += nth) {
+                const int c_ = i / hn, rem = i - c_ * hn;
+                const int hr = rem / W, j = rem - hr * W;
+                const int lr = hr < P ? hr : rows + hr;          // below the last own row
+                int ir = r0 - P + lr;                            // image row before reflection
+                if (ir < 0) ir = -ir;
+                if (ir >= H) ir = 2 * (H - 1) - ir;
+                const int owner = ir / R;
+                const int olr = ir - owner * R + P;
+                const float* src = (owner == s) ? tile : cluster.map_shared_rank(tile, owner);
+                tile[((size_t)c_ * RS + lr) * W + j] = src[((size_t)c_ * RS + olr) * W + j];
+            }
+        }
+        if (S > 1) cluster.sync(); else __syncthreads();         // also: nobody exits while peers read
+    } else {
+        __syncthreads();
+    }
+
+    // ---- phase 5: separable blur, cutout, store --------------------------------------------
+    for (int task = tid; task < C * W; task += nth) {
+        const int c_ = task / W, j = task - c_ * W;
+        int jidx[K];
+#pragma unroll
+        for (int u = 0; u < K; ++u) {
+            int jj = j + u - P;
+            if (jj < 0) jj = -jj;
+            if (jj >= W) jj = 2 * (W - 1) - jj;
+            jidx[u] = jj;
+        }
+        const float* base = tile + (size_t)c_ * RS * W;
+        float ring[K];
+#pragma unroll
+        for (int lr = 0; lr < K - 1; ++lr) {
+            float h = 0.0f;
+#pragma unroll
+            for (int u = 0; u < K; ++u) h = fmaf(p.taps[u], base[lr * W + jidx[u]], h);
+            ring[lr] = h;
+        }
+        const bool col_cut = do_cut && j >= p.sw && j < p.sw + p.pw;
+        for (int r = 0; r < rows; ++r) {
+            float h = 0.0f;
+#pragma unroll
+            for (int u = 0; u < K; ++u) h = fmaf(p.taps[u], base[(r + K - 1) * W + jidx[u]], h);
+            ring[K - 1] = h;
+            float v = 0.0f;
+#pragma unroll
+            for (int u = 0; u < K; ++u) v = fmaf(p.taps[u], ring[u], v);
+#pragma unroll
+            for (int u = 0; u < K - 1; ++u) ring[u] = ring[u + 1];
+            const int ir = r0 + r;
+            if (col_cut && ir >= p.sh && ir < p.sh + p.ph) v = 0.0f;
+            if (p.io_mode == 0) {
+                static_cast<float*>(p.out)[(((size_t)b * C + c_) * H + ir) * W + j] = v;
+            } else {
+                static_cast<uint8_t*>(p.out)[(((size_t)b * H + ir) * W + j) * C + c_] =
+                    static_cast<uint8_t>(__fmul_rn(v, 255.0f));
+            }
+        }
+    }
+}
+
+template <int K>
+static int launch_disturb(const DisturbParams& p, size_t smem, cudaStream_t stream) {
+    static bool configured = false;     // opt in to > 48 KB dynamic smem once per instantiation
+    if (!configured) {
+        CLIPPPO_CUDA_TRY(cudaFuncSetAttribute(disturb_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        configured = true;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(static_cast<unsigned>(p.B) * p.S);
+    cfg.blockDim = dim3(kDisturbThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = p.S;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    CLIPPPO_CUDA_TRY(cudaLaunchKernelEx(&cfg, disturb_kernel<K>, p));
+    return CLIPPPO_OK;
+}
+
+static int run_disturb(DisturbParams& p, const float* k1d_host, int k, cudaStream_t stream) {
+    if (p.B <= 0 || p.C <= 0 || p.H <= 0 || p.W <= 0) return CLIPPPO_ERR_BAD_SHAPE;
+    if (!p.x || !p.out) return CLIPPPO_ERR_NULL;
+    if ((p.stages & CLIPPPO_STAGE_NOISE) && !p.noise) return CLIPPPO_ERR_NULL;
+    if ((p.stages & CLIPPPO_STAGE_CONTRAST) && p.C != 1 && p.C != 3) return CLIPPPO_ERR_BAD_CHANNELS;
+    int K = 1;
+    if (p.stages & CLIPPPO_STAGE_BLUR) {
+        if (!k1d_host) return CLIPPPO_ERR_NULL;
+        if (k < 1 || k > CLIPPPO_MAX_BLUR_TAPS || (k & 1) == 0) return CLIPPPO_ERR_BAD_SHAPE;
+        if (k / 2 >= p.H || k / 2 >= p.W) return CLIPPPO_ERR_BAD_PAD;
+        K = k;
+        for (int i = 0; i < k; ++i) p.taps[i] = k1d_host[i];
+    } else {
+        p.taps[0] = 1.0f;
+    }
+    if (p.stages & CLIPPPO_STAGE_CUTOUT) {
+        if (p.sh < 0 || p.sw < 0 || p.ph < 0 || p.pw < 0) return CLIPPPO_ERR_BAD_SHAPE;
+    }
+    // stripes per image: the smallest cluster whose stripe fits the occupancy target
+    const int P = K / 2;
+    auto smem_for = [&](int S) {
+        const int R = (p.H + S - 1) / S;
+        return (size_t)(kSmemHeaderFloats + (size_t)p.C * (R + 2 * P) * p.W) * sizeof(float);
+    };
+    const size_t budgets[3] = {56 * 1024, 113 * 1024, 227 * 1024};
+    int S = 0;
+    for (int bi = 0; bi < 3 && !S; ++bi)
+        for (int cand = 1; cand <= 8; cand *= 2)
+            if (smem_for(cand) <= budgets[bi]) { S = cand; break; }
+    if (!S) return CLIPPPO_ERR_UNSUPPORTED;
+    p.S = S;
+    p.R = (p.H + S - 1) / S;
+    const size_t smem = smem_for(S);
+    switch (K) {
+        case 1:  return launch_disturb<1>(p, smem, stream);
+        case 3:  return launch_disturb<3>(p, smem, stream);
+        case 5:  return launch_disturb<5>(p, smem, stream);
+        case 7:  return launch_disturb<7>(p, smem, stream);
+        case 9:  return launch_disturb<9>(p, smem, stream);
+        case 11: return launch_disturb<11>(p, smem, stream);
+        case 13: return launch_disturb<13>(p, smem, stream);
+        case 15: return launch_disturb<15>(p, smem, stream);
+    }
+    return CLIPPPO_ERR_UNSUPPORTED;
+}
+
+static bool is_contig_nchw(const long long s[4], int C, int H, int W) {
+    return s[3] == 1 && s[2] == W && s[1] == (long long)H * W && s[0] == (long long)C * H * W;
+}
+
+}  // namespace clipppo
+
+using namespace clipppo;
+
+extern "C" int clipppo_disturb_f32(const float* x, const int64_t x_strides_host[4],
+                                   const float* noise, const int64_t noise_strides_host[4],
+                                   float* out, int B, int C, int H, int W, int stages,
+                                   float noise_sigma, float contrast,
+                                   const float* k1d_host, int k,
+                                   int sh, int sw, int ph, int pw, clipppo_stream_t stream) {
+    DisturbParams p = {};
+    p.x = x; p.noise = noise; p.out = out;
+    p.B = B; p.C = C; p.H = H; p.W = W;
+    if (B <= 0 || C <= 0 || H <= 0 || W <= 0) return CLIPPPO_ERR_BAD_SHAPE;
+    for (int i = 0; i < 4; ++i) {
+        const long long dflt[4] = {(long long)C * H * W, (long long)H * W, W, 1};
+        p.xs[i] = x_strides_host ? x_strides_host[i] : dflt[i];
+        p.ns[i] = noise_strides_host ? noise_strides_host[i] : dflt[i];
+    }
+    p.stages = stages & CLIPPPO_STAGE_ALL;
+    p.sigma_n = noise_sigma;
+    p.c = contrast;
+    p.omc = static_cast<float>(1.0 - static_cast<double>(contrast));
+    p.sh = sh; p.sw = sw; p.ph = ph; p.pw = pw;
+    p.io_mode = 0;
+    const bool need_noise = (p.stages & CLIPPPO_STAGE_NOISE) != 0;
+    p.fast = is_contig_nchw(p.xs, C, H, W) && (!need_noise || is_contig_nchw(p.ns, C, H, W)) &&
+             (W % 4 == 0) && (reinterpret_cast<uintptr_t>(x) % 16 == 0) &&
+             (!need_noise || reinterpret_cast<uintptr_t>(noise) % 16 == 0);
+    return run_disturb(p, k1d_host, k, as_stream(stream));
+}
+
+extern "C" int clipppo_disturb_nhwc_u8(const void* obs, int obs_is_f32,
+                                       const float* noise, const int64_t noise_strides_host[4],
+                                       uint8_t* out_nhwc, int B, int H, int W, int C, int stages,
+                                       float noise_sigma, float contrast, const float* k1d_host, int k,
+                                       int sh, int sw, int ph, int pw, clipppo_stream_t stream) {
+    DisturbParams p = {};
+    p.x = obs; p.noise = noise; p.out = out_nhwc;
+    p.B = B; p.C = C; p.H = H; p.W = W;
+    if (B <= 0 || C <= 0 || H <= 0 || W <= 0) return CLIPPPO_ERR_BAD_SHAPE;
+    // logical [B,C,H,W] view of NHWC memory
+    p.xs[0] = (long long)H * W * C; p.xs[1] = 1; p.xs[2] = (long long)W * C; p.xs[3] = C;
+    const long long dflt[4] = {(long long)C * H * W, (long long)H * W, W, 1};
+    for (int i = 0; i < 4; ++i) p.ns[i] = noise_strides_host ? noise_strides_host[i] : dflt[i];
+    p.stages = stages & CLIPPPO_STAGE_ALL;
+    p.sigma_n = noise_sigma;
+    p.c = contrast;
+    p.omc = static_cast<float>(1.0 - static_cast<double>(contrast));
+    p.sh = sh; p.sw = sw; p.ph = ph; p.pw = pw;
+    p.io_mode = obs_is_f32 ? 2 : 1;
+    p.fast = 0;
+    return run_disturb(p, k1d_host, k, as_stream(stream));
+}

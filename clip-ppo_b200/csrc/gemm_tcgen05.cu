@@ -1,0 +1,330 @@
+// V1/V3/V5/V6/V7 - the one GEMM of the frozen CLIP tower:  out = epilogue(A[M,K] @ W[N,K]^T)
+// bf16 operands (both K-major), fp32 accumulation in TMEM, tcgen05.mma fed by TMA.
+//
+// Replaces the cuBLAS/cuDNN calls behind [clip] VisionTransformer (conv1, in_proj, out_proj,
+// c_fc, c_proj, proj) that reference shared/clip_ppo_utils.py:163 / :213-215 trigger.
+//
+// Persistent, warp-specialised, one CTA per SM:
+//   warp 0      TMA producer: A tile 128x64 and W tile 256x64 per k-block into a 4-stage smem ring
+//   warp 1      MMA issuer: one thread issues 4 x tcgen05.mma (128x256x16) per k-block; the fp32
+//               accumulator (128 lanes x 256 columns) lives in TMEM, double-buffered (2 x 256 cols)
+//   warp 2      TMEM allocator
+//   warps 4-11  epilogue: tcgen05.ld 32x32 sub-tiles -> swizzled smem transpose -> coalesced
+//               global access with the fused bias / QuickGELU / residual / pos-emb epilogue
+// so the epilogue of tile i overlaps the MMAs of tile i+1.
+#include "common.cuh"
+#include "tc_ptx.cuh"
+#include "gemm.cuh"
+
+namespace clipppo {
+
+using namespace ptx;
+
+namespace {
+
+constexpr int BM = 128, BN = 256, BK = 64, UMMA_K = 16, STAGES = 4, ACC_STAGES = 2;
+constexpr int A_STAGE_BYTES = BM * BK * 2;              // 16 KB
+constexpr int B_STAGE_BYTES = BN * BK * 2;              // 32 KB
+constexpr int EPI_WARPS = 8;
+constexpr int EPI_STAGE_BYTES = 32 * 32 * 4;            // one 32x32 fp32 sub-tile per warp
+constexpr int NUM_THREADS = 128 + EPI_WARPS * 32;       // 4 control warps + 8 epilogue warps
+constexpr int OFF_A = 0;
+constexpr int OFF_B = OFF_A + STAGES * A_STAGE_BYTES;
+constexpr int OFF_EPI = OFF_B + STAGES * B_STAGE_BYTES;
+constexpr int OFF_BAR = OFF_EPI + EPI_WARPS * EPI_STAGE_BYTES;
+constexpr int NUM_BARS = 2 * STAGES + 2 * ACC_STAGES;
+constexpr int SMEM_BYTES = OFF_BAR + NUM_BARS * 8 + 16 + 1024;   // + tmem slot + alignment slack
+constexpr uint32_t TMEM_COLS = ACC_STAGES * BN;          // 512: the whole TMEM of the SM
+
+struct GemmArgs {
+    int M, N, K;
+    const float* bias;     // [N] or null
+    const float* pos;      // EPI_PATCH: positional embedding [tokens, N]
+    int tokens;            // EPI_PATCH: tokens per image (patch rows + 1)
+    void* out;
+    long long ldo;         // elements
+};
+
+__device__ __forceinline__ float quick_gelu(float v) {
+    return __fdividef(v, 1.0f + __expf(-1.702f * v));
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+
+template <int EPI>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                 const GemmArgs g) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const uint32_t sbase = smem_u32(smem);
+    const uint32_t bar0 = sbase + OFF_BAR;
+    auto full_bar = [&](int s) { return bar0 + 8u * s; };
+    auto empty_bar = [&](int s) { return bar0 + 8u * (STAGES + s); };
+    auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * STAGES + a); };
+    auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * STAGES + ACC_STAGES + a); };
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_BAR + NUM_BARS * 8);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m_tiles = (g.M + BM - 1) / BM, n_tiles = (g.N + BN - 1) / BN;
+    const int num_tiles = m_tiles * n_tiles;
+    const int num_kb = g.K / BK;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmap_a);
+        prefetch_tmap(&tmap_b);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        for (int a = 0; a < ACC_STAGES; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), EPI_WARPS); }
+        fence_barrier_init();
+        fence_proxy_async_smem();
+    }
+    if (warp == 2) tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int m_blk = tile / n_tiles, n_blk = tile - m_blk * n_tiles;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(empty_bar(stage), phase ^ 1);
+                    mbar_arrive_expect_tx(full_bar(stage), A_STAGE_BYTES + B_STAGE_BYTES);
+                    tma_load_2d(sbase + OFF_A + stage * A_STAGE_BYTES, &tmap_a, full_bar(stage), kb * BK, m_blk * BM);
+                    tma_load_2d(sbase + OFF_B + stage * B_STAGE_BYTES, &tmap_b, full_bar(stage), kb * BK, n_blk * BN);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
+            int stage = 0; uint32_t phase = 0;
+            int as = 0; uint32_t aphase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                mbar_wait(tempty_bar(as), aphase ^ 1);          // epilogue has drained this accumulator
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + as * BN;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(full_bar(stage), phase);          // TMA bytes have landed
+                    tc_fence_after();
+                    const uint64_t da = make_kmajor_sw128_desc(sbase + OFF_A + stage * A_STAGE_BYTES);
+                    const uint64_t db = make_kmajor_sw128_desc(sbase + OFF_B + stage * B_STAGE_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k) {
+                        // +32 bytes per 16-element k-step inside the 128-byte swizzle atom
+                        umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                    }
+                    umma_commit(empty_bar(stage));              // smem slot free once these MMAs retire
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(tfull_bar(as));                     // accumulator complete
+                if (++as == ACC_STAGES) { as = 0; aphase ^= 1; }
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue =====================
+        const int e = warp - 4;
+        const int q = warp & 3;                  // TMEM lane quarter this warp may access
+        const int hh = e >> 2;                   // which 128-column half of the tile
+        uint8_t* stg = smem + OFF_EPI + e * EPI_STAGE_BYTES;
+        int as = 0; uint32_t aphase = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const int m_blk = tile / n_tiles, n_blk = tile - m_blk * n_tiles;
+            mbar_wait(tfull_bar(as), aphase);
+            tc_fence_after();
+            const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN + hh * 128;
+            const int row_base = m_blk * BM + q * 32;
+#pragma unroll 1
+            for (int ch = 0; ch < 4; ++ch) {
+                uint32_t v[32];
+                tmem_ld_32x32(trow + ch * 32, v);
+                tmem_ld_wait();
+                if (ch == 3) {                   // all TMEM reads of this tile done: hand it back
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(tempty_bar(as));
+                }
+                // transpose through smem: thread = row, 8 x 16-byte chunks, XOR-swizzled by row
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    uint4 c4 = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                    *reinterpret_cast<uint4*>(stg + lane * 128 + ((j ^ (lane & 7)) << 4)) = c4;
+                }
+                __syncwarp();
+                const int col0 = n_blk * BN + hh * 128 + ch * 32;
+                if (col0 < g.N) {
+                    if constexpr (EPI == CLIPPPO_EPI_BIAS_BF16 || EPI == CLIPPPO_EPI_BIAS_GELU_BF16) {
+                        // lane -> (row = it*8 + lane/4, 8 consecutive columns)
+                        const int j2 = lane & 3;
+                        const int gcol = col0 + j2 * 8;
+                        const float4 b0 = __ldg(reinterpret_cast<const float4*>(g.bias + gcol));
+                        const float4 b1 = __ldg(reinterpret_cast<const float4*>(g.bias + gcol + 4));
+#pragma unroll
+                        for (int it = 0; it < 4; ++it) {
+                            const int r = it * 8 + (lane >> 2);
+                            const float4 a0 = *reinterpret_cast<const float4*>(stg + r * 128 + (((2 * j2) ^ (r & 7)) << 4));
+                            const float4 a1 = *reinterpret_cast<const float4*>(stg + r * 128 + (((2 * j2 + 1) ^ (r & 7)) << 4));
+                            float o[8] = {a0.x + b0.x, a0.y + b0.y, a0.z + b0.z, a0.w + b0.w,
+                                          a1.x + b1.x, a1.y + b1.y, a1.z + b1.z, a1.w + b1.w};
+                            if constexpr (EPI == CLIPPPO_EPI_BIAS_GELU_BF16) {
+#pragma unroll
+                                for (int t = 0; t < 8; ++t) o[t] = quick_gelu(o[t]);
+                            }
+                            const int grow = row_base + r;
+                            if (grow < g.M) {
+                                uint4 pk = make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]),
+                                                      pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7]));
+                                __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(g.out) + (size_t)grow * g.ldo + gcol;
+                                *reinterpret_cast<uint4*>(dst) = pk;
+                            }
+                        }
+                    } else {
+                        // fp32 outputs: lane -> (row = it*4 + lane/8, 4 consecutive columns)
+                        const int j = lane & 7;
+                        const int gcol = col0 + j * 4;
+                        float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if constexpr (EPI == CLIPPPO_EPI_BIAS_RESID_F32) bb = __ldg(reinterpret_cast<const float4*>(g.bias + gcol));
+#pragma unroll
+                        for (int it = 0; it < 8; ++it) {
+                            const int r = it * 4 + (lane >> 3);
+                            const int grow = row_base + r;
+                            if (grow < g.M) {
+                                float4 a = *reinterpret_cast<const float4*>(stg + r * 128 + ((j ^ (r & 7)) << 4));
+                                float* outp = static_cast<float*>(g.out);
+                                if constexpr (EPI == CLIPPPO_EPI_BIAS_RESID_F32) {
+                                    float4* dst = reinterpret_cast<float4*>(outp + (size_t)grow * g.ldo + gcol);
+                                    const float4 x = *dst;
+                                    a.x = x.x + (a.x + bb.x); a.y = x.y + (a.y + bb.y);
+                                    a.z = x.z + (a.z + bb.z); a.w = x.w + (a.w + bb.w);
+                                    *dst = a;
+                                } else if constexpr (EPI == CLIPPPO_EPI_PATCH_F32) {
+                                    const int gp = g.tokens - 1;
+                                    const int img = grow / gp, p = grow - img * gp;
+                                    const float4 pe = __ldg(reinterpret_cast<const float4*>(g.pos + (size_t)(1 + p) * g.N + gcol));
+                                    a.x += pe.x; a.y += pe.y; a.z += pe.z; a.w += pe.w;
+                                    *reinterpret_cast<float4*>(outp + ((size_t)img * g.tokens + 1 + p) * g.ldo + gcol) = a;
+                                } else {
+                                    *reinterpret_cast<float4*>(outp + (size_t)grow * g.ldo + gcol) = a;
+                                }
+                            }
+                        }
+                    }
+                }
+                __syncwarp();                    // staging buffer is reused by the next chunk
+            }
+            if (++as == ACC_STAGES) { as = 0; aphase ^= 1; }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+// ---- host side ------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+            qres != cudaDriverEntryPointSuccess)
+            return nullptr;
+        fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+template <int EPI>
+int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& g, cudaStream_t stream) {
+    static bool configured = false;
+    if (!configured) {
+        CLIPPPO_CUDA_TRY(cudaFuncSetAttribute(gemm_bf16_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        configured = true;
+    }
+    const int m_tiles = (g.M + BM - 1) / BM, n_tiles = (g.N + BN - 1) / BN;
+    const int grid = min(m_tiles * n_tiles, kNumSMs);
+    gemm_bf16_kernel<EPI><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ta, tb, g);
+    CLIPPPO_CHECK_LAUNCH();
+    return CLIPPPO_OK;
+}
+
+}  // namespace
+
+int make_bf16_kmajor_tmap(CUtensorMap* map, const void* ptr, int rows, int K, long long ld_elems, int box_rows) {
+    EncodeTiledFn enc = get_encode_fn();
+    if (!enc) { last_cuda_error_ref() = static_cast<int>(cudaErrorNotSupported); return CLIPPPO_ERR_CUDA; }
+    if ((reinterpret_cast<uintptr_t>(ptr) & 15) || ((ld_elems * 2) & 15)) return CLIPPPO_ERR_ALIGN;
+    cuuint64_t dims[2] = {static_cast<cuuint64_t>(K), static_cast<cuuint64_t>(rows)};
+    cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld_elems) * 2};
+    cuuint32_t box[2] = {static_cast<cuuint32_t>(BK), static_cast<cuuint32_t>(box_rows)};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { last_cuda_error_ref() = 10000 + static_cast<int>(r); return CLIPPPO_ERR_CUDA; }
+    return CLIPPPO_OK;
+}
+
+int gemm_a_box_rows() { return BM; }
+int gemm_b_box_rows() { return BN; }
+
+int gemm_bf16_launch(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, int epilogue,
+                     const float* bias, const float* pos, int tokens, void* out, long long ldo, cudaStream_t stream) {
+    if (M <= 0 || N <= 0 || K <= 0 || (K % BK) || (N % 32)) return CLIPPPO_ERR_BAD_SHAPE;
+    if (!out) return CLIPPPO_ERR_NULL;
+    GemmArgs g{M, N, K, bias, pos, tokens, out, ldo};
+    const bool bf16_out = epilogue == CLIPPPO_EPI_BIAS_BF16 || epilogue == CLIPPPO_EPI_BIAS_GELU_BF16;
+    if ((reinterpret_cast<uintptr_t>(out) & 15) || ((ldo * (bf16_out ? 2 : 4)) & 15)) return CLIPPPO_ERR_ALIGN;
+    switch (epilogue) {
+        case CLIPPPO_EPI_BIAS_BF16:
+            if (!bias) return CLIPPPO_ERR_NULL;
+            return launch_gemm<CLIPPPO_EPI_BIAS_BF16>(ta, tb, g, stream);
+        case CLIPPPO_EPI_BIAS_GELU_BF16:
+            if (!bias) return CLIPPPO_ERR_NULL;
+            return launch_gemm<CLIPPPO_EPI_BIAS_GELU_BF16>(ta, tb, g, stream);
+        case CLIPPPO_EPI_BIAS_RESID_F32:
+            if (!bias) return CLIPPPO_ERR_NULL;
+            return launch_gemm<CLIPPPO_EPI_BIAS_RESID_F32>(ta, tb, g, stream);
+        case CLIPPPO_EPI_PATCH_F32:
+            if (!pos || tokens < 2) return CLIPPPO_ERR_NULL;
+            return launch_gemm<CLIPPPO_EPI_PATCH_F32>(ta, tb, g, stream);
+        case CLIPPPO_EPI_F32:
+            return launch_gemm<CLIPPPO_EPI_F32>(ta, tb, g, stream);
+    }
+    return CLIPPPO_ERR_UNSUPPORTED;
+}
+
+}  // namespace clipppo
+
+using namespace clipppo;
+
+extern "C" int clipppo_gemm_bf16(const void* a_bf16, const void* w_bf16, int M, int N, int K, int epilogue,
+                                 const float* bias, const float* pos, int tokens, void* out, int64_t ldo,
+                                 clipppo_stream_t stream) {
+    if (!a_bf16 || !w_bf16) return CLIPPPO_ERR_NULL;
+    if (M <= 0 || N <= 0 || K <= 0 || (K % 64)) return CLIPPPO_ERR_BAD_SHAPE;
+    CUtensorMap ta, tb;
+    int st = make_bf16_kmajor_tmap(&ta, a_bf16, M, K, K, gemm_a_box_rows());
+    if (st) return st;
+    st = make_bf16_kmajor_tmap(&tb, w_bf16, N, K, K, gemm_b_box_rows());
+    if (st) return st;
+    return gemm_bf16_launch(ta, tb, M, N, K, epilogue, bias, pos, tokens, out, ldo, as_stream(stream));
+}

@@ -1,0 +1,147 @@
+// V0 - CLIP image preprocessing fused with im2col:  raw frames -> bf16 patch matrix.
+//
+// Replaces, in one pass, what reference shared/clip_ppo_utils.py:146-159 (and :201-210) does in
+// four eager ops plus the fp16 cast and the unfold inside conv1:
+//     u = raw * pre_scale ; bilinear resize to image x image (align_corners=False; antialias is
+//     a no-op when up-sampling) ; (u - mean_c) / std_c ; cast ;
+//     A[b*G*G + gy*G + gx, c*P*P + ky*P + kx] = pixel(b, c, gy*P+ky, gx*P+kx)
+// so the 224x224 fp32 intermediate (79 GB at the Atari config) is never materialised.
+// C == 1 inputs (Atari gray frames) are broadcast to the three channels in registers.
+#include "common.cuh"
+#include "gemm.cuh"
+
+namespace clipppo {
+
+namespace {
+
+struct PreParams {
+    const void* img;
+    long long s[4];
+    int N, C, h, w;
+    int dtype;
+    float pre_scale;
+    int normalize;
+    int P, G, image, kpad;
+    float scale_h, scale_w;
+    __nv_bfloat16* out;
+};
+
+__constant__ float kClipMean[3] = {0.48145466f, 0.4578275f, 0.40821073f};
+__constant__ float kClipStd[3] = {0.26862954f, 0.26130258f, 0.27577711f};
+
+__device__ __forceinline__ float load_px(const PreParams& p, long long off) {
+    const float raw = (p.dtype == CLIPPPO_IMG_U8) ? static_cast<float>(static_cast<const uint8_t*>(p.img)[off])
+                                                  : static_cast<const float*>(p.img)[off];
+    return raw * p.pre_scale;
+}
+
+// ATen area_pixel_compute_source_index + guard_index_and_lambda (align_corners = false)
+__device__ __forceinline__ void src_index(float scale, int dst, int in_size, int& i0, int& i1, float& l1) {
+    float s = scale * (static_cast<float>(dst) + 0.5f) - 0.5f;
+    s = fmaxf(s, 0.0f);
+    i0 = min(static_cast<int>(s), in_size - 1);
+    i1 = i0 + ((i0 + 1 < in_size) ? 1 : 0);
+    l1 = fminf(fmaxf(s - static_cast<float>(i0), 0.0f), 1.0f);
+}
+
+// grid: (N * G) CTAs, one per (image, patch row gy); each thread produces VEC consecutive kx.
+template <int VEC>
+__global__ void __launch_bounds__(256) preprocess_kernel(const PreParams p) {
+    const int b = blockIdx.x / p.G, gy = blockIdx.x - b * p.G;
+    const int P = p.P, G = p.G;
+    const int vec_per_row = P / VEC;                       // vectors per (c, ky) line of one patch
+    const int per_patch = 3 * P * vec_per_row;
+    const int total = G * per_patch;
+    const long long img_off = static_cast<long long>(b) * p.s[0];
+    for (int i = threadIdx.x; i < total; i += blockDim.x) {
+        const int gx = i / per_patch;
+        int rem = i - gx * per_patch;
+        const int c = rem / (P * vec_per_row);
+        rem -= c * (P * vec_per_row);
+        const int ky = rem / vec_per_row;
+        const int kx0 = (rem - ky * vec_per_row) * VEC;
+        const int oy = gy * P + ky;
+        int y0, y1; float ly;
+        src_index(p.scale_h, oy, p.h, y0, y1, ly);
+        const int cin = (p.C == 1) ? 0 : c;
+        const long long base0 = img_off + cin * p.s[1] + static_cast<long long>(y0) * p.s[2];
+        const long long base1 = img_off + cin * p.s[1] + static_cast<long long>(y1) * p.s[2];
+        const float mean = p.normalize ? kClipMean[c] : 0.0f, stdv = p.normalize ? kClipStd[c] : 1.0f;
+        float o[VEC];
+#pragma unroll
+        for (int t = 0; t < VEC; ++t) {
+            const int ox = gx * P + kx0 + t;
+            int x0, x1; float lx;
+            src_index(p.scale_w, ox, p.w, x0, x1, lx);
+            const float p00 = load_px(p, base0 + x0 * p.s[3]), p01 = load_px(p, base0 + x1 * p.s[3]);
+            const float p10 = load_px(p, base1 + x0 * p.s[3]), p11 = load_px(p, base1 + x1 * p.s[3]);
+            const float v = (1.0f - ly) * ((1.0f - lx) * p00 + lx * p01) + ly * ((1.0f - lx) * p10 + lx * p11);
+            o[t] = (v - mean) / stdv;
+        }
+        __nv_bfloat16* dst = p.out + (static_cast<size_t>(b) * G * G + gy * G + gx) * p.kpad + (c * P + ky) * P + kx0;
+        if constexpr (VEC == 8) {
+            uint4 pk;
+            __nv_bfloat162 h0 = __floats2bfloat162_rn(o[0], o[1]), h1 = __floats2bfloat162_rn(o[2], o[3]);
+            __nv_bfloat162 h2 = __floats2bfloat162_rn(o[4], o[5]), h3 = __floats2bfloat162_rn(o[6], o[7]);
+            pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
+            pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
+            *reinterpret_cast<uint4*>(dst) = pk;
+        } else {
+#pragma unroll
+            for (int t = 0; t < VEC; t += 2) *reinterpret_cast<__nv_bfloat162*>(dst + t) = __floats2bfloat162_rn(o[t], o[t + 1]);
+        }
+    }
+    // zero the K padding (only when 3*P*P is not a multiple of 64, e.g. patch 14)
+    const int kreal = 3 * P * P;
+    if (p.kpad > kreal) {
+        const int padn = p.kpad - kreal;
+        for (int i = threadIdx.x; i < G * padn; i += blockDim.x) {
+            const int gx = i / padn, t = i - gx * padn;
+            p.out[(static_cast<size_t>(b) * G * G + gy * G + gx) * p.kpad + kreal + t] = __float2bfloat16(0.0f);
+        }
+    }
+}
+
+}  // namespace
+
+int preprocess_launch(const void* images, int img_dtype, const long long strides[4], int N, int C, int h, int w,
+                      float pre_scale, int normalize, int patch, int image, int kpad, void* patches_bf16,
+                      cudaStream_t stream) {
+    if (!images || !patches_bf16) return CLIPPPO_ERR_NULL;
+    if (N <= 0 || h <= 0 || w <= 0 || patch <= 0 || image <= 0 || image % patch) return CLIPPPO_ERR_BAD_SHAPE;
+    if (C != 1 && C != 3) return CLIPPPO_ERR_BAD_CHANNELS;
+    if (img_dtype != CLIPPPO_IMG_F32 && img_dtype != CLIPPPO_IMG_U8) return CLIPPPO_ERR_UNSUPPORTED;
+    if (h > image || w > image) return CLIPPPO_ERR_UNSUPPORTED;   // down-sampling needs the antialias filter
+    if (patch % 2 || kpad < 3 * patch * patch || (kpad % 8)) return CLIPPPO_ERR_UNSUPPORTED;
+    PreParams p;
+    p.img = images;
+    for (int i = 0; i < 4; ++i) p.s[i] = strides[i];
+    p.N = N; p.C = C; p.h = h; p.w = w; p.dtype = img_dtype; p.pre_scale = pre_scale; p.normalize = normalize;
+    p.P = patch; p.G = image / patch; p.image = image; p.kpad = kpad;
+    p.scale_h = static_cast<float>(h) / static_cast<float>(image);
+    p.scale_w = static_cast<float>(w) / static_cast<float>(image);
+    p.out = static_cast<__nv_bfloat16*>(patches_bf16);
+    const unsigned grid = static_cast<unsigned>(N) * p.G;
+    if (patch % 8 == 0 && (reinterpret_cast<uintptr_t>(patches_bf16) % 16 == 0))
+        preprocess_kernel<8><<<grid, 256, 0, stream>>>(p);
+    else
+        preprocess_kernel<2><<<grid, 256, 0, stream>>>(p);
+    CLIPPPO_CHECK_LAUNCH();
+    return CLIPPPO_OK;
+}
+
+}  // namespace clipppo
+
+using namespace clipppo;
+
+extern "C" int clipppo_preprocess_bf16(const void* images, int img_dtype, const int64_t img_strides_host[4],
+                                       int N, int C, int h, int w, float pre_scale, int normalize,
+                                       int patch, int image, void* patches_bf16, clipppo_stream_t stream) {
+    if (N <= 0 || C <= 0 || h <= 0 || w <= 0) return CLIPPPO_ERR_BAD_SHAPE;
+    long long s[4] = {static_cast<long long>(C) * h * w, static_cast<long long>(h) * w, w, 1};
+    if (img_strides_host) for (int i = 0; i < 4; ++i) s[i] = img_strides_host[i];
+    const int kreal = 3 * patch * patch;
+    const int kpad = (kreal + 63) / 64 * 64;
+    return preprocess_launch(images, img_dtype, s, N, C, h, w, pre_scale, normalize, patch, image, kpad, patches_bf16,
+                             as_stream(stream));
+}

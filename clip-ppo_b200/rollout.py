@@ -1,0 +1,79 @@
+"""The hot-path fragments of the reference TRAINING SCRIPTS, as functions over the B200 kernels.
+
+The scripts themselves (env stepping, logging, checkpoints) are out of scope; these
+are the statements of theirs that sit on the observation path,
+each with the reference line range it stands for, so the scripts can call them in place.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional, Tuple
+
+import torch
+
+from . import _native as N
+from . import disturb as D
+from . import losses as L
+
+
+# ---- a10: MiniGrid env-step disturbance (clip_ppo_minigrid.py:381-388) -----------------------------
+def disturb_minigrid_obs(disturber, next_obs: torch.Tensor) -> torch.Tensor:
+    """next_obs [E,H,W,C] (fp32 holding 0..255, or uint8) -> disturbed uint8 [E,H,W,C].
+    Equals ``(disturber.apply_disturbances((next_obs.float()/255).permute(0,3,1,2)).permute(0,2,3,1)*255).byte()``
+    with the same RNG consumption, in one launch (no NCHW round trip, no fp32 intermediate)."""
+    if next_obs.dim() != 4:
+        raise ValueError(f"expected [E,H,W,C], got {tuple(next_obs.shape)}")
+    E, H, W, C = next_obs.shape
+    like = next_obs if next_obs.dtype == torch.float32 and next_obs.is_contiguous() else \
+        torch.empty((E, H, W, C), dtype=torch.float32, device=next_obs.device)
+    noise = torch.randn_like(like.permute(0, 3, 1, 2))           # NHWC strides, like the reference's view
+    c = disturber._draw_contrast()
+    taps = disturber._draw_blur_taps()
+    window = disturber._draw_cutout(H, W, None)
+    return D.fused_disturb_nhwc_u8(next_obs, stages=N.STAGE_ALL, noise=noise, noise_sigma=disturber.gaussian_noise_sigma,
+                                   contrast=c, taps=taps, window=window)
+
+
+# ---- a11: Atari env-step disturbance (clip_ppo_atari.py:568-584) -----------------------------------
+def disturb_atari_stack(disturber, next_obs: torch.Tensor) -> torch.Tensor:
+    """next_obs [E,4,H,W] fp32 0..255 -> disturbed fp32 [E,4,H,W] (non-integer, x255), each stacked
+    frame disturbed as its own [E,1,H,W] call with its own draws, in the reference's order."""
+    x = next_obs.float() / 255.0
+    frames = [disturber.apply_disturbances(x[:, f:f + 1]) for f in range(x.shape[1])]
+    return torch.cat(frames, dim=1) * 255.0
+
+
+# ---- a17: Atari frame stack -> CLIP embeddings (clip_ppo_atari.py:249-299, 661) --------------------
+def convert_atari_frames_for_clip(obs_batch: torch.Tensor) -> torch.Tensor:
+    """[B,4,84,84] gray -> [B,4,3,84,84] by channel repeat (reference :249-269).  Returned as an
+    expanded VIEW (no copy): the tower broadcasts a gray plane to RGB in registers."""
+    B, F, H, W = obs_batch.shape
+    return obs_batch.unsqueeze(2).expand(B, F, 3, H, W)
+
+
+def process_multiframe_clip_embeddings(rgb_frames: torch.Tensor, clip_model, ablation_mode, modality: str,
+                                       batch_size: int, device) -> torch.Tensor:
+    """[B,F,3,h,w] -> [B, F*512]: all B*F frames through the tower in one call (reference :272-299)."""
+    import shared.clip_ppo_utils as U
+    B, F = rgb_frames.shape[0], rgb_frames.shape[1]
+    if rgb_frames.stride(2) == 0:                       # expanded gray view: feed the single plane, C = 1
+        frames = rgb_frames[:, :, 0].reshape(B * F, 1, *rgb_frames.shape[-2:])
+    else:
+        frames = rgb_frames.reshape(B * F, *rgb_frames.shape[2:])
+    e = U.generate_clip_embeddings(ablation_mode, clip_model, modality=modality, batch_size=B * F, device=device,
+                                   images=frames)
+    return e.reshape(B, F * e.shape[-1])
+
+
+# ---- a21: GAE (clip_ppo_minigrid.py:437-450 = clip_ppo_atari.py:619-632) ---------------------------
+def compute_gae(rewards: torch.Tensor, values: torch.Tensor, dones: torch.Tensor, next_value: torch.Tensor,
+                next_done: torch.Tensor, gamma: float = 0.99, gae_lambda: float = 0.95) -> Tuple[torch.Tensor, torch.Tensor]:
+    return L.gae(rewards, values, dones, next_value, next_done, gamma, gae_lambda)
+
+
+# ---- a22: PPO minibatch loss (clip_ppo_minigrid.py:498-531,559) ------------------------------------
+def ppo_minibatch_loss(newlogprob, entropy, newvalue, old_logprob, advantages, returns, old_values,
+                       clip_loss: Optional[torch.Tensor] = None, clip_lambda: float = 0.0, clip_coef: float = 0.1,
+                       ent_coef: float = 0.01, vf_coef: float = 0.5, norm_adv: bool = True,
+                       clip_vloss: bool = True) -> Dict[str, torch.Tensor]:
+    return L.ppo_loss(newlogprob, entropy, newvalue, old_logprob, advantages, returns, old_values, clip_loss,
+                      clip_lambda, clip_coef, ent_coef, vf_coef, norm_adv, clip_vloss)

@@ -1,0 +1,199 @@
+/*
+ * clipppo_b200.h - C ABI of the B200-native CLIP-PPO observation path.
+ *
+ * One shared library (libclipppo_b200.so, sm_100a only).  Plain pointers and sizes, no
+ * torch types.  Every entry point is asynchronous on the caller's stream, never allocates
+ * or frees device memory (the caller owns all buffers including workspaces) and returns
+ * 0 on success or a negative clipppo_status.  Pointers are DEVICE pointers unless the
+ * parameter name ends in _host.
+ *
+ * Each function cites the reference interface it replaces
+ * (paths relative to AlexanderBurkhart/CLIP-PPO).
+ */
+#ifndef CLIPPPO_B200_H_
+#define CLIPPPO_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CLIPPPO_ABI_VERSION 1
+
+typedef enum clipppo_status {
+    CLIPPPO_OK = 0,
+    CLIPPPO_ERR_BAD_SHAPE = -1,      /* non-positive dims, k even, window outside image ...     */
+    CLIPPPO_ERR_BAD_CHANNELS = -2,   /* contrast needs C in {1,3} (torchvision raises TypeError) */
+    CLIPPPO_ERR_BAD_PAD = -3,        /* reflect pad needs k/2 < min(H,W)                         */
+    CLIPPPO_ERR_NULL = -4,           /* required pointer is NULL                                 */
+    CLIPPPO_ERR_WORKSPACE = -5,      /* workspace too small                                      */
+    CLIPPPO_ERR_UNSUPPORTED = -6,    /* config outside what the kernels were built for           */
+    CLIPPPO_ERR_ALIGN = -7,          /* pointer / stride alignment requirement not met           */
+    CLIPPPO_ERR_CUDA = -8,           /* a CUDA runtime / driver call failed (see last_cuda_error) */
+    CLIPPPO_ERR_DIM_MISMATCH = -9    /* latent vs embedding width (reference raises ValueError)  */
+} clipppo_status;
+
+typedef void* clipppo_stream_t;      /* a cudaStream_t */
+
+int         clipppo_abi_version(void);
+const char* clipppo_strerror(int status);
+/* cudaError_t of the most recent CLIPPPO_ERR_CUDA on this thread (0 if none). */
+int         clipppo_last_cuda_error(void);
+
+/* ------------------------------------------------------------------------------------------
+ * D1  fused visual disturbance: noise -> contrast -> blur -> cutout in ONE launch.
+ * Replaces DisturbanceWrapperGPU.apply_disturbances and its four stage methods
+ * (shared/disturbances_gpu.py:66-73, 97-99, 117-119, 137-139, 157-172).
+ *
+ *   x, noise : fp32 [B,C,H,W] with arbitrary element strides (the MiniGrid call site passes an
+ *              NHWC-strided view, minigrid_experiments/clip_ppo/clip_ppo_minigrid.py:385).
+ *              noise may be NULL iff CLIPPPO_STAGE_NOISE is not in `stages`.
+ *   out      : fp32 [B,C,H,W] contiguous.
+ *   stages   : bit mask of CLIPPPO_STAGE_*; stages always run in the reference's fixed order.
+ *   contrast : the per-call factor c (one for the batch); the gray mean is per image.
+ *   k1d_host : HOST pointer to the k normalised 1-D Gaussian taps (k odd, <= 15).
+ *   sh,sw,ph,pw : cutout window (same for every image and channel).
+ * ---------------------------------------------------------------------------------------- */
+#define CLIPPPO_STAGE_NOISE    1
+#define CLIPPPO_STAGE_CONTRAST 2
+#define CLIPPPO_STAGE_BLUR     4
+#define CLIPPPO_STAGE_CUTOUT   8
+#define CLIPPPO_STAGE_ALL      15
+#define CLIPPPO_MAX_BLUR_TAPS  15
+
+int clipppo_disturb_f32(const float* x, const int64_t x_strides_host[4],
+                        const float* noise, const int64_t noise_strides_host[4],
+                        float* out, int B, int C, int H, int W, int stages,
+                        float noise_sigma, float contrast,
+                        const float* k1d_host, int k,
+                        int sh, int sw, int ph, int pw,
+                        clipppo_stream_t stream);
+
+/* Same chain for the MiniGrid env-step call site (clip_ppo_minigrid.py:381-388) and the *_numpy
+ * shims (shared/disturbances_gpu.py:75-95): NHWC frames in (uint8, or fp32 holding 0..255),
+ * `/255`, disturb, `*255`, truncate to uint8 NHWC.  noise is fp32, logical [B,C,H,W] with the
+ * given element strides (randn_like of an NHWC view keeps NHWC strides). */
+int clipppo_disturb_nhwc_u8(const void* obs, int obs_is_f32,
+                            const float* noise, const int64_t noise_strides_host[4],
+                            uint8_t* out_nhwc, int B, int H, int W, int C, int stages,
+                            float noise_sigma, float contrast, const float* k1d_host, int k,
+                            int sh, int sw, int ph, int pw, clipppo_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * L1  cosine alignment loss, forward and backward.
+ * Replaces compute_cosine_embedding_loss (shared/clip_ppo_utils.py:48-76) and its autograd.
+ *   z, c      : fp32 [rows, dim] contiguous.   loss: fp32 scalar.
+ *   row_stats : fp32 [rows,3] scratch written by fwd (|z|, |c|, cos) and read by bwd.
+ *   grad_z / grad_c may be NULL to skip that side.  grad_loss is a DEVICE scalar.
+ * ---------------------------------------------------------------------------------------- */
+int clipppo_cosine_loss_fwd(const float* z, const float* c, int rows, int dim,
+                            float* loss, float* row_stats, clipppo_stream_t stream);
+int clipppo_cosine_loss_bwd(const float* z, const float* c, const float* row_stats,
+                            const float* grad_loss, int rows, int dim,
+                            float* grad_z, float* grad_c, clipppo_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * G1  generalised advantage estimation, one launch for the whole [T,E] rollout.
+ * Replaces the 128-step Python loop at clip_ppo_minigrid.py:437-450 / clip_ppo_atari.py:619-632.
+ * gamma / gae_lambda are doubles because the reference rounds (gamma*lambda) to fp32 AFTER the
+ * double-precision product; all [T,E] arrays are fp32 contiguous, next_value / next_done are [E].
+ * ---------------------------------------------------------------------------------------- */
+int clipppo_gae_f32(const float* rewards, const float* values, const float* dones,
+                    const float* next_value, const float* next_done, int T, int E,
+                    double gamma, double gae_lambda, float* advantages, float* returns,
+                    clipppo_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * P1  PPO minibatch loss, forward (+ gradients wrt newlogprob / entropy / newvalue).
+ * Replaces clip_ppo_minigrid.py:498-531,559 (= clip_ppo_atari.py:691-720,747).
+ *   stats_out[8] = { loss, pg_loss, v_loss, entropy, old_approx_kl, approx_kl, clipfrac, adv_std }
+ *   clip_loss    : DEVICE scalar (may be NULL => 0), weighted by clip_lambda.
+ *   g_* may all be NULL for a forward-only call; otherwise they receive d loss / d input.
+ * ---------------------------------------------------------------------------------------- */
+int clipppo_ppo_loss_f32(const float* newlogprob, const float* entropy, const float* newvalue,
+                         const float* old_logprob, const float* advantages, const float* returns,
+                         const float* old_values, const float* clip_loss, int n,
+                         float clip_coef, float ent_coef, float vf_coef, float clip_lambda,
+                         int norm_adv, int clip_vloss, float* stats_out,
+                         float* g_newlogprob, float* g_entropy, float* g_newvalue,
+                         clipppo_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * V*  frozen CLIP image tower (ViT-B/32, ViT-L/14 ...), bf16 tcgen05 GEMMs, fp32 residual.
+ * Replaces clip_model.encode_image / clip.model.VisionTransformer.forward as called from
+ * generate_clip_embeddings (shared/clip_ppo_utils.py:141-164) and get_frozen_clip_features
+ * (:185-217), including their resize / normalise preprocessing and the final L2 normalise.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct clipppo_vit_config {
+    int width, layers, heads, patch, image, out_dim;
+} clipppo_vit_config;
+
+typedef struct clipppo_vit_layer {
+    const void*  w_qkv;   /* bf16 [3D, D]  (in_proj_weight)      */
+    const float* b_qkv;   /* fp32 [3D]                            */
+    const void*  w_out;   /* bf16 [D, D]   (attn.out_proj.weight) */
+    const float* b_out;   /* fp32 [D]                             */
+    const void*  w_fc;    /* bf16 [4D, D]  (mlp.c_fc.weight)      */
+    const float* b_fc;    /* fp32 [4D]                            */
+    const void*  w_proj;  /* bf16 [D, 4D]  (mlp.c_proj.weight)    */
+    const float* b_proj;  /* fp32 [D]                             */
+    const float *ln1_g, *ln1_b, *ln2_g, *ln2_b;   /* fp32 [D] */
+} clipppo_vit_layer;
+
+typedef struct clipppo_vit_weights {
+    const void*  w_patch;   /* bf16 [D, 3*P*P]   (conv1.weight flattened, K-major)   */
+    const float* cls_pos0;  /* fp32 [D]          class_embedding + positional_embedding[0] */
+    const float* pos;       /* fp32 [T, D]       positional_embedding                 */
+    const float *ln_pre_g, *ln_pre_b, *ln_post_g, *ln_post_b;   /* fp32 [D] */
+    const void*  w_head;    /* bf16 [out_dim, D] (proj transposed, K-major)           */
+    const clipppo_vit_layer* layers_host;   /* HOST array of `layers` entries          */
+} clipppo_vit_weights;
+
+typedef struct clipppo_vit_s* clipppo_vit_t;
+
+/* The handle stores pointers + TMA descriptors of the caller-owned weights; no device alloc. */
+int clipppo_vit_create(clipppo_vit_t* handle, const clipppo_vit_config* cfg,
+                       const clipppo_vit_weights* weights_host);
+int clipppo_vit_destroy(clipppo_vit_t handle);
+/* Bytes of scratch clipppo_vit_encode needs for n_images (<= the value used at encode). */
+int clipppo_vit_workspace_bytes(clipppo_vit_t handle, int n_images, size_t* bytes);
+
+#define CLIPPPO_IMG_F32 0
+#define CLIPPPO_IMG_U8  1
+#define CLIPPPO_VIT_L2NORM        1   /* L2-normalise the output rows (generate_clip_embeddings)      */
+#define CLIPPPO_VIT_PRENORMALIZED 2   /* input already (u - mean)/std: skip the normalise step        */
+/*   images : [N,C,h,w] with element strides; C == 3, or C == 1 (gray broadcast to RGB, the
+ *            Atari path clip_ppo_atari.py:249-269).  pre_scale multiplies the raw pixel before
+ *            resize (1/255 for generate_clip_embeddings, 1/255^2 for the Atari double divide,
+ *            1 for get_frozen_clip_features).
+ *   flags  : CLIPPPO_VIT_* bits.
+ *   out    : fp32 [N, out_dim].                                                            */
+int clipppo_vit_encode(clipppo_vit_t handle, const void* images, int img_dtype,
+                       const int64_t img_strides_host[4], int N, int C, int h, int w,
+                       float pre_scale, int flags, float* out,
+                       void* workspace, size_t workspace_bytes, clipppo_stream_t stream);
+
+/* Building blocks of the tower, exported for parity tests and micro-benchmarks. */
+int clipppo_preprocess_bf16(const void* images, int img_dtype, const int64_t img_strides_host[4],
+                            int N, int C, int h, int w, float pre_scale, int normalize,
+                            int patch, int image, void* patches_bf16 /* [N*G*G, 3*P*P] */, clipppo_stream_t stream);
+int clipppo_layernorm_bf16(const float* x, const float* gamma, const float* beta, int rows,
+                           int width, int64_t row_stride, void* y_bf16, clipppo_stream_t stream);
+#define CLIPPPO_EPI_BIAS_BF16       0   /* out bf16 = acc + bias                       */
+#define CLIPPPO_EPI_BIAS_GELU_BF16  1   /* out bf16 = quickgelu(acc + bias)            */
+#define CLIPPPO_EPI_BIAS_RESID_F32  2   /* out fp32 += acc + bias (in place residual)  */
+#define CLIPPPO_EPI_PATCH_F32       3   /* token rows of X = acc + pos                 */
+#define CLIPPPO_EPI_F32             4   /* out fp32 = acc                              */
+/* out[M,N] = epilogue(A[M,K] @ W[N,K]^T); A, W bf16 K-major, 16-byte aligned rows. */
+int clipppo_gemm_bf16(const void* a_bf16, const void* w_bf16, int M, int N, int K, int epilogue,
+                      const float* bias, const float* pos, int tokens, void* out, int64_t ldo,
+                      clipppo_stream_t stream);
+int clipppo_attention_bf16(const void* qkv_bf16, int n_images, int tokens, int heads, int head_dim,
+                           void* out_bf16, clipppo_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CLIPPPO_B200_H_ */

@@ -1,0 +1,59 @@
+"""The C-ABI library loads and exports every symbol include/clipppo_b200.h declares (no compute)."""
+import ctypes
+import os
+import re
+
+from conftest import ROOT
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "clipppo_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(clipppo_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_are_exported(native):
+    names = _declared_symbols()
+    assert len(names) >= 17
+    for n in names:
+        assert hasattr(native, n), f"{n} declared in the header but not exported"
+
+
+def test_binding_lists_every_header_symbol():
+    from clip_ppo_b200 import _native
+    assert sorted(_native.SYMBOLS) == _declared_symbols()
+
+
+def test_version_and_strerror(native):
+    assert native.clipppo_abi_version() == 1
+    assert native.clipppo_strerror(0) == b"ok"
+    assert b"channels" in native.clipppo_strerror(-2)
+    assert native.clipppo_strerror(-12345) == b"unknown status"
+
+
+def test_argument_validation_without_gpu(native):
+    """Entry points reject bad arguments before touching the device."""
+    i64x4 = (ctypes.c_int64 * 4)(1, 1, 1, 1)
+    taps = (ctypes.c_float * 3)(0.25, 0.5, 0.25)
+    # null image pointer
+    assert native.clipppo_disturb_f32(None, i64x4, None, i64x4, None, 1, 3, 8, 8, 15, 0.1, 1.0, taps, 3, 0, 0, 2, 2, None) == -4
+    # non-positive shape
+    assert native.clipppo_disturb_f32(None, i64x4, None, i64x4, None, 0, 3, 8, 8, 15, 0.1, 1.0, taps, 3, 0, 0, 2, 2, None) == -1
+    assert native.clipppo_gae_f32(None, None, None, None, None, 4, 4, 0.99, 0.95, None, None, None) == -4
+    assert native.clipppo_cosine_loss_fwd(None, None, 4, 512, None, None, None) == -4
+    assert native.clipppo_gemm_bf16(None, None, 128, 256, 64, 0, None, None, 0, None, 256, None) == -4
+
+
+def test_library_is_sm100a_native():
+    """The shipped code object targets sm_100a and contains the tcgen05 / TMA instructions."""
+    import shutil
+    import subprocess
+    from clip_ppo_b200 import _native
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        import pytest
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run([cuobjdump, "-sass", _native.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in sass
+    for mnemonic in ("UTCHMMA", "UTMALDG", "LDTM"):
+        assert mnemonic in sass, f"{mnemonic} missing from SASS"

@@ -1,0 +1,185 @@
+"""Parity of the fused disturbance kernel (through the C ABI) with the reference goldens and the
+oracle.  Tolerance: 1e-5 absolute (BASELINE.json north_star)."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import disturb as od
+
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+FILES = sorted(glob.glob(os.path.join(GOLDEN, "disturb_*.npz")))
+
+
+def _wrapper(sev):
+    from shared.disturbances_gpu import DisturbanceWrapperGPU
+    from shared.disturbance_types import DisturbanceSeverity
+    return DisturbanceWrapperGPU(device="cuda", severity=DisturbanceSeverity[sev])
+
+
+def _case(path):
+    g = np.load(path)
+    u8 = torch.from_numpy(g["u8"]).cuda()
+    x = (u8.float() / 255.0).permute(0, 3, 1, 2)
+    if str(g["layout"]) != "nhwc_view":
+        x = x.contiguous()
+    return g, x
+
+
+@pytest.mark.parametrize("path", FILES, ids=[os.path.basename(p)[:-4] for p in FILES])
+def test_chain_matches_reference_golden(native, path):
+    g, x = _case(path)
+    w = _wrapper(str(g["severity"]))
+    noise = torch.from_numpy(g["noise"]).cuda()
+    if str(g["layout"]) == "nhwc_view":                   # randn_like of the view keeps its strides
+        noise = noise.permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2)
+    out = w.apply_disturbances(x, noise=noise, contrast_factor=float(g["c"]), cutout_start=(int(g["sh"]), int(g["sw"])))
+    assert out.shape == x.shape and out.is_contiguous() and out.dtype == torch.float32
+    err = (out.cpu() - torch.from_numpy(g["out"])).abs().max().item()
+    assert err <= TOL, err
+    sh, sw, ph, pw = int(g["sh"]), int(g["sw"]), int(g["ph"]), int(g["pw"])
+    assert out[:, :, sh:sh + ph, sw:sw + pw].abs().max().item() == 0.0
+
+
+@pytest.mark.parametrize("path", FILES[2:4] + FILES[8:], ids=["rgb", "gray", "nhwc", "224", "ragged"])
+def test_each_stage_matches_oracle(native, path):
+    g, x = _case(path)
+    sev = str(g["severity"])
+    cfg = od.SEVERITY_TABLE[sev]
+    w = _wrapper(sev)
+    xc = x.cpu()
+    noise = torch.from_numpy(g["noise"])
+    k1d = torch.from_numpy(g["k1d"])
+    a = w.apply_gaussian_noise(x, noise=noise.cuda())
+    assert torch.equal(a.cpu(), od.add_noise(xc, noise, cfg["noise_sigma"]))          # bit-exact stage
+    b = w.apply_contrast_jitter(x, contrast_factor=float(g["c"]))
+    assert (b.cpu() - od.contrast(xc, float(g["c"]))).abs().max() <= TOL
+    c = w.apply_gaussian_blur(x)
+    assert (c.cpu() - od.blur(xc, k1d)).abs().max() <= TOL
+    d = w.apply_cutout(x, cutout_start=(int(g["sh"]), int(g["sw"])))
+    assert torch.equal(d.cpu(), od.cutout(xc, int(g["sh"]), int(g["sw"]), int(g["ph"]), int(g["pw"])))
+
+
+def test_seeded_call_consumes_rng_like_the_reference(native):
+    """Same seed => same contrast factor / window as the CPU reference stream, and the noise is
+    exactly torch.randn_like(obs) from the device generator."""
+    from shared.disturbances_gpu import DisturbanceWrapperGPU
+    from shared.disturbance_types import DisturbanceSeverity
+    x = torch.rand(4, 3, 84, 84, device="cuda")
+    w = DisturbanceWrapperGPU(device="cuda", seed=77, severity=DisturbanceSeverity.MODERATE)
+    out = w.apply_disturbances(x)
+    torch.manual_seed(77)
+    r = od.draw_call_randomness(x, od.SEVERITY_TABLE["MODERATE"])       # randn_like on the CUDA generator
+    k1d = od.gaussian_kernel1d(r["k"], r["sigma_b"])
+    ref = od.disturb(x.cpu(), r["noise"].cpu(), 0.12, r["c"], k1d, r["sh"], r["sw"], r["ph"], r["pw"])
+    assert (out.cpu() - ref).abs().max() <= TOL
+    # and twice the same seed => identical result
+    w2 = DisturbanceWrapperGPU(device="cuda", seed=77, severity=DisturbanceSeverity.MODERATE)
+    assert torch.equal(out, w2.apply_disturbances(x))
+
+
+@pytest.mark.parametrize("shape,sev", [((64, 3, 84, 84), "MODERATE"), ((256, 1, 84, 84), "HARD"),
+                                       ((9, 3, 224, 224), "SEVERE"), ((5, 3, 50, 70), "MILD"),
+                                       ((3, 1, 17, 23), "SEVERE"), ((2, 3, 224, 224), "MILD")])
+def test_random_shapes_against_oracle(native, shape, sev):
+    g = torch.Generator().manual_seed(hash((shape, sev)) % 2**31)
+    x = torch.rand(shape, generator=g)
+    noise = torch.randn(shape, generator=g)
+    cfg = od.SEVERITY_TABLE[sev]
+    H, W = shape[-2:]
+    ph, pw = od.cutout_patch(H, W, cfg["cutout"])
+    sh, sw = (H - ph) // 3, (W - pw) // 2
+    c = 0.5 * (cfg["contrast"][0] + cfg["contrast"][1]) + 0.07
+    w = _wrapper(sev)
+    out = w.apply_disturbances(x.cuda(), noise=noise.cuda(), contrast_factor=c, cutout_start=(sh, sw))
+    k = od.blur_kernel_size(cfg["blur_sigma"])
+    sigma32 = float(torch.tensor(cfg["blur_sigma"], dtype=torch.float32))
+    ref = od.disturb(x, noise, cfg["noise_sigma"], c, od.gaussian_kernel1d(k, sigma32), sh, sw, ph, pw)
+    assert (out.cpu() - ref).abs().max() <= TOL
+
+
+def test_full_size_batch_properties(native):
+    """BASELINE config sizes (4096 x 3 x 224 x 224 is 2.4 GB): size-independent properties plus an
+    oracle comparison on a slice of the batch."""
+    B = 1024
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x = torch.rand(B, 3, 224, 224, device="cuda", generator=g)
+    noise = torch.randn(B, 3, 224, 224, device="cuda", generator=g)
+    w = _wrapper("SEVERE")
+    out = w.apply_disturbances(x, noise=noise, contrast_factor=1.23, cutout_start=(30, 60))
+    assert out.min().item() >= 0.0 and out.max().item() <= 1.0 + 1e-6
+    assert out[:, :, 30:30 + 112, 60:60 + 112].abs().max().item() == 0.0
+    # per-image independence: a slice processed alone gives the same answer
+    idx = torch.tensor([0, 511, 1023], device="cuda")
+    sub = w.apply_disturbances(x[idx], noise=noise[idx], contrast_factor=1.23, cutout_start=(30, 60))
+    assert torch.equal(sub, out[idx])
+    k1d = od.gaussian_kernel1d(7, 3.0)
+    ref = od.disturb(x[idx].cpu(), noise[idx].cpu(), 0.26, 1.23, k1d, 30, 60, 112, 112)
+    assert (sub.cpu() - ref).abs().max() <= TOL
+    # linearity of the blur stage: blur(a + b) == blur(a) + blur(b)
+    a, b = x[:8] * 0.5, noise[:8].abs().clamp(0, 0.5)
+    lhs = w.apply_gaussian_blur(a + b)
+    rhs = w.apply_gaussian_blur(a) + w.apply_gaussian_blur(b)
+    assert (lhs - rhs).abs().max() <= 1e-6
+
+
+def test_numpy_shims_and_minigrid_call_site(native):
+    from clip_ppo_b200 import rollout
+    w = _wrapper("MODERATE")
+    rng = np.random.RandomState(0)
+    img = rng.randint(0, 256, (84, 84, 3), dtype=np.uint8)
+    batch = rng.randint(0, 256, (6, 84, 84, 3), dtype=np.uint8)
+    for arr in (img, batch):
+        out = w.apply_cutout_numpy(arr)
+        assert out.shape == arr.shape and out.dtype == np.uint8
+        # cutout of uint8 frames is exact: every pixel is either untouched or zero
+        assert np.all((out == arr) | (out == 0))
+        for fn in (w.apply_disturbances_numpy, w.apply_gaussian_noise_numpy, w.apply_contrast_jitter_numpy, w.apply_gaussian_blur_numpy):
+            o = fn(arr)
+            assert o.shape == arr.shape and o.dtype == np.uint8
+    # MiniGrid env-step call site: fp32 0..255 NHWC in -> uint8 NHWC out == reference expression
+    obs = torch.from_numpy(batch).cuda().float()
+    torch.manual_seed(3)
+    got = rollout.disturb_minigrid_obs(w, obs)
+    torch.manual_seed(3)
+    chw = (obs / 255.0).permute(0, 3, 1, 2)
+    r = od.draw_call_randomness(chw, od.SEVERITY_TABLE["MODERATE"])
+    ref = od.disturb(chw.cpu(), r["noise"].cpu(), 0.12, r["c"], od.gaussian_kernel1d(r["k"], r["sigma_b"]),
+                     r["sh"], r["sw"], r["ph"], r["pw"])
+    ref_u8 = (ref.permute(0, 2, 3, 1) * 255.0).byte()
+    assert got.dtype == torch.uint8 and got.shape == obs.shape
+    diff = (got.cpu().int() - ref_u8.int()).abs()
+    assert diff.max().item() <= 1 and (diff > 0).float().mean().item() < 1e-3      # floor-boundary flips only
+
+
+def test_atari_call_site(native):
+    from clip_ppo_b200 import rollout
+    w = _wrapper("HARD")
+    obs = torch.randint(0, 256, (16, 4, 84, 84), device="cuda").float()
+    torch.manual_seed(9)
+    got = rollout.disturb_atari_stack(w, obs)
+    torch.manual_seed(9)
+    frames = []
+    for f in range(4):
+        fr = (obs / 255.0)[:, f:f + 1]
+        r = od.draw_call_randomness(fr, od.SEVERITY_TABLE["HARD"])
+        frames.append(od.disturb(fr.cpu(), r["noise"].cpu(), 0.13, r["c"], od.gaussian_kernel1d(r["k"], r["sigma_b"]),
+                                 r["sh"], r["sw"], r["ph"], r["pw"]))
+    ref = torch.cat(frames, dim=1) * 255.0
+    assert got.shape == obs.shape and (got.cpu() - ref).abs().max() <= 255 * TOL
+
+
+def test_error_mapping(native):
+    w = _wrapper("MILD")
+    with pytest.raises(TypeError):
+        w.apply_contrast_jitter(torch.rand(2, 2, 16, 16, device="cuda"))
+    with pytest.raises(RuntimeError):
+        _wrapper("SEVERE").apply_gaussian_blur(torch.rand(1, 3, 3, 40, device="cuda"))       # pad 3 >= H 3
+    with pytest.raises(ValueError):
+        w.apply_disturbances(torch.rand(3, 16, 16, device="cuda"))
+    assert w.apply_disturbances(torch.rand(0, 3, 16, 16, device="cuda")).shape == (0, 3, 16, 16)

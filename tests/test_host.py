@@ -1,0 +1,115 @@
+"""Host-side logic of the drop-in surface that needs no GPU: parameter table, constructor
+contract, CPU-generator draw order, warm-up / gating scalars, loud failure without CUDA."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import disturb as od
+
+from conftest import GOLDEN
+
+
+def test_severity_table_matches_reference_rows():
+    from shared.disturbance_types import DisturbanceSeverity, SEVERITY_CONFIGS
+    assert [s.value for s in DisturbanceSeverity] == ["NONE", "MILD", "MODERATE", "HARD", "SEVERE"]
+    assert DisturbanceSeverity.NONE not in SEVERITY_CONFIGS
+    for name, row in od.SEVERITY_TABLE.items():
+        mine = SEVERITY_CONFIGS[DisturbanceSeverity[name]]
+        assert mine == dict(gaussian_noise_sigma=row["noise_sigma"], gaussian_blur_sigma=row["blur_sigma"],
+                            contrast_range=row["contrast"], cutout_ratio=row["cutout"])
+
+
+def test_wrapper_constructor_contract():
+    from shared.disturbances_gpu import DisturbanceWrapperGPU
+    from shared.disturbance_types import DisturbanceSeverity
+    w = DisturbanceWrapperGPU(device="cpu", severity=DisturbanceSeverity.HARD)
+    assert (w.gaussian_noise_sigma, w.gaussian_blur_sigma, w.contrast_range, w.cutout_ratio) == (0.13, 2.1, (0.69, 1.31), 0.18)
+    assert w.device == torch.device("cpu")
+    assert w.blur_transform.kernel_size == (5, 5) and w.noise_transform.sigma == 0.13
+    with pytest.raises(ValueError):
+        DisturbanceWrapperGPU(device="cpu", severity=None, gaussian_noise_sigma=0.1)
+    c = DisturbanceWrapperGPU(device="cpu", severity=None, gaussian_noise_sigma=0.1, gaussian_blur_sigma=3.0,
+                              contrast_range=(0.5, 1.5), cutout_ratio=0.2)
+    assert c._kernel_size == 7
+    assert DisturbanceWrapperGPU().gaussian_noise_sigma == 0.08          # default severity is MILD
+
+
+def test_seed_is_global_like_the_reference():
+    from shared.disturbances_gpu import DisturbanceWrapperGPU
+    DisturbanceWrapperGPU(device="cpu", seed=123)
+    a = torch.rand(3)
+    torch.manual_seed(123)
+    assert torch.equal(a, torch.rand(3))
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "disturb_0[0-7]*.npz"))))
+def test_cpu_generator_draw_order_matches_golden(path):
+    """After the device randn_like, the wrapper's CPU-generator draws (randperm, uniform, uniform,
+    randint, randint) must yield the reference's contrast factor, taps and cutout window."""
+    from shared.disturbances_gpu import DisturbanceWrapperGPU
+    from shared.disturbance_types import DisturbanceSeverity
+    g = np.load(path)
+    B, H, W, C = g["u8"].shape
+    w = DisturbanceWrapperGPU(device="cpu", seed=int(g["seed"]), severity=DisturbanceSeverity[str(g["severity"])])
+    torch.randn(B, C, H, W)                   # stands for randn_like(obs) on a CPU tensor
+    c = w._draw_contrast()
+    taps = w._draw_blur_taps()
+    window = w._draw_cutout(H, W, None)
+    assert c == float(g["c"])
+    assert np.array_equal(np.array(taps, dtype=np.float32), g["k1d"])
+    assert window == (int(g["sh"]), int(g["sw"]), int(g["ph"]), int(g["pw"]))
+
+
+def test_no_cpu_fallback():
+    from shared.disturbances_gpu import DisturbanceWrapperGPU, create_disturbance_wrapper
+    w = DisturbanceWrapperGPU(device="cpu")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        w.apply_disturbances(torch.rand(1, 3, 8, 8))
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError):
+            create_disturbance_wrapper(use_gpu=True)
+    import shared.clip_ppo_utils as U
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        U.compute_cosine_embedding_loss(torch.rand(2, 512), torch.rand(2, 512))
+
+
+def test_clip_utils_scalars_and_errors():
+    import shared.clip_ppo_utils as U
+    g = np.load(os.path.join(GOLDEN, "losses.npz"))
+    assert [U.get_clip_lambda_with_warmup(1e-5, i, 16) for i in range(16)] == list(g["warmup_16"])
+    assert [U.get_clip_lambda_with_warmup(3e-4, i, 100) for i in range(100)] == list(g["warmup_100"])
+    assert U.CLIP_LOSS_FREQUENCY == 4
+    assert U.should_compute_clip_loss(U.AblationMode.NONE, 1e-5)
+    assert not U.should_compute_clip_loss(U.AblationMode.NONE, 0.0)
+    assert not U.should_compute_clip_loss(U.AblationMode.FROZEN_CLIP, 1e-5)
+    assert U.should_compute_clip_loss(U.AblationMode.RANDOM_ENCODER, 1e-5)
+    with pytest.raises(ValueError, match="Dimension mismatch"):
+        U.compute_cosine_embedding_loss(torch.zeros(2, 512), torch.zeros(2, 768))
+    with pytest.raises(ValueError, match="images required"):
+        U.generate_clip_embeddings(U.AblationMode.NONE, None, "image", 2, "cpu")
+    with pytest.raises(ValueError, match="descriptions required"):
+        U.generate_clip_embeddings(U.AblationMode.NONE, None, "text", 2, "cpu")
+    with pytest.raises(ValueError, match="Invalid modality"):
+        U.generate_clip_embeddings(U.AblationMode.NONE, None, "audio", 2, "cpu")
+    e = U.generate_clip_embeddings(U.AblationMode.RANDOM_ENCODER, None, "image", 5, "cpu")
+    assert e.shape == (5, 512) and torch.allclose(e.norm(dim=-1), torch.ones(5), atol=1e-6)
+    cfg = U.ClipPPOConfig()
+    assert (cfg.clip_lambda, cfg.clip_model, cfg.clip_modality, cfg.disturbance_severity) == (1e-5, "ViT-B/32", "text", "MODERATE")
+    assert torch.allclose(U._CLIP_MEAN, torch.tensor([0.48145466, 0.4578275, 0.40821073]))
+    import clip
+    assert isinstance(clip.model.VisionTransformer, type) and isinstance(clip.model.CLIP, type)
+
+
+def test_compat_state_dict_matches_oracle_weights():
+    """The shim's seeded random weights are the oracle's (same generator stream), so GPU-vs-oracle
+    parity tests and the golden embeddings refer to the same tower."""
+    from clip_ppo_b200.clip_compat.model import random_visual_state_dict
+    from oracle import vit as ov
+    a = random_visual_state_dict("ViT-B/32", 0)
+    b = ov.random_state_dict(ov.VIT_B32, 0)
+    assert a.keys() == b.keys()
+    for k in ("visual.conv1.weight", "visual.transformer.resblocks.11.mlp.c_proj.weight", "visual.proj"):
+        assert torch.equal(a[k], b[k])

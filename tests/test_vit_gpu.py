@@ -1,0 +1,197 @@
+"""Parity of the tower and its building blocks.  bf16 operands / fp32 accumulate vs the fp32
+oracle: embeddings must reach cosine >= 0.999 (north_star); building blocks are checked against
+plain torch fp32 references of the same op on bf16-rounded inputs."""
+import ctypes
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import vit as ov
+
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (256, 512, 128), (1000, 768, 768), (6400, 2304, 768),
+                                   (6400, 768, 3072), (50, 512, 768), (12800, 3072, 768), (19000, 768, 768)])
+@pytest.mark.parametrize("epi", [0, 1, 2, 4])
+def test_gemm_epilogues_vs_torch(native, M, N, K, epi):
+    from clip_ppo_b200 import _native as Nn
+    gen = torch.Generator(device="cuda").manual_seed(M + N + K + epi)
+    a = (torch.randn(M, K, device="cuda", generator=gen) * 0.5).bfloat16()
+    w = (torch.randn(N, K, device="cuda", generator=gen) * (K ** -0.5)).bfloat16()
+    bias = torch.randn(N, device="cuda", generator=gen) * 0.1
+    acc = a.float() @ w.float().t()
+    if epi in (0, 1):
+        out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+        ref = acc + bias
+        if epi == 1:
+            ref = ref * torch.sigmoid(1.702 * ref)
+    elif epi == 2:
+        x0 = torch.randn(M, N, device="cuda", generator=gen)
+        out = x0.clone()
+        ref = x0 + acc + bias
+    else:
+        out = torch.empty(M, N, device="cuda", dtype=torch.float32)
+        ref = acc
+    st = native.clipppo_gemm_bf16(a.data_ptr(), w.data_ptr(), M, N, K, epi, bias.data_ptr(), None, 0, out.data_ptr(), N, _stream())
+    Nn.check(st)
+    torch.cuda.synchronize()
+    err = (out.float() - ref).abs().max().item()
+    tol = 2e-2 if epi in (0, 1) else 2e-3            # bf16 output rounding vs fp32 accumulate-order noise
+    assert err <= tol, err
+
+
+def test_gemm_patch_epilogue(native):
+    from clip_ppo_b200 import _native as Nn
+    n, G2, T, D, K = 5, 49, 50, 768, 3072
+    gen = torch.Generator(device="cuda").manual_seed(1)
+    a = (torch.randn(n * G2, K, device="cuda", generator=gen) * 0.5).bfloat16()
+    w = (torch.randn(D, K, device="cuda", generator=gen) * (K ** -0.5)).bfloat16()
+    pos = torch.randn(T, D, device="cuda", generator=gen)
+    X = torch.full((n * T, D), 7.0, device="cuda")
+    Nn.check(native.clipppo_gemm_bf16(a.data_ptr(), w.data_ptr(), n * G2, D, K, 3, None, pos.data_ptr(), T, X.data_ptr(), D, _stream()))
+    torch.cuda.synchronize()
+    ref = (a.float() @ w.float().t()).reshape(n, G2, D) + pos[1:]
+    Xv = X.reshape(n, T, D)
+    assert (Xv[:, 1:] - ref).abs().max().item() <= 2e-3
+    assert torch.all(Xv[:, 0] == 7.0)                # CLS rows untouched by the patch GEMM
+
+
+@pytest.mark.parametrize("rows,width", [(50, 768), (6401, 768), (257, 1024)])
+def test_layernorm_vs_torch(native, rows, width):
+    from clip_ppo_b200 import _native as Nn
+    gen = torch.Generator(device="cuda").manual_seed(rows)
+    x = torch.randn(rows, width, device="cuda", generator=gen) * 3 + 0.5
+    g = 1 + 0.1 * torch.randn(width, device="cuda", generator=gen)
+    b = 0.1 * torch.randn(width, device="cuda", generator=gen)
+    y = torch.empty(rows, width, device="cuda", dtype=torch.bfloat16)
+    Nn.check(native.clipppo_layernorm_bf16(x.data_ptr(), g.data_ptr(), b.data_ptr(), rows, width, width, y.data_ptr(), _stream()))
+    ref = torch.nn.functional.layer_norm(x, (width,), g, b, 1e-5)
+    assert (y.float() - ref).abs().max().item() <= 2e-2
+    assert (y.float() - ref.bfloat16().float()).abs().mean().item() <= 1e-4
+
+
+@pytest.mark.parametrize("n,T", [(1, 50), (37, 50), (3, 17), (2, 64)])
+def test_attention_vs_torch(native, n, T):
+    from clip_ppo_b200 import _native as Nn
+    H, dh = 12, 64
+    D = H * dh
+    gen = torch.Generator(device="cuda").manual_seed(n * 100 + T)
+    qkv = torch.randn(n * T, 3 * D, device="cuda", generator=gen).bfloat16()
+    out = torch.empty(n * T, D, device="cuda", dtype=torch.bfloat16)
+    Nn.check(native.clipppo_attention_bf16(qkv.data_ptr(), n, T, H, dh, out.data_ptr(), _stream()))
+    q, k, v = qkv.float().reshape(n, T, 3, H, dh).permute(2, 0, 3, 1, 4)
+    s = torch.softmax(q @ k.transpose(-1, -2) / math.sqrt(dh), dim=-1)
+    ref = (s @ v).permute(0, 2, 1, 3).reshape(n * T, D)
+    assert (out.float() - ref).abs().max().item() <= 3e-2
+
+
+@pytest.mark.parametrize("shape,dtype,scale", [((3, 3, 84, 84), torch.float32, 1 / 255.0), ((2, 3, 224, 224), torch.float32, 1 / 255.0),
+                                               ((2, 1, 84, 84), torch.float32, 1 / 255.0 / 255.0), ((3, 3, 84, 84), torch.uint8, 1 / 255.0),
+                                               ((2, 3, 60, 100), torch.float32, 1.0)])
+def test_preprocess_vs_oracle(native, shape, dtype, scale):
+    from clip_ppo_b200 import _native as Nn
+    gen = torch.Generator().manual_seed(sum(shape))
+    raw = torch.randint(0, 256, shape, generator=gen)
+    img = raw.to(dtype) if dtype == torch.uint8 else (raw.float() if scale != 1.0 else raw.float() / 255.0)
+    n, C, h, w = shape
+    dev = img.cuda()
+    out = torch.empty(n * 49, 3072, device="cuda", dtype=torch.bfloat16)
+    Nn.check(native.clipppo_preprocess_bf16(dev.data_ptr(), 1 if dtype == torch.uint8 else 0, Nn.strides4(dev), n, C, h, w,
+                                            scale, 1, 32, 224, out.data_ptr(), _stream()))
+    x = img.float() * scale
+    if C == 1:
+        x = x.repeat(1, 3, 1, 1)
+    ref = ov.preprocess(x, False)                                        # antialias bilinear + normalise, fp32
+    ref = ref.reshape(n, 3, 7, 32, 7, 32).permute(0, 2, 4, 1, 3, 5).reshape(n * 49, 3072)
+    err = (out.float().cpu() - ref).abs()
+    assert err.max().item() <= 2e-2 and err.mean().item() <= 3e-3        # bf16 rounding of values up to ~2.2
+
+
+def _engine(seed=0):
+    from clip_ppo_b200.clip_compat.model import random_visual_state_dict
+    from clip_ppo_b200.vit import VitEngine
+    return VitEngine(random_visual_state_dict("ViT-B/32", seed), device="cuda")
+
+
+def test_embeddings_match_reference_golden(native):
+    import shared.clip_ppo_utils as U
+    g = np.load(os.path.join(GOLDEN, "vit_b32_seed0.npz"))
+    model = U.load_clip_model("ViT-B/32", device="cuda")               # compat shim, seed-0 random weights
+    for tag in ("84", "224"):
+        img = torch.from_numpy(g[f"img{tag}"]).cuda().float()
+        emb = U.generate_clip_embeddings(U.AblationMode.NONE, model, "image", img.shape[0], "cuda", images=img)
+        ref = torch.from_numpy(g[f"emb{tag}"])
+        assert emb.shape == ref.shape and emb.dtype == torch.float32
+        cos = torch.sum(emb.cpu() * ref, dim=-1)
+        assert cos.min().item() >= 0.999, cos
+        assert torch.allclose(emb.norm(dim=-1).cpu(), torch.ones(len(ref)), atol=1e-5)
+    # Atari path: gray frames already divided by 255 once by the caller (clip_ppo_atari.py:661)
+    from clip_ppo_b200 import rollout
+    gray = torch.from_numpy(g["gray_atari"]).cuda().float()          # [3,1,84,84]
+    stack = gray.reshape(1, 3, 84, 84)                                 # pretend a 3-frame stack of one env
+    rgb = rollout.convert_atari_frames_for_clip(stack) / 255.0
+    e = rollout.process_multiframe_clip_embeddings(rgb, model, U.AblationMode.NONE, "image", 1, "cuda")
+    assert e.shape == (1, 3 * 512)
+    cos = torch.sum(e.reshape(3, 512).cpu() * torch.from_numpy(g["emb_atari"]), dim=-1)
+    assert cos.min().item() >= 0.999, cos
+
+
+@pytest.mark.parametrize("n,hw", [(1, 84), (37, 84), (130, 84), (5, 224)])
+def test_embeddings_vs_oracle(native, n, hw):
+    eng = _engine(0)
+    sd = ov.random_state_dict(ov.VIT_B32, 0)
+    gen = torch.Generator().manual_seed(n + hw)
+    img = torch.randint(0, 256, (n, 3, hw, hw), generator=gen).float()
+    emb = eng.encode(img.cuda(), pre_scale=1 / 255.0, l2norm=True).cpu()
+    m = min(n, 6)                                                     # the CPU oracle is slow: check a subset
+    idx = torch.linspace(0, n - 1, m).long()
+    ref = ov.image_embeddings(sd, img[idx])
+    cos = torch.sum(emb[idx] * ref, dim=-1)
+    assert cos.min().item() >= 0.999, cos
+    # batch-size invariance: an image encoded alone == encoded inside the batch (bitwise)
+    alone = eng.encode(img[idx[-1:]].cuda(), pre_scale=1 / 255.0, l2norm=True).cpu()
+    assert torch.equal(alone[0], emb[idx[-1]])
+
+
+def test_chunked_batch_and_uint8_input(native):
+    eng = _engine(0)
+    gen = torch.Generator().manual_seed(4)
+    u8 = torch.randint(0, 256, (600, 3, 84, 84), generator=gen, dtype=torch.uint8).cuda()     # > one 512-image chunk
+    a = eng.encode(u8, pre_scale=1 / 255.0, l2norm=True)
+    b = eng.encode(u8.float(), pre_scale=1 / 255.0, l2norm=True)
+    assert torch.equal(a, b)
+    c = eng.encode(u8[505:530], pre_scale=1 / 255.0, l2norm=True)
+    assert torch.equal(a[505:530], c)
+    assert torch.isfinite(a).all()
+
+
+def test_frozen_features_and_encode_image(native):
+    import shared.clip_ppo_utils as U
+    model = U.load_clip_model("ViT-B/32", device="cuda")
+    sd = ov.random_state_dict(ov.VIT_B32, 0)
+    gen = torch.Generator().manual_seed(8)
+    x = torch.rand(4, 3, 84, 84, generator=gen)
+    f = U.get_frozen_clip_features(x.cuda(), model.visual).cpu()       # bare VisionTransformer dispatch (:212-213)
+    f2 = U.get_frozen_clip_features(x.cuda(), model).cpu()             # full CLIP object
+    ref = ov.frozen_features(sd, x)
+    assert torch.equal(f, f2)
+    cos = torch.nn.functional.cosine_similarity(f, ref, dim=-1)
+    assert cos.min().item() >= 0.999
+    assert abs(f.norm(dim=-1).mean().item() / ref.norm(dim=-1).mean().item() - 1) < 2e-2       # not L2-normalised
+    # upstream-style encode_image on an already normalised batch
+    pre = ov.preprocess(x, False)
+    e = model.encode_image(pre.cuda()).cpu()
+    cos = torch.nn.functional.cosine_similarity(e, ov.vision_tower(sd, pre), dim=-1)
+    assert cos.min().item() >= 0.999
+    assert all(not p.requires_grad for p in model.parameters())
+    assert "conv1.weight" in model.visual.state_dict()
