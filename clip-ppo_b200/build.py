@@ -19,7 +19,7 @@ INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 BUILD = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libclipppo_b200.so")
 
-SOURCES = ["capi.cu", "disturb.cu", "losses.cu", "preprocess.cu", "layernorm.cu",
+SOURCES = ["capi.cu", "prof.cu", "disturb.cu", "losses.cu", "preprocess.cu", "layernorm.cu",
            "gemm_tcgen05.cu", "attention.cu", "vit.cu"]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

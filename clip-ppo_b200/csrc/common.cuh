@@ -6,6 +6,7 @@
 #include <stdint.h>
 
 #include "../../include/clipppo_b200.h"
+#include "prof.cuh"
 
 namespace clipppo {
 
@@ -25,7 +26,11 @@ inline int record_cuda(cudaError_t e) {
     } while (0)
 
 // Launch-error check that never synchronises.
-#define CLIPPPO_CHECK_LAUNCH() CLIPPPO_CUDA_TRY(cudaGetLastError())
+#define CLIPPPO_CHECK_LAUNCH()                        \
+    do {                                              \
+        ::clipppo::prof_count_launch();               \
+        CLIPPPO_CUDA_TRY(cudaGetLastError());         \
+    } while (0)
 
 inline cudaStream_t as_stream(clipppo_stream_t s) { return static_cast<cudaStream_t>(s); }
 

@@ -241,6 +241,7 @@ static int launch_disturb(const DisturbParams& p, size_t smem, cudaStream_t stre
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     CLIPPPO_CUDA_TRY(cudaLaunchKernelEx(&cfg, disturb_kernel<K>, p));
+    prof_count_launch();
     return CLIPPPO_OK;
 }
 

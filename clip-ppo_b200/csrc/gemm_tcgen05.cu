@@ -261,7 +261,11 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& g,
     }
     const int m_tiles = (g.M + BM - 1) / BM, n_tiles = (g.N + BN - 1) / BN;
     const int grid = min(m_tiles * n_tiles, kNumSMs);
+    void* span = nullptr;
+    const bool timed = prof_timing_enabled();
+    if (timed) prof_span_begin(stream, 2.0 * g.M * static_cast<double>(g.N) * g.K, &span);
     gemm_bf16_kernel<EPI><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ta, tb, g);
+    if (timed) prof_span_end(stream, span);
     CLIPPPO_CHECK_LAUNCH();
     return CLIPPPO_OK;
 }

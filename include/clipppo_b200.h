@@ -42,6 +42,12 @@ const char* clipppo_strerror(int status);
 /* cudaError_t of the most recent CLIPPPO_ERR_CUDA on this thread (0 if none). */
 int         clipppo_last_cuda_error(void);
 
+/* Instrumentation (bench.py): launches of this library's kernels since prof_begin; with
+ * time_gemms != 0 every tcgen05 GEMM launch is bracketed by CUDA events on its stream and
+ * prof_end returns their summed duration (ms) and algorithmic FLOPs.  Off by default. */
+int clipppo_prof_begin(int time_gemms);
+int clipppo_prof_end(long long* launches, double* gemm_ms, double* gemm_flops, long long* gemm_launches);
+
 /* ------------------------------------------------------------------------------------------
  * D1  fused visual disturbance: noise -> contrast -> blur -> cutout in ONE launch.
  * Replaces DisturbanceWrapperGPU.apply_disturbances and its four stage methods
