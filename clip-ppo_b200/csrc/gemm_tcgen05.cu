@@ -140,12 +140,30 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         int as = 0; uint32_t aphase = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
             const int m_blk = tile / n_tiles, n_blk = tile - m_blk * n_tiles;
+            const int row_base = m_blk * BM + q * 32;
+            // RESID: the fp32 residual sub-tile of chunk ch+1 is fetched while chunk ch is drained
+            // from TMEM (and chunk 0 while the MMAs of this tile are still running).
+            float4 xres[2][8];
+            auto fetch_resid = [&](float4 (&buf)[8], int ch) {
+                if constexpr (EPI == CLIPPPO_EPI_BIAS_RESID_F32) {
+                    const int gcol = n_blk * BN + hh * 128 + ch * 32 + (lane & 7) * 4;
+                    if (gcol < g.N) {
+#pragma unroll
+                        for (int it = 0; it < 8; ++it) {
+                            const int grow = row_base + it * 4 + (lane >> 3);
+                            if (grow < g.M)
+                                buf[it] = *reinterpret_cast<const float4*>(static_cast<const float*>(g.out) + (size_t)grow * g.ldo + gcol);
+                        }
+                    }
+                }
+            };
+            fetch_resid(xres[0], 0);
             mbar_wait(tfull_bar(as), aphase);
             tc_fence_after();
             const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN + hh * 128;
-            const int row_base = m_blk * BM + q * 32;
-#pragma unroll 1
+#pragma unroll
             for (int ch = 0; ch < 4; ++ch) {
+                if (ch + 1 < 4) fetch_resid(xres[(ch + 1) & 1], ch + 1);
                 uint32_t v[32];
                 tmem_ld_32x32(trow + ch * 32, v);
                 tmem_ld_wait();
@@ -202,11 +220,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                                 float4 a = *reinterpret_cast<const float4*>(stg + r * 128 + ((j ^ (r & 7)) << 4));
                                 float* outp = static_cast<float*>(g.out);
                                 if constexpr (EPI == CLIPPPO_EPI_BIAS_RESID_F32) {
-                                    float4* dst = reinterpret_cast<float4*>(outp + (size_t)grow * g.ldo + gcol);
-                                    const float4 x = *dst;
+                                    const float4 x = xres[ch & 1][it];
                                     a.x = x.x + (a.x + bb.x); a.y = x.y + (a.y + bb.y);
                                     a.z = x.z + (a.z + bb.z); a.w = x.w + (a.w + bb.w);
-                                    *dst = a;
+                                    *reinterpret_cast<float4*>(outp + (size_t)grow * g.ldo + gcol) = a;
                                 } else if constexpr (EPI == CLIPPPO_EPI_PATCH_F32) {
                                     const int gp = g.tokens - 1;
                                     const int img = grow / gp, p = grow - img * gp;
