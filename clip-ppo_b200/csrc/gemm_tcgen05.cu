@@ -4,14 +4,22 @@
 // Replaces the cuBLAS/cuDNN calls behind [clip] VisionTransformer (conv1, in_proj, out_proj,
 // c_fc, c_proj, proj) that reference shared/clip_ppo_utils.py:163 / :213-215 trigger.
 //
-// Persistent, warp-specialised, one CTA per SM:
-//   warp 0      TMA producer: A tile 128x64 and W tile 256x64 per k-block into a 4-stage smem ring
-//   warp 1      MMA issuer: one thread issues 4 x tcgen05.mma (128x256x16) per k-block; the fp32
-//               accumulator (128 lanes x 256 columns) lives in TMEM, double-buffered (2 x 256 cols)
+// Persistent and warp-specialised.  Default mode: CTA PAIRS (cluster 2x1, tcgen05 cta_group::2).
+// A pair owns a 256 x 256 output tile; each CTA stages only ITS 128 rows of A and ITS 128 rows of W
+// per k-block (32 KB instead of 48 KB), the two tensor cores exchange the W halves, and each CTA's
+// TMEM receives its own 128 x 256 half of the accumulator.  That halves the shared-memory operand
+// traffic per MMA (the limiter of the single-CTA 128x256 tile on Blackwell) and leaves room for a
+// 6-stage TMA ring.
+//   warp 0      TMA producer (both CTAs; bytes are counted on the LEADER's full barrier)
+//   warp 1      MMA issuer (leader CTA only): 4 x tcgen05.mma.cta_group::2 (256x256x16) per k-block;
+//               fp32 accumulators double-buffered in TMEM (2 x 256 columns per CTA)
 //   warp 2      TMEM allocator
-//   warps 4-11  epilogue: tcgen05.ld 32x32 sub-tiles -> swizzled smem transpose -> coalesced
-//               global access with the fused bias / QuickGELU / residual / pos-emb epilogue
-// so the epilogue of tile i overlaps the MMAs of tile i+1.
+//   warps 4-11  epilogue (both CTAs): tcgen05.ld 32x32 sub-tiles -> swizzled smem transpose ->
+//               coalesced global access with the fused bias / QuickGELU / residual / pos-emb epilogue
+// so the epilogue of tile i overlaps the MMAs of tile i+1.  MODE 1 (env CLIPPPO_GEMM_CLUSTER=1) is
+// the same kernel with one CTA per 128x256 tile and cta_group::1, kept for A/B measurements.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "tc_ptx.cuh"
 #include "gemm.cuh"
@@ -22,19 +30,25 @@ using namespace ptx;
 
 namespace {
 
-constexpr int BM = 128, BN = 256, BK = 64, UMMA_K = 16, STAGES = 4, ACC_STAGES = 2;
-constexpr int A_STAGE_BYTES = BM * BK * 2;              // 16 KB
-constexpr int B_STAGE_BYTES = BN * BK * 2;              // 32 KB
+constexpr int BM = 128, BN = 256, BK = 64, UMMA_K = 16, ACC_STAGES = 2;
 constexpr int EPI_WARPS = 8;
 constexpr int EPI_STAGE_BYTES = 32 * 32 * 4;            // one 32x32 fp32 sub-tile per warp
 constexpr int NUM_THREADS = 128 + EPI_WARPS * 32;       // 4 control warps + 8 epilogue warps
-constexpr int OFF_A = 0;
-constexpr int OFF_B = OFF_A + STAGES * A_STAGE_BYTES;
-constexpr int OFF_EPI = OFF_B + STAGES * B_STAGE_BYTES;
-constexpr int OFF_BAR = OFF_EPI + EPI_WARPS * EPI_STAGE_BYTES;
-constexpr int NUM_BARS = 2 * STAGES + 2 * ACC_STAGES;
-constexpr int SMEM_BYTES = OFF_BAR + NUM_BARS * 8 + 16 + 1024;   // + tmem slot + alignment slack
-constexpr uint32_t TMEM_COLS = ACC_STAGES * BN;          // 512: the whole TMEM of the SM
+constexpr uint32_t TMEM_COLS = ACC_STAGES * BN;         // 512: the whole TMEM of the SM
+
+template <int MODE>
+struct Cfg {
+    static constexpr int CL = MODE;                                   // CTAs per cluster
+    static constexpr int STAGES = (MODE == 2) ? 6 : 4;
+    static constexpr int A_STAGE_BYTES = BM * BK * 2;                 // 16 KB: my 128 rows of A
+    static constexpr int B_STAGE_BYTES = (MODE == 2 ? BN / 2 : BN) * BK * 2;   // 16 KB (my W half) / 32 KB
+    static constexpr int OFF_A = 0;
+    static constexpr int OFF_B = OFF_A + STAGES * A_STAGE_BYTES;
+    static constexpr int OFF_EPI = OFF_B + STAGES * B_STAGE_BYTES;
+    static constexpr int OFF_BAR = OFF_EPI + EPI_WARPS * EPI_STAGE_BYTES;
+    static constexpr int NUM_BARS = 2 * STAGES + 2 * ACC_STAGES;
+    static constexpr int SMEM_BYTES = OFF_BAR + NUM_BARS * 8 + 16 + 1024;   // + tmem slot + alignment slack
+};
 
 struct GemmArgs {
     int M, N, K;
@@ -54,24 +68,29 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
     return *reinterpret_cast<uint32_t*>(&h);
 }
 
-template <int EPI>
+template <int EPI, int MODE>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const GemmArgs g) {
+    using C = Cfg<MODE>;
+    constexpr int CL = C::CL, STAGES = C::STAGES;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const uint32_t sbase = smem_u32(smem);
-    const uint32_t bar0 = sbase + OFF_BAR;
+    const uint32_t bar0 = sbase + C::OFF_BAR;
     auto full_bar = [&](int s) { return bar0 + 8u * s; };
     auto empty_bar = [&](int s) { return bar0 + 8u * (STAGES + s); };
     auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * STAGES + a); };
     auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * STAGES + ACC_STAGES + a); };
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_BAR + NUM_BARS * 8);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + C::OFF_BAR + C::NUM_BARS * 8);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m_tiles = (g.M + BM - 1) / BM, n_tiles = (g.N + BN - 1) / BN;
-    const int num_tiles = m_tiles * n_tiles;
     const int num_kb = g.K / BK;
+    // work decomposition: unit = CTA (MODE 1) or CTA pair (MODE 2); a work item is CL stacked M-tiles
+    const int rank = (CL == 2) ? static_cast<int>(cluster_ctarank()) : 0;
+    const int unit = blockIdx.x / CL, num_units = gridDim.x / CL;
+    const int num_work = ((m_tiles + CL - 1) / CL) * n_tiles;
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmap_a);
@@ -79,13 +98,17 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-        for (int a = 0; a < ACC_STAGES; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), EPI_WARPS); }
+        // the leader's "accumulator drained" barrier collects the epilogue warps of BOTH CTAs
+        for (int a = 0; a < ACC_STAGES; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), EPI_WARPS * CL); }
         fence_barrier_init();
         fence_proxy_async_smem();
     }
-    if (warp == 2) tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
+    if (warp == 2) {
+        if constexpr (CL == 2) tmem_alloc_2sm(smem_u32(tmem_slot), TMEM_COLS);
+        else tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
+    }
     tc_fence_before();
-    __syncthreads();
+    if constexpr (CL == 2) cluster_sync_all(); else __syncthreads();   // peer barriers are initialised too
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -93,41 +116,54 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         // ===================== TMA producer =====================
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int m_blk = tile / n_tiles, n_blk = tile - m_blk * n_tiles;
+            for (int w = unit; w < num_work; w += num_units) {
+                const int mg = w / n_tiles, n_blk = w - mg * n_tiles, m_blk = mg * CL + rank;
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(empty_bar(stage), phase ^ 1);
-                    mbar_arrive_expect_tx(full_bar(stage), A_STAGE_BYTES + B_STAGE_BYTES);
-                    tma_load_2d(sbase + OFF_A + stage * A_STAGE_BYTES, &tmap_a, full_bar(stage), kb * BK, m_blk * BM);
-                    tma_load_2d(sbase + OFF_B + stage * B_STAGE_BYTES, &tmap_b, full_bar(stage), kb * BK, n_blk * BN);
+                    const uint32_t sa = sbase + C::OFF_A + stage * C::A_STAGE_BYTES;
+                    const uint32_t sb = sbase + C::OFF_B + stage * C::B_STAGE_BYTES;
+                    if constexpr (CL == 2) {
+                        // the leader's barrier expects both CTAs' A tile and W half
+                        if (rank == 0) mbar_arrive_expect_tx(full_bar(stage), 2 * (C::A_STAGE_BYTES + C::B_STAGE_BYTES));
+                        tma_load_2d_2sm(sa, &tmap_a, full_bar(stage), kb * BK, m_blk * BM);
+                        tma_load_2d_2sm(sb, &tmap_b, full_bar(stage), kb * BK, n_blk * BN + rank * (BN / 2));
+                    } else {
+                        mbar_arrive_expect_tx(full_bar(stage), C::A_STAGE_BYTES + C::B_STAGE_BYTES);
+                        tma_load_2d(sa, &tmap_a, full_bar(stage), kb * BK, m_blk * BM);
+                        tma_load_2d(sb, &tmap_b, full_bar(stage), kb * BK, n_blk * BN);
+                        tma_load_2d(sb + C::B_STAGE_BYTES / 2, &tmap_b, full_bar(stage), kb * BK, n_blk * BN + BN / 2);
+                    }
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
+        // ===================== MMA issuer (leader CTA of the pair) =====================
+        if (lane == 0 && rank == 0) {
+            constexpr uint32_t idesc = make_idesc_bf16(BM * CL, BN);
             int stage = 0; uint32_t phase = 0;
             int as = 0; uint32_t aphase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                mbar_wait(tempty_bar(as), aphase ^ 1);          // epilogue has drained this accumulator
+            for (int w = unit; w < num_work; w += num_units) {
+                mbar_wait(tempty_bar(as), aphase ^ 1);          // epilogues have drained this accumulator
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + as * BN;
                 for (int kb = 0; kb < num_kb; ++kb) {
-                    mbar_wait(full_bar(stage), phase);          // TMA bytes have landed
+                    mbar_wait(full_bar(stage), phase);          // TMA bytes (of both CTAs) have landed
                     tc_fence_after();
-                    const uint64_t da = make_kmajor_sw128_desc(sbase + OFF_A + stage * A_STAGE_BYTES);
-                    const uint64_t db = make_kmajor_sw128_desc(sbase + OFF_B + stage * B_STAGE_BYTES);
+                    const uint64_t da = make_kmajor_sw128_desc(sbase + C::OFF_A + stage * C::A_STAGE_BYTES);
+                    const uint64_t db = make_kmajor_sw128_desc(sbase + C::OFF_B + stage * C::B_STAGE_BYTES);
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; ++k) {
                         // +32 bytes per 16-element k-step inside the 128-byte swizzle atom
-                        umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                        if constexpr (CL == 2) umma_bf16_2sm(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                        else umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
                     }
-                    umma_commit(empty_bar(stage));              // smem slot free once these MMAs retire
+                    // smem slot free (in both CTAs) once these MMAs retire
+                    if constexpr (CL == 2) umma_commit_2sm(empty_bar(stage), 0x3); else umma_commit(empty_bar(stage));
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(tfull_bar(as));                     // accumulator complete
+                // accumulator complete: wake the epilogue warps of both CTAs
+                if constexpr (CL == 2) umma_commit_2sm(tfull_bar(as), 0x3); else umma_commit(tfull_bar(as));
                 if (++as == ACC_STAGES) { as = 0; aphase ^= 1; }
             }
         }
@@ -136,10 +172,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         const int e = warp - 4;
         const int q = warp & 3;                  // TMEM lane quarter this warp may access
         const int hh = e >> 2;                   // which 128-column half of the tile
-        uint8_t* stg = smem + OFF_EPI + e * EPI_STAGE_BYTES;
+        uint8_t* stg = smem + C::OFF_EPI + e * EPI_STAGE_BYTES;
         int as = 0; uint32_t aphase = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-            const int m_blk = tile / n_tiles, n_blk = tile - m_blk * n_tiles;
+        for (int w = unit; w < num_work; w += num_units) {
+            const int mg = w / n_tiles, n_blk = w - mg * n_tiles, m_blk = mg * CL + rank;
             const int row_base = m_blk * BM + q * 32;
             // RESID: the fp32 residual sub-tile of chunk ch+1 is fetched while chunk ch is drained
             // from TMEM (and chunk 0 while the MMAs of this tile are still running).
@@ -170,7 +206,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 if (ch == 3) {                   // all TMEM reads of this tile done: hand it back
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(tempty_bar(as));
+                    if (lane == 0) {
+                        if constexpr (CL == 2) mbar_arrive_leader(tempty_bar(as)); else mbar_arrive(tempty_bar(as));
+                    }
                 }
                 // transpose through smem: thread = row, 8 x 16-byte chunks, XOR-swizzled by row
 #pragma unroll
@@ -244,10 +282,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
 
     tc_fence_before();
-    __syncthreads();
+    if constexpr (CL == 2) cluster_sync_all(); else __syncthreads();   // the peer may still signal my barriers
     if (warp == 2) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, TMEM_COLS);
+        if constexpr (CL == 2) tmem_dealloc_2sm(tmem_base, TMEM_COLS);
+        else tmem_dealloc(tmem_base, TMEM_COLS);
     }
 }
 
@@ -269,22 +308,51 @@ EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
-template <int EPI>
-int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& g, cudaStream_t stream) {
+int cluster_mode() {
+    static int mode = 0;
+    if (!mode) {
+        const char* e = getenv("CLIPPPO_GEMM_CLUSTER");
+        mode = (e && e[0] == '1') ? 1 : 2;
+    }
+    return mode;
+}
+
+template <int EPI, int MODE>
+int launch_gemm_mode(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& g, cudaStream_t stream) {
+    using C = Cfg<MODE>;
     static bool configured = false;
     if (!configured) {
-        CLIPPPO_CUDA_TRY(cudaFuncSetAttribute(gemm_bf16_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        CLIPPPO_CUDA_TRY(cudaFuncSetAttribute(gemm_bf16_kernel<EPI, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
         configured = true;
     }
     const int m_tiles = (g.M + BM - 1) / BM, n_tiles = (g.N + BN - 1) / BN;
-    const int grid = min(m_tiles * n_tiles, kNumSMs);
+    const int work = ((m_tiles + C::CL - 1) / C::CL) * n_tiles;
+    const int grid = min(work, kNumSMs / C::CL) * C::CL;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = C::SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = C::CL;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
     void* span = nullptr;
     const bool timed = prof_timing_enabled();
     if (timed) prof_span_begin(stream, 2.0 * g.M * static_cast<double>(g.N) * g.K, &span);
-    gemm_bf16_kernel<EPI><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ta, tb, g);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<EPI, MODE>, ta, tb, g);
     if (timed) prof_span_end(stream, span);
-    CLIPPPO_CHECK_LAUNCH();
+    prof_count_launch();
+    CLIPPPO_CUDA_TRY(e);
     return CLIPPPO_OK;
+}
+
+template <int EPI>
+int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& g, cudaStream_t stream) {
+    return cluster_mode() == 2 ? launch_gemm_mode<EPI, 2>(ta, tb, g, stream) : launch_gemm_mode<EPI, 1>(ta, tb, g, stream);
 }
 
 }  // namespace
@@ -305,7 +373,7 @@ int make_bf16_kmajor_tmap(CUtensorMap* map, const void* ptr, int rows, int K, lo
 }
 
 int gemm_a_box_rows() { return BM; }
-int gemm_b_box_rows() { return BN; }
+int gemm_b_box_rows() { return BN / 2; }   // W is fetched as two 128-row halves (one per CTA of a pair)
 
 int gemm_bf16_launch(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, int epilogue,
                      const float* bias, const float* pos, int tokens, void* out, long long ldo, cudaStream_t stream) {

@@ -27,9 +27,9 @@ namespace clipppo {
 
 namespace {
 
-// 504 images = 25200 token rows = 197 M-tiles: 197 x {3, 9, 12} N-tiles fill 3.99 / 11.98 / 15.97
-// waves of 148 SMs, so no GEMM of the block ends on a nearly empty wave.
-constexpr int kChunkImages = 504;
+// 501 images = 25050 token rows = 196 M-tiles = 98 CTA-pair work rows: 98 x {3, 9, 12} N-tiles fill
+// 3.97 / 11.92 / 15.89 waves of 74 CTA pairs, so no GEMM of the block ends on a nearly empty wave.
+constexpr int kChunkImages = 501;
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
