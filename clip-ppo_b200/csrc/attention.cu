@@ -1,11 +1,12 @@
 // V4 - multi-head self-attention core of one ResidualAttentionBlock: softmax(Q K^T / sqrt(d)) V,
 // no mask, eval mode.  Replaces the SDPA call inside [clip] nn.MultiheadAttention.
 //
-// ViT-B/32 has T = 50 tokens and d_head = 64: ~1 % of the tower's FLOPs, HBM/L2-bound (it reads
-// the packed QKV rows once and writes the head outputs once), so one CTA owns one (image, head)
-// and keeps Q, K, V (padded to 64 rows) in shared memory.  The two tiny matmuls run on the
-// warp-level tensor-core path (mma.sync m16n8k16 bf16, fp32 accumulate); the softmax lives in
-// the accumulator registers and P never leaves them.  Keys >= T are masked; padded V rows are 0.
+// ViT-B/32 has T = 50 tokens and d_head = 64: ~1 % of the tower's FLOPs, bound by memory latency
+// and instruction issue rather than math.  Persistent CTAs (4 per SM) walk over (image, head)
+// items; the Q/K/V head slices of item i+1 stream into the second shared-memory buffer with
+// cp.async (zero-filled beyond T) while item i is computed, so no warp ever waits on a global
+// load.  The two tiny matmuls run on the warp-level tensor-core path (mma.sync m16n8k16 bf16, fp32
+// accumulate); the softmax lives in the accumulator registers and P never leaves them.
 #include "common.cuh"
 #include "gemm.cuh"
 
@@ -16,6 +17,11 @@ namespace {
 constexpr int TP = 64;          // padded tokens
 constexpr int DH = 64;          // head dim
 constexpr int PITCH = DH + 8;   // bf16 elements per smem row (144 B: conflict-free ldmatrix)
+constexpr int MAT_ELEMS = TP * PITCH;
+constexpr int BUF_ELEMS = 3 * MAT_ELEMS;                    // Q, K, V of one head
+constexpr int ATT_SMEM_BYTES = 2 * BUF_ELEMS * 2;           // double buffered: 55296 B
+constexpr int ATT_THREADS = 128;
+constexpr int ATT_CTAS_PER_SM = 4;
 
 __device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
     asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
@@ -34,119 +40,154 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
     __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&h);
 }
+__device__ __forceinline__ float ex2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// 16-byte async copy global -> shared; src_bytes = 0 zero-fills the destination instead
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, int src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-// grid = n_images * heads, 128 threads (4 warps x 16 query rows)
-__global__ void __launch_bounds__(128)
-attention_kernel(const __nv_bfloat16* __restrict__ qkv, int T, int heads, __nv_bfloat16* __restrict__ out) {
-    __shared__ __align__(16) __nv_bfloat16 sQ[TP * PITCH];
-    __shared__ __align__(16) __nv_bfloat16 sK[TP * PITCH];
-    __shared__ __align__(16) __nv_bfloat16 sV[TP * PITCH];
-    const int img = blockIdx.x / heads, head = blockIdx.x - img * heads;
+// Q, K, V slices of one (image, head): 3 x 64 rows x 8 chunks of 16 B = 12 chunks per thread
+__device__ __forceinline__ void prefetch_item(const __nv_bfloat16* __restrict__ qkv, int item, int heads, int T, int D,
+                                              uint32_t buf_addr, int tid) {
+    const int img = item / heads, head = item - img * heads;
+    const __nv_bfloat16* src = qkv + static_cast<size_t>(img) * T * (3 * D) + head * DH;
+    const int c8 = tid & 7, r0 = tid >> 3;                    // 16 rows per pass
+#pragma unroll
+    for (int m = 0; m < 3; ++m) {
+#pragma unroll
+        for (int pass = 0; pass < 4; ++pass) {
+            const int r = r0 + pass * 16;
+            const bool ok = r < T;
+            const __nv_bfloat16* g = ok ? src + static_cast<size_t>(r) * (3 * D) + m * D + c8 * 8 : qkv;
+            cp_async16(buf_addr + (m * MAT_ELEMS + r * PITCH + c8 * 8) * 2, g, ok ? 16 : 0);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(ATT_THREADS, ATT_CTAS_PER_SM)
+attention_kernel(const __nv_bfloat16* __restrict__ qkv, int n_items, int T, int heads, __nv_bfloat16* __restrict__ out) {
+    extern __shared__ __align__(16) __nv_bfloat16 att_smem[];
     const int D = heads * DH;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-
-    // ---- load Q, K, V head slices (rows >= T zero-filled) ----
-    const __nv_bfloat16* src = qkv + static_cast<size_t>(img) * T * (3 * D) + head * DH;
-    for (int i = tid; i < 3 * TP * 8; i += 128) {
-        const int m = i / (TP * 8);                  // 0 Q, 1 K, 2 V
-        const int rem = i - m * (TP * 8);
-        const int r = rem >> 3, c8 = rem & 7;
-        uint4 val = make_uint4(0, 0, 0, 0);
-        if (r < T) val = *reinterpret_cast<const uint4*>(src + static_cast<size_t>(r) * (3 * D) + m * D + c8 * 8);
-        __nv_bfloat16* dst = (m == 0 ? sQ : (m == 1 ? sK : sV)) + r * PITCH + c8 * 8;
-        *reinterpret_cast<uint4*>(dst) = val;
-    }
-    __syncthreads();
-
+    const uint32_t smem0 = ptx_smem(att_smem);
     const int row0 = warp * 16;
-    if (row0 < T) {
-        // ---- S = Q K^T (16 x 64 per warp) ----
-        float s[8][4];
-#pragma unroll
-        for (int nt = 0; nt < 8; ++nt) { s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f; }
-        const uint32_t q_addr = ptx_smem(sQ) + ((row0 + (lane & 15)) * PITCH + (lane >> 4) * 8) * 2;
-        const uint32_t k_addr = ptx_smem(sK) + (((lane & 7) + (lane >> 4) * 8) * PITCH + ((lane >> 3) & 1) * 8) * 2;
-#pragma unroll
-        for (int ks = 0; ks < DH / 16; ++ks) {
-            uint32_t a[4];
-            ldsm_x4(q_addr + ks * 32, a[0], a[1], a[2], a[3]);
-#pragma unroll
-            for (int np = 0; np < 4; ++np) {          // pairs of key tiles
-                uint32_t b0, b1, b2, b3;
-                ldsm_x4(k_addr + (np * 16 * PITCH) * 2 + ks * 32, b0, b1, b2, b3);
-                mma_bf16_16816(s[2 * np], a, b0, b1);
-                mma_bf16_16816(s[2 * np + 1], a, b2, b3);
-            }
-        }
-        // ---- softmax over keys (rows lane/4 and lane/4 + 8), scale 1/sqrt(64) folded into exp2 ----
-        const float sl2 = 0.125f * 1.4426950408889634f;
-        float mx0 = -INFINITY, mx1 = -INFINITY;
-#pragma unroll
-        for (int nt = 0; nt < 8; ++nt) {
-            const int n = nt * 8 + 2 * (lane & 3);
-            if (n >= T)     { s[nt][0] = -INFINITY; s[nt][2] = -INFINITY; }
-            if (n + 1 >= T) { s[nt][1] = -INFINITY; s[nt][3] = -INFINITY; }
-            mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
-            mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
-        }
-        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
-        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
-        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
-        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
-        float sum0 = 0.f, sum1 = 0.f;
-#pragma unroll
-        for (int nt = 0; nt < 8; ++nt) {
-            s[nt][0] = exp2f((s[nt][0] - mx0) * sl2);
-            s[nt][1] = exp2f((s[nt][1] - mx0) * sl2);
-            s[nt][2] = exp2f((s[nt][2] - mx1) * sl2);
-            s[nt][3] = exp2f((s[nt][3] - mx1) * sl2);
-            sum0 += s[nt][0] + s[nt][1];
-            sum1 += s[nt][2] + s[nt][3];
-        }
-        sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1);
-        sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
-        sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1);
-        sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
-        const float inv0 = 1.0f / sum0, inv1 = 1.0f / sum1;
 
-        // ---- O = P V ----
-        float o[8][4];
+    int item = blockIdx.x;
+    if (item < n_items) prefetch_item(qkv, item, heads, T, D, smem0, tid);
+    cp_async_commit();
+    int b = 0;
+    for (; item < n_items; item += gridDim.x, b ^= 1) {
+        const int next = item + gridDim.x;
+        if (next < n_items) prefetch_item(qkv, next, heads, T, D, smem0 + (b ^ 1) * BUF_ELEMS * 2, tid);
+        cp_async_commit();
+        cp_async_wait<1>();                                   // this item's slices have landed
+        __syncthreads();
+
+        __nv_bfloat16* sQ = att_smem + b * BUF_ELEMS;
+        const uint32_t q_base = smem0 + b * BUF_ELEMS * 2;
+        const uint32_t k_base = q_base + MAT_ELEMS * 2, v_base = k_base + MAT_ELEMS * 2;
+        const int img = item / heads, head = item - img * heads;
+        if (row0 < T) {
+            // ---- S = Q K^T (16 x 64 per warp) ----
+            float s[8][4];
 #pragma unroll
-        for (int nt = 0; nt < 8; ++nt) { o[nt][0] = o[nt][1] = o[nt][2] = o[nt][3] = 0.f; }
-        const uint32_t v_addr = ptx_smem(sV) + (((lane & 7) + ((lane >> 3) & 1) * 8) * PITCH + (lane >> 4) * 8) * 2;
+            for (int nt = 0; nt < 8; ++nt) { s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f; }
+            const uint32_t q_addr = q_base + ((row0 + (lane & 15)) * PITCH + (lane >> 4) * 8) * 2;
+            const uint32_t k_addr = k_base + (((lane & 7) + (lane >> 4) * 8) * PITCH + ((lane >> 3) & 1) * 8) * 2;
 #pragma unroll
-        for (int kk = 0; kk < TP / 16; ++kk) {        // 16 keys per step
-            uint32_t a[4];
-            a[0] = pack2(s[2 * kk][0] * inv0, s[2 * kk][1] * inv0);
-            a[1] = pack2(s[2 * kk][2] * inv1, s[2 * kk][3] * inv1);
-            a[2] = pack2(s[2 * kk + 1][0] * inv0, s[2 * kk + 1][1] * inv0);
-            a[3] = pack2(s[2 * kk + 1][2] * inv1, s[2 * kk + 1][3] * inv1);
+            for (int ks = 0; ks < DH / 16; ++ks) {
+                uint32_t a[4];
+                ldsm_x4(q_addr + ks * 32, a[0], a[1], a[2], a[3]);
 #pragma unroll
-            for (int dp = 0; dp < 4; ++dp) {          // pairs of d tiles
-                uint32_t b0, b1, b2, b3;
-                ldsm_x4_trans(v_addr + (kk * 16 * PITCH + dp * 16) * 2, b0, b1, b2, b3);
-                mma_bf16_16816(o[2 * dp], a, b0, b1);
-                mma_bf16_16816(o[2 * dp + 1], a, b2, b3);
+                for (int np = 0; np < 4; ++np) {          // pairs of key tiles
+                    uint32_t b0, b1, b2, b3;
+                    ldsm_x4(k_addr + (np * 16 * PITCH) * 2 + ks * 32, b0, b1, b2, b3);
+                    mma_bf16_16816(s[2 * np], a, b0, b1);
+                    mma_bf16_16816(s[2 * np + 1], a, b2, b3);
+                }
+            }
+            // ---- softmax over keys (rows lane/4 and lane/4 + 8), scale 1/sqrt(64) folded into exp2 ----
+            const float sl2 = 0.125f * 1.4426950408889634f;
+            float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) {
+                if (nt * 8 + 8 > T) {                     // only the tiles that straddle T need masking
+                    const int n = nt * 8 + 2 * (lane & 3);
+                    if (n >= T)     { s[nt][0] = -INFINITY; s[nt][2] = -INFINITY; }
+                    if (n + 1 >= T) { s[nt][1] = -INFINITY; s[nt][3] = -INFINITY; }
+                }
+                mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
+                mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
+            }
+            mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+            mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+            mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+            mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+            const float m0 = mx0 * sl2, m1 = mx1 * sl2;
+            float sum0 = 0.f, sum1 = 0.f;
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) {
+                s[nt][0] = ex2(fmaf(s[nt][0], sl2, -m0));
+                s[nt][1] = ex2(fmaf(s[nt][1], sl2, -m0));
+                s[nt][2] = ex2(fmaf(s[nt][2], sl2, -m1));
+                s[nt][3] = ex2(fmaf(s[nt][3], sl2, -m1));
+                sum0 += s[nt][0] + s[nt][1];
+                sum1 += s[nt][2] + s[nt][3];
+            }
+            sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1);
+            sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
+            sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1);
+            sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
+            const float inv0 = 1.0f / sum0, inv1 = 1.0f / sum1;
+
+            // ---- O = P V ----
+            float o[8][4];
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) { o[nt][0] = o[nt][1] = o[nt][2] = o[nt][3] = 0.f; }
+            const uint32_t v_addr = v_base + (((lane & 7) + ((lane >> 3) & 1) * 8) * PITCH + (lane >> 4) * 8) * 2;
+#pragma unroll
+            for (int kk = 0; kk < TP / 16; ++kk) {        // 16 keys per step
+                uint32_t a[4];
+                a[0] = pack2(s[2 * kk][0] * inv0, s[2 * kk][1] * inv0);
+                a[1] = pack2(s[2 * kk][2] * inv1, s[2 * kk][3] * inv1);
+                a[2] = pack2(s[2 * kk + 1][0] * inv0, s[2 * kk + 1][1] * inv0);
+                a[3] = pack2(s[2 * kk + 1][2] * inv1, s[2 * kk + 1][3] * inv1);
+#pragma unroll
+                for (int dp = 0; dp < 4; ++dp) {          // pairs of d tiles
+                    uint32_t b0, b1, b2, b3;
+                    ldsm_x4_trans(v_addr + (kk * 16 * PITCH + dp * 16) * 2, b0, b1, b2, b3);
+                    mma_bf16_16816(o[2 * dp], a, b0, b1);
+                    mma_bf16_16816(o[2 * dp + 1], a, b2, b3);
+                }
+            }
+            // ---- stage the 16 x 64 output in this warp's own Q rows, then 16-byte coalesced stores ----
+            __syncwarp();
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) {
+                const int c = nt * 8 + 2 * (lane & 3);
+                *reinterpret_cast<uint32_t*>(sQ + (row0 + (lane >> 2)) * PITCH + c) = pack2(o[nt][0], o[nt][1]);
+                *reinterpret_cast<uint32_t*>(sQ + (row0 + (lane >> 2) + 8) * PITCH + c) = pack2(o[nt][2], o[nt][3]);
+            }
+            __syncwarp();
+            __nv_bfloat16* dst = out + static_cast<size_t>(img) * T * D + head * DH;
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+                const int r = row0 + it * 4 + (lane >> 3), c8 = lane & 7;
+                if (r < T)
+                    *reinterpret_cast<uint4*>(dst + static_cast<size_t>(r) * D + c8 * 8) =
+                        *reinterpret_cast<const uint4*>(sQ + r * PITCH + c8 * 8);
             }
         }
-        // ---- stage the 16 x 64 output in this warp's own Q rows, then 16-byte coalesced stores ----
-        __syncwarp();
-#pragma unroll
-        for (int nt = 0; nt < 8; ++nt) {
-            const int c = nt * 8 + 2 * (lane & 3);
-            *reinterpret_cast<uint32_t*>(sQ + (row0 + (lane >> 2)) * PITCH + c) = pack2(o[nt][0], o[nt][1]);
-            *reinterpret_cast<uint32_t*>(sQ + (row0 + (lane >> 2) + 8) * PITCH + c) = pack2(o[nt][2], o[nt][3]);
-        }
-        __syncwarp();
-        __nv_bfloat16* dst = out + static_cast<size_t>(img) * T * D + head * DH;
-#pragma unroll
-        for (int it = 0; it < 4; ++it) {
-            const int r = row0 + it * 4 + (lane >> 3), c8 = lane & 7;
-            if (r < T)
-                *reinterpret_cast<uint4*>(dst + static_cast<size_t>(r) * D + c8 * 8) =
-                    *reinterpret_cast<const uint4*>(sQ + r * PITCH + c8 * 8);
-        }
+        __syncthreads();                                      // buffer b is overwritten by the prefetch of item+2
     }
+    cp_async_wait<0>();
 }
 
 }  // namespace
@@ -157,8 +198,16 @@ int attention_launch(const void* qkv_bf16, int n_images, int tokens, int heads, 
     if (n_images <= 0 || tokens <= 0 || heads <= 0) return CLIPPPO_ERR_BAD_SHAPE;
     if (head_dim != DH || tokens > TP) return CLIPPPO_ERR_UNSUPPORTED;
     if ((reinterpret_cast<uintptr_t>(qkv_bf16) % 16) || (reinterpret_cast<uintptr_t>(out_bf16) % 16)) return CLIPPPO_ERR_ALIGN;
-    attention_kernel<<<static_cast<unsigned>(n_images) * heads, 128, 0, stream>>>(
-        static_cast<const __nv_bfloat16*>(qkv_bf16), tokens, heads, static_cast<__nv_bfloat16*>(out_bf16));
+    static bool configured = false;
+    if (!configured) {
+        CLIPPPO_CUDA_TRY(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
+        configured = true;
+    }
+    const long long items = static_cast<long long>(n_images) * heads;
+    const int grid = static_cast<int>(items < kNumSMs * ATT_CTAS_PER_SM ? items : kNumSMs * ATT_CTAS_PER_SM);
+    attention_kernel<<<grid, ATT_THREADS, ATT_SMEM_BYTES, stream>>>(
+        static_cast<const __nv_bfloat16*>(qkv_bf16), static_cast<int>(items), tokens, heads,
+        static_cast<__nv_bfloat16*>(out_bf16));
     CLIPPPO_CHECK_LAUNCH();
     return CLIPPPO_OK;
 }

@@ -37,6 +37,7 @@ struct DisturbParams {
     float taps[CLIPPPO_MAX_BLUR_TAPS];
     int sh, sw, ph, pw;
     int S, R;       // stripes per image (= cluster size), rows per stripe
+    int nsplit;     // row splits of a stripe in the blur phase (balances the 4-column tasks over the CTA)
     int fast;       // x / noise contiguous NCHW fp32, W % 4 == 0, 16-byte aligned
     int io_mode;    // 0: fp32 strided in, fp32 NCHW out.  1: u8 NHWC in / u8 NHWC out.
                     // 2: fp32 (0..255) NHWC in / u8 NHWC out.
@@ -179,6 +180,80 @@ disturb_kernel(const __grid_constant__ DisturbParams p) {
     }
 
     // ---- phase 5: separable blur, cutout, store --------------------------------------------
+    // Fast path: each thread produces a 4-column x `rps`-row block.  Per row it reads 12 smem values
+    // (3 x LDS.128), forms 4 horizontally filtered values and pushes them into a K-deep register
+    // ring whose slots are addressed at compile time (row loop unrolled by K), so the vertical
+    // pass costs K FMAs per output and no register moves; stores are 128-bit and coalesced.
+    if (p.io_mode == 0 && (W & 3) == 0 && P <= 4) {
+        const int nq = W >> 2, nsplit = p.nsplit;
+        const int rps = (rows + nsplit - 1) / nsplit;
+        const int ntasks = C * nsplit * nq;
+        float* outp = static_cast<float*>(p.out);
+        for (int task = tid; task < ntasks; task += nth) {
+            const int q = task % nq, rest = task / nq;
+            const int sp = rest % nsplit, c_ = rest / nsplit;
+            const int ra = sp * rps, rb = min(ra + rps, rows);
+            if (ra >= rb) continue;
+            const float* base = tile + (size_t)c_ * RS * W;
+            const int j0 = q * 4;
+            const bool interior = (q > 0) && (q < nq - 1);
+            auto hrow = [&](int lr, float (&h)[4]) {
+                const float* rowp = base + (size_t)lr * W;
+                float v[12];                                   // columns j0-4 .. j0+7
+                if (interior) {
+                    const float4 a = *reinterpret_cast<const float4*>(rowp + j0 - 4);
+                    const float4 m = *reinterpret_cast<const float4*>(rowp + j0);
+                    const float4 z = *reinterpret_cast<const float4*>(rowp + j0 + 4);
+                    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+                    v[4] = m.x; v[5] = m.y; v[6] = m.z; v[7] = m.w;
+                    v[8] = z.x; v[9] = z.y; v[10] = z.z; v[11] = z.w;
+                } else {
+#pragma unroll
+                    for (int t = 4 - P; t < 8 + P; ++t) {
+                        int jj = j0 - 4 + t;
+                        if (jj < 0) jj = -jj;
+                        if (jj >= W) jj = 2 * (W - 1) - jj;
+                        v[t] = rowp[jj];
+                    }
+                }
+#pragma unroll
+                for (int o = 0; o < 4; ++o) {
+                    float acc = 0.0f;
+#pragma unroll
+                    for (int u = 0; u < K; ++u) acc = fmaf(p.taps[u], v[4 + o + u - P], acc);
+                    h[o] = acc;
+                }
+            };
+            float ring[K][4];
+#pragma unroll
+            for (int i = 0; i < K - 1; ++i) hrow(ra + i, ring[i]);
+            const bool quad_cut = do_cut && (j0 + 3 >= p.sw) && (j0 < p.sw + p.pw);
+            for (int r = ra; r < rb; r += K) {
+#pragma unroll
+                for (int rr = 0; rr < K; ++rr) {
+                    if (r + rr < rb) {
+                        hrow(r + rr + K - 1, ring[(rr + K - 1) % K]);
+                        float o4[4];
+#pragma unroll
+                        for (int o = 0; o < 4; ++o) {
+                            float acc = 0.0f;
+#pragma unroll
+                            for (int u = 0; u < K; ++u) acc = fmaf(p.taps[u], ring[(rr + u) % K][o], acc);
+                            o4[o] = acc;
+                        }
+                        const int ir = r0 + r + rr;
+                        if (quad_cut && ir >= p.sh && ir < p.sh + p.ph) {
+#pragma unroll
+                            for (int o = 0; o < 4; ++o)
+                                if (j0 + o >= p.sw && j0 + o < p.sw + p.pw) o4[o] = 0.0f;
+                        }
+                        st_stream_f4(outp + (((size_t)b * C + c_) * H + ir) * W + j0, make_float4(o4[0], o4[1], o4[2], o4[3]));
+                    }
+                }
+            }
+        }
+        return;
+    }
     for (int task = tid; task < C * W; task += nth) {
         const int c_ = task / W, j = task - c_ * W;
         int jidx[K];
@@ -277,6 +352,17 @@ static int run_disturb(DisturbParams& p, const float* k1d_host, int k, cudaStrea
     if (!S) return CLIPPPO_ERR_UNSUPPORTED;
     p.S = S;
     p.R = (p.H + S - 1) / S;
+    {   // blur-phase task shape: minimise rounds x (rows per task + ring warm-up rows)
+        const int nq = (p.W + 3) / 4;
+        long best_cost = -1;
+        p.nsplit = 1;
+        for (int sp = 1; sp <= 8 && sp <= p.R; ++sp) {
+            const long tasks = (long)p.C * nq * sp;
+            const long rounds = (tasks + kDisturbThreads - 1) / kDisturbThreads;
+            const long cost = rounds * ((p.R + sp - 1) / sp + 2 * P);
+            if (best_cost < 0 || cost < best_cost) { best_cost = cost; p.nsplit = sp; }
+        }
+    }
     const size_t smem = smem_for(S);
     switch (K) {
         case 1:  return launch_disturb<1>(p, smem, stream);
