@@ -54,6 +54,76 @@ __device__ __forceinline__ float noisy(float x, float n, float sigma) {
     return clamp01(__fadd_rn(x, __fmul_rn(n, sigma)));
 }
 
+// Horizontal K-tap filter of 4 adjacent columns of one smem row.  `rowq` points at column j0 of the
+// row.  EDGE = false: the quad is interior, so columns j0-4 .. j0+7 exist and are fetched with three
+// 128-bit loads.  EDGE = true: first / last quad of a row, scalar loads with reflect indexing.
+template <int K, bool EDGE>
+__device__ __forceinline__ void hfilter4(const float* __restrict__ rowq, int j0, int W, const float (&taps)[K], float (&h)[4]) {
+    constexpr int P = K / 2;
+    float v[12];                                   // columns j0-4 .. j0+7
+    if constexpr (!EDGE) {
+        const float4 a = *reinterpret_cast<const float4*>(rowq - 4);
+        const float4 m = *reinterpret_cast<const float4*>(rowq);
+        const float4 z = *reinterpret_cast<const float4*>(rowq + 4);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+        v[4] = m.x; v[5] = m.y; v[6] = m.z; v[7] = m.w;
+        v[8] = z.x; v[9] = z.y; v[10] = z.z; v[11] = z.w;
+    } else {
+#pragma unroll
+        for (int t = 4 - P; t < 8 + P; ++t) {
+            int jj = j0 - 4 + t;
+            if (jj < 0) jj = -jj;
+            if (jj >= W) jj = 2 * (W - 1) - jj;
+            v[t] = rowq[jj - j0];
+        }
+    }
+#pragma unroll
+    for (int o = 0; o < 4; ++o) {
+        float acc = 0.0f;
+#pragma unroll
+        for (int u = 0; u < K; ++u) acc = fmaf(taps[u], v[4 + o + u - P], acc);
+        h[o] = acc;
+    }
+}
+
+// One blur task: a 4-column x [ra, rb) block of channel plane `base`.  The horizontally filtered rows
+// live in a K-deep register ring whose slots are compile-time (row loop unrolled by K): the vertical
+// pass is K FMAs per output, no register moves, no address arithmetic beyond two pointer bumps.
+template <int K, bool EDGE>
+__device__ __forceinline__ void blur_task(const float* __restrict__ base, float* __restrict__ outq, int W, int j0,
+                                          int ra, int rb, int ir0, const float (&taps)[K], unsigned cutmask, int sh, int sh_end) {
+    const float* rowq = base + ra * W + j0;        // tile row `ra` <-> first input row of output row ra
+    float ring[K][4];
+#pragma unroll
+    for (int i = 0; i < K - 1; ++i) { hfilter4<K, EDGE>(rowq, j0, W, taps, ring[i]); rowq += W; }
+    int ir = ir0 + ra;
+    outq += static_cast<size_t>(ra) * W;
+    for (int r = ra; r < rb; r += K) {
+#pragma unroll
+        for (int rr = 0; rr < K; ++rr) {
+            if (r + rr < rb) {
+                hfilter4<K, EDGE>(rowq, j0, W, taps, ring[(rr + K - 1) % K]);
+                rowq += W;
+                float o4[4];
+#pragma unroll
+                for (int o = 0; o < 4; ++o) {
+                    float acc = 0.0f;
+#pragma unroll
+                    for (int u = 0; u < K; ++u) acc = fmaf(taps[u], ring[(rr + u) % K][o], acc);
+                    o4[o] = acc;
+                }
+                if (cutmask && ir >= sh && ir < sh_end) {
+#pragma unroll
+                    for (int o = 0; o < 4; ++o) if (cutmask & (1u << o)) o4[o] = 0.0f;
+                }
+                st_stream_f4(outq, make_float4(o4[0], o4[1], o4[2], o4[3]));
+                outq += W;
+                ++ir;
+            }
+        }
+    }
+}
+
 template <int K>
 __global__ void __launch_bounds__(kDisturbThreads)
 disturb_kernel(const __grid_constant__ DisturbParams p) {
@@ -68,50 +138,53 @@ disturb_kernel(const __grid_constant__ DisturbParams p) {
     const int b = blockIdx.x / S, s = blockIdx.x % S;
     const int r0 = min(s * R, H), r1 = min(r0 + R, H), rows = r1 - r0;
     const int RS = R + 2 * P;                 // smem rows per channel
+    const int plane = RS * W;                 // smem floats per channel
     const int tid = threadIdx.x, nth = blockDim.x;
     const bool do_noise = (p.stages & CLIPPPO_STAGE_NOISE) != 0;
     const bool do_contrast = (p.stages & CLIPPPO_STAGE_CONTRAST) != 0;
     const bool do_cut = (p.stages & CLIPPPO_STAGE_CUTOUT) != 0;
     const float sigma = p.sigma_n;
+    const bool vec4 = (W & 3) == 0;           // smem rows are 16-byte aligned
 
     // ---- phase 1: stripe -> smem -----------------------------------------------------------
     float gsum = 0.0f;
     if (p.fast) {
-        const int W4 = W >> 2;
-        const int n4 = rows * W4;             // float4 per channel
-        const int total4 = C * n4;
-        const float* xb = static_cast<const float*>(p.x) + (size_t)b * C * H * W;
-        const float* nb = p.noise ? p.noise + (size_t)b * C * H * W : nullptr;
+        const int n4 = (rows * W) >> 2;       // float4 per channel of this stripe (contiguous in global)
         constexpr int UNR = 4;
-        for (int i0 = tid; i0 < total4; i0 += nth * UNR) {
-            float4 xv[UNR], nv[UNR];
+        for (int c_ = 0; c_ < C; ++c_) {
+            const size_t goff = (static_cast<size_t>(b) * C + c_) * H * W + static_cast<size_t>(r0) * W;
+            const float* xs = static_cast<const float*>(p.x) + goff;
+            const float* ns = do_noise ? p.noise + goff : nullptr;
+            float4* dst = reinterpret_cast<float4*>(tile + c_ * plane + P * W);
+            const float wc = (C == 3) ? (c_ == 0 ? 0.2989f : (c_ == 1 ? 0.587f : 0.114f)) : 1.0f;
+            float csum = 0.0f;
+            for (int i0 = tid; i0 < n4; i0 += nth * UNR) {
+                float4 xv[UNR], nv[UNR];
 #pragma unroll
-            for (int u = 0; u < UNR; ++u) {
-                const int i = i0 + u * nth;
-                if (i < total4) {
-                    const int c_ = i / n4, rem = i - c_ * n4;
-                    const size_t g = ((size_t)c_ * H + r0) * W + (size_t)rem * 4;
-                    xv[u] = ld_stream_f4(xb + g);
-                    if (do_noise) nv[u] = ld_stream_f4(nb + g);
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < UNR; ++u) {
-                const int i = i0 + u * nth;
-                if (i < total4) {
-                    const int c_ = i / n4, rem = i - c_ * n4;
-                    float4 v = xv[u];
-                    if (do_noise) {
-                        v.x = noisy(v.x, nv[u].x, sigma);
-                        v.y = noisy(v.y, nv[u].y, sigma);
-                        v.z = noisy(v.z, nv[u].z, sigma);
-                        v.w = noisy(v.w, nv[u].w, sigma);
+                for (int u = 0; u < UNR; ++u) {
+                    const int i = i0 + u * nth;
+                    if (i < n4) {
+                        xv[u] = ld_stream_f4(xs + 4 * i);
+                        if (do_noise) nv[u] = ld_stream_f4(ns + 4 * i);
                     }
-                    const float wc = (C == 3) ? (c_ == 0 ? 0.2989f : (c_ == 1 ? 0.587f : 0.114f)) : 1.0f;
-                    gsum += wc * ((v.x + v.y) + (v.z + v.w));
-                    *reinterpret_cast<float4*>(tile + ((size_t)c_ * RS + P) * W + (size_t)rem * 4) = v;
+                }
+#pragma unroll
+                for (int u = 0; u < UNR; ++u) {
+                    const int i = i0 + u * nth;
+                    if (i < n4) {
+                        float4 v = xv[u];
+                        if (do_noise) {
+                            v.x = noisy(v.x, nv[u].x, sigma);
+                            v.y = noisy(v.y, nv[u].y, sigma);
+                            v.z = noisy(v.z, nv[u].z, sigma);
+                            v.w = noisy(v.w, nv[u].w, sigma);
+                        }
+                        csum += (v.x + v.y) + (v.z + v.w);
+                        dst[i] = v;
+                    }
                 }
             }
+            gsum = fmaf(wc, csum, gsum);
         }
     } else {
         const int n = rows * W;
@@ -132,7 +205,7 @@ disturb_kernel(const __grid_constant__ DisturbParams p) {
             }
             const float wc = (C == 3) ? (c_ == 0 ? 0.2989f : (c_ == 1 ? 0.587f : 0.114f)) : 1.0f;
             gsum += wc * v;
-            tile[((size_t)c_ * RS + P + r) * W + j] = v;
+            tile[c_ * plane + (P + r) * W + j] = v;
         }
     }
 
@@ -147,12 +220,27 @@ disturb_kernel(const __grid_constant__ DisturbParams p) {
         }
         const float m = tot / static_cast<float>(H * W);
         const float cm = __fmul_rn(p.omc, m);
-        const int n = rows * W;
+        const float cf = p.c;
         __syncthreads();
-        for (int i = tid; i < C * n; i += nth) {
-            const int c_ = i / n, rem = i - c_ * n;
-            float* q = tile + ((size_t)c_ * RS + P) * W + rem;
-            *q = clamp01(__fadd_rn(__fmul_rn(p.c, *q), cm));
+        if (vec4) {
+            const int n4 = (rows * W) >> 2;
+            for (int c_ = 0; c_ < C; ++c_) {
+                float4* q4 = reinterpret_cast<float4*>(tile + c_ * plane + P * W);
+                for (int i = tid; i < n4; i += nth) {
+                    float4 v = q4[i];
+                    v.x = clamp01(__fadd_rn(__fmul_rn(cf, v.x), cm));
+                    v.y = clamp01(__fadd_rn(__fmul_rn(cf, v.y), cm));
+                    v.z = clamp01(__fadd_rn(__fmul_rn(cf, v.z), cm));
+                    v.w = clamp01(__fadd_rn(__fmul_rn(cf, v.w), cm));
+                    q4[i] = v;
+                }
+            }
+        } else {
+            const int n = rows * W;
+            for (int c_ = 0; c_ < C; ++c_) {
+                float* q = tile + c_ * plane + P * W;
+                for (int i = tid; i < n; i += nth) q[i] = clamp01(__fadd_rn(__fmul_rn(cf, q[i]), cm));
+            }
         }
     }
 
@@ -160,18 +248,23 @@ disturb_kernel(const __grid_constant__ DisturbParams p) {
     if (K > 1) {
         if (S > 1) cluster.sync(); else __syncthreads();
         if (rows > 0) {
-            const int hn = 2 * P * W;
-            for (int i = tid; i < C * hn; i += nth) {
-                const int c_ = i / hn, rem = i - c_ * hn;
-                const int hr = rem / W, j = rem - hr * W;
-                const int lr = hr < P ? hr : rows + hr;          // below the last own row
-                int ir = r0 - P + lr;                            // image row before reflection
+            // 2P halo rows per channel; one (channel, halo row) pair per loop trip, columns by thread
+            for (int hr_c = 0; hr_c < C * 2 * P; ++hr_c) {
+                const int c_ = hr_c / (2 * P), hr = hr_c - c_ * (2 * P);
+                const int lr = hr < P ? hr : rows + hr;              // below the last own row
+                int ir = r0 - P + lr;                                // image row before reflection
                 if (ir < 0) ir = -ir;
                 if (ir >= H) ir = 2 * (H - 1) - ir;
                 const int owner = ir / R;
                 const int olr = ir - owner * R + P;
-                const float* src = (owner == s) ? tile : cluster.map_shared_rank(tile, owner);
-                tile[((size_t)c_ * RS + lr) * W + j] = src[((size_t)c_ * RS + olr) * W + j];
+                const float* src = ((owner == s) ? tile : cluster.map_shared_rank(tile, owner)) + c_ * plane + olr * W;
+                float* dstrow = tile + c_ * plane + lr * W;
+                if (vec4) {
+                    for (int j = tid; j < (W >> 2); j += nth)
+                        reinterpret_cast<float4*>(dstrow)[j] = reinterpret_cast<const float4*>(src)[j];
+                } else {
+                    for (int j = tid; j < W; j += nth) dstrow[j] = src[j];
+                }
             }
         }
         if (S > 1) cluster.sync(); else __syncthreads();         // also: nobody exits while peers read
@@ -180,80 +273,34 @@ disturb_kernel(const __grid_constant__ DisturbParams p) {
     }
 
     // ---- phase 5: separable blur, cutout, store --------------------------------------------
-    // Fast path: each thread produces a 4-column x `rps`-row block.  Per row it reads 12 smem values
-    // (3 x LDS.128), forms 4 horizontally filtered values and pushes them into a K-deep register
-    // ring whose slots are addressed at compile time (row loop unrolled by K), so the vertical
-    // pass costs K FMAs per output and no register moves; stores are 128-bit and coalesced.
-    if (p.io_mode == 0 && (W & 3) == 0 && P <= 4) {
+    float taps[K];
+#pragma unroll
+    for (int u = 0; u < K; ++u) taps[u] = p.taps[u];
+    if (p.io_mode == 0 && vec4 && P <= 4) {
+        // Fast path: 4-column x rps-row tasks, consecutive threads on consecutive column quads.
         const int nq = W >> 2, nsplit = p.nsplit;
         const int rps = (rows + nsplit - 1) / nsplit;
         const int ntasks = C * nsplit * nq;
-        float* outp = static_cast<float*>(p.out);
+        const int sh_end = p.sh + p.ph, sw_end = p.sw + p.pw;
         for (int task = tid; task < ntasks; task += nth) {
             const int q = task % nq, rest = task / nq;
             const int sp = rest % nsplit, c_ = rest / nsplit;
             const int ra = sp * rps, rb = min(ra + rps, rows);
             if (ra >= rb) continue;
-            const float* base = tile + (size_t)c_ * RS * W;
             const int j0 = q * 4;
-            const bool interior = (q > 0) && (q < nq - 1);
-            auto hrow = [&](int lr, float (&h)[4]) {
-                const float* rowp = base + (size_t)lr * W;
-                float v[12];                                   // columns j0-4 .. j0+7
-                if (interior) {
-                    const float4 a = *reinterpret_cast<const float4*>(rowp + j0 - 4);
-                    const float4 m = *reinterpret_cast<const float4*>(rowp + j0);
-                    const float4 z = *reinterpret_cast<const float4*>(rowp + j0 + 4);
-                    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
-                    v[4] = m.x; v[5] = m.y; v[6] = m.z; v[7] = m.w;
-                    v[8] = z.x; v[9] = z.y; v[10] = z.z; v[11] = z.w;
-                } else {
+            unsigned cutmask = 0;
+            if (do_cut) {
 #pragma unroll
-                    for (int t = 4 - P; t < 8 + P; ++t) {
-                        int jj = j0 - 4 + t;
-                        if (jj < 0) jj = -jj;
-                        if (jj >= W) jj = 2 * (W - 1) - jj;
-                        v[t] = rowp[jj];
-                    }
-                }
-#pragma unroll
-                for (int o = 0; o < 4; ++o) {
-                    float acc = 0.0f;
-#pragma unroll
-                    for (int u = 0; u < K; ++u) acc = fmaf(p.taps[u], v[4 + o + u - P], acc);
-                    h[o] = acc;
-                }
-            };
-            float ring[K][4];
-#pragma unroll
-            for (int i = 0; i < K - 1; ++i) hrow(ra + i, ring[i]);
-            const bool quad_cut = do_cut && (j0 + 3 >= p.sw) && (j0 < p.sw + p.pw);
-            for (int r = ra; r < rb; r += K) {
-#pragma unroll
-                for (int rr = 0; rr < K; ++rr) {
-                    if (r + rr < rb) {
-                        hrow(r + rr + K - 1, ring[(rr + K - 1) % K]);
-                        float o4[4];
-#pragma unroll
-                        for (int o = 0; o < 4; ++o) {
-                            float acc = 0.0f;
-#pragma unroll
-                            for (int u = 0; u < K; ++u) acc = fmaf(p.taps[u], ring[(rr + u) % K][o], acc);
-                            o4[o] = acc;
-                        }
-                        const int ir = r0 + r + rr;
-                        if (quad_cut && ir >= p.sh && ir < p.sh + p.ph) {
-#pragma unroll
-                            for (int o = 0; o < 4; ++o)
-                                if (j0 + o >= p.sw && j0 + o < p.sw + p.pw) o4[o] = 0.0f;
-                        }
-                        st_stream_f4(outp + (((size_t)b * C + c_) * H + ir) * W + j0, make_float4(o4[0], o4[1], o4[2], o4[3]));
-                    }
-                }
+                for (int o = 0; o < 4; ++o) if (j0 + o >= p.sw && j0 + o < sw_end) cutmask |= 1u << o;
             }
+            const float* base = tile + c_ * plane;
+            float* outq = static_cast<float*>(p.out) + ((static_cast<size_t>(b) * C + c_) * H + r0) * W + j0;
+            if (q > 0 && q < nq - 1) blur_task<K, false>(base, outq, W, j0, ra, rb, r0, taps, cutmask, p.sh, sh_end);
+            else                     blur_task<K, true>(base, outq, W, j0, ra, rb, r0, taps, cutmask, p.sh, sh_end);
         }
         return;
     }
+    // Generic path (odd widths, wide kernels, uint8 NHWC output): one column per thread.
     for (int task = tid; task < C * W; task += nth) {
         const int c_ = task / W, j = task - c_ * W;
         int jidx[K];
@@ -264,32 +311,32 @@ disturb_kernel(const __grid_constant__ DisturbParams p) {
             if (jj >= W) jj = 2 * (W - 1) - jj;
             jidx[u] = jj;
         }
-        const float* base = tile + (size_t)c_ * RS * W;
+        const float* base = tile + c_ * plane;
         float ring[K];
 #pragma unroll
         for (int lr = 0; lr < K - 1; ++lr) {
             float h = 0.0f;
 #pragma unroll
-            for (int u = 0; u < K; ++u) h = fmaf(p.taps[u], base[lr * W + jidx[u]], h);
+            for (int u = 0; u < K; ++u) h = fmaf(taps[u], base[lr * W + jidx[u]], h);
             ring[lr] = h;
         }
         const bool col_cut = do_cut && j >= p.sw && j < p.sw + p.pw;
         for (int r = 0; r < rows; ++r) {
             float h = 0.0f;
 #pragma unroll
-            for (int u = 0; u < K; ++u) h = fmaf(p.taps[u], base[(r + K - 1) * W + jidx[u]], h);
+            for (int u = 0; u < K; ++u) h = fmaf(taps[u], base[(r + K - 1) * W + jidx[u]], h);
             ring[K - 1] = h;
             float v = 0.0f;
 #pragma unroll
-            for (int u = 0; u < K; ++u) v = fmaf(p.taps[u], ring[u], v);
+            for (int u = 0; u < K; ++u) v = fmaf(taps[u], ring[u], v);
 #pragma unroll
             for (int u = 0; u < K - 1; ++u) ring[u] = ring[u + 1];
             const int ir = r0 + r;
             if (col_cut && ir >= p.sh && ir < p.sh + p.ph) v = 0.0f;
             if (p.io_mode == 0) {
-                static_cast<float*>(p.out)[(((size_t)b * C + c_) * H + ir) * W + j] = v;
+                static_cast<float*>(p.out)[((static_cast<size_t>(b) * C + c_) * H + ir) * W + j] = v;
             } else {
-                static_cast<uint8_t*>(p.out)[(((size_t)b * H + ir) * W + j) * C + c_] =
+                static_cast<uint8_t*>(p.out)[((static_cast<size_t>(b) * H + ir) * W + j) * C + c_] =
                     static_cast<uint8_t>(__fmul_rn(v, 255.0f));
             }
         }

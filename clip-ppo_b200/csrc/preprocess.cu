@@ -44,6 +44,68 @@ __device__ __forceinline__ void src_index(float scale, int dst, int in_size, int
     l1 = fminf(fmaxf(s - static_cast<float>(i0), 0.0f), 1.0f);
 }
 
+// Up-sampling path (h, w < image), patch % 8 == 0.  One CTA per (image, patch row gy), two passes:
+//   1. horizontal: the ~P*h/image + 2 source rows this patch row touches are interpolated along x
+//      into shared memory  tmp[cin][row][ox]  (x indices / weights are per-thread constants);
+//   2. vertical + normalise + bf16 + im2col: each thread blends two smem rows for 8 consecutive ox
+//      (4 x LDS.128) and writes one 16-byte chunk of the patch matrix.
+// Same association as ATen's bilinear kernel: horizontal blends first, then the vertical blend.
+__global__ void __launch_bounds__(256) preprocess_resize_kernel(const PreParams p, int max_rows) {
+    extern __shared__ __align__(16) float tmp[];
+    const int b = blockIdx.x / p.G, gy = blockIdx.x - b * p.G;
+    const int P = p.P, G = p.G, IMG = p.image;
+    const int Cin = p.C;                                       // 1 (gray, broadcast) or 3
+    const long long img_off = static_cast<long long>(b) * p.s[0];
+    int y_lo, y_hi, dummy_i; float dummy_f;
+    src_index(p.scale_h, gy * P, p.h, y_lo, dummy_i, dummy_f);
+    src_index(p.scale_h, gy * P + P - 1, p.h, dummy_i, y_hi, dummy_f);
+    const int nrows = min(y_hi - y_lo + 1, max_rows);
+    // ---- pass 1: thread = output column ----
+    for (int ox = threadIdx.x; ox < IMG; ox += blockDim.x) {
+        int x0, x1; float lx;
+        src_index(p.scale_w, ox, p.w, x0, x1, lx);
+        const float w0 = 1.0f - lx;
+        for (int c = 0; c < Cin; ++c) {
+            const long long cb = img_off + c * p.s[1];
+            for (int r = 0; r < nrows; ++r) {
+                const long long rb = cb + static_cast<long long>(y_lo + r) * p.s[2];
+                const float a = load_px(p, rb + x0 * p.s[3]), d = load_px(p, rb + x1 * p.s[3]);
+                tmp[(c * max_rows + r) * IMG + ox] = w0 * a + lx * d;
+            }
+        }
+    }
+    __syncthreads();
+    // ---- pass 2: thread = (line (c, ky), 8 consecutive ox) ----
+    const int groups = IMG >> 3;                               // 16-byte output chunks per image row
+    const int total = 3 * P * groups;
+    for (int i = threadIdx.x; i < total; i += blockDim.x) {
+        const int grp = i % groups, line = i / groups;
+        const int c = line / P, ky = line - c * P;
+        const int oy = gy * P + ky;
+        int y0, y1; float ly;
+        src_index(p.scale_h, oy, p.h, y0, y1, ly);
+        const int cin = (Cin == 1) ? 0 : c;
+        const float* r0p = tmp + (cin * max_rows + (y0 - y_lo)) * IMG + grp * 8;
+        const float* r1p = tmp + (cin * max_rows + (y1 - y_lo)) * IMG + grp * 8;
+        const float4 a0 = *reinterpret_cast<const float4*>(r0p), a1 = *reinterpret_cast<const float4*>(r0p + 4);
+        const float4 b0 = *reinterpret_cast<const float4*>(r1p), b1 = *reinterpret_cast<const float4*>(r1p + 4);
+        const float h0 = 1.0f - ly;
+        const float mean = p.normalize ? kClipMean[c] : 0.0f, stdv = p.normalize ? kClipStd[c] : 1.0f;
+        float o[8] = {h0 * a0.x + ly * b0.x, h0 * a0.y + ly * b0.y, h0 * a0.z + ly * b0.z, h0 * a0.w + ly * b0.w,
+                      h0 * a1.x + ly * b1.x, h0 * a1.y + ly * b1.y, h0 * a1.z + ly * b1.z, h0 * a1.w + ly * b1.w};
+#pragma unroll
+        for (int t = 0; t < 8; ++t) o[t] = (o[t] - mean) / stdv;
+        const int ox0 = grp * 8, gx = ox0 / P, kx0 = ox0 - gx * P;
+        __nv_bfloat16* dst = p.out + (static_cast<size_t>(b) * G * G + gy * G + gx) * p.kpad + (c * P + ky) * P + kx0;
+        uint4 pk;
+        __nv_bfloat162 q0 = __floats2bfloat162_rn(o[0], o[1]), q1 = __floats2bfloat162_rn(o[2], o[3]);
+        __nv_bfloat162 q2 = __floats2bfloat162_rn(o[4], o[5]), q3 = __floats2bfloat162_rn(o[6], o[7]);
+        pk.x = *reinterpret_cast<uint32_t*>(&q0); pk.y = *reinterpret_cast<uint32_t*>(&q1);
+        pk.z = *reinterpret_cast<uint32_t*>(&q2); pk.w = *reinterpret_cast<uint32_t*>(&q3);
+        *reinterpret_cast<uint4*>(dst) = pk;
+    }
+}
+
 // grid: (N * G) CTAs, one per (image, patch row gy); each thread produces VEC consecutive kx.
 template <int VEC, bool IDENT>
 __global__ void __launch_bounds__(256) preprocess_kernel(const PreParams p) {
@@ -156,9 +218,18 @@ int preprocess_launch(const void* images, int img_dtype, const long long strides
     const bool ident = vec8 && h == image && w == image && strides[3] == 1 && strides[0] % al == 0 &&
                        strides[1] % al == 0 && strides[2] % al == 0 &&
                        reinterpret_cast<uintptr_t>(images) % (img_dtype == CLIPPPO_IMG_U8 ? 8 : 16) == 0;
-    if (ident)
+    const int max_rows = (patch * h + image - 1) / image + 2;
+    const size_t rs_smem = static_cast<size_t>(C) * max_rows * image * sizeof(float);
+    if (ident) {
         preprocess_kernel<8, true><<<grid, 256, 0, stream>>>(p);
-    else if (vec8)
+    } else if (vec8 && image % 8 == 0 && rs_smem <= 200 * 1024) {
+        static size_t configured = 48 * 1024;
+        if (rs_smem > configured) {
+            CLIPPPO_CUDA_TRY(cudaFuncSetAttribute(preprocess_resize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            configured = 200 * 1024;
+        }
+        preprocess_resize_kernel<<<grid, 256, rs_smem, stream>>>(p, max_rows);
+    } else if (vec8)
         preprocess_kernel<8, false><<<grid, 256, 0, stream>>>(p);
     else
         preprocess_kernel<2, false><<<grid, 256, 0, stream>>>(p);
