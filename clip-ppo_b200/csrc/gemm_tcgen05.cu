@@ -36,16 +36,21 @@ constexpr int EPI_STAGE_BYTES = 32 * 32 * 4;            // one 32x32 fp32 sub-ti
 constexpr int NUM_THREADS = 128 + EPI_WARPS * 32;       // 4 control warps + 8 epilogue warps
 constexpr uint32_t TMEM_COLS = ACC_STAGES * BN;         // 512: the whole TMEM of the SM
 
-template <int MODE>
+constexpr int EPI_RESID_TMA = 5;    // internal: CLIPPPO_EPI_BIAS_RESID_F32 executed as a TMA reduce-add
+
+template <int MODE, int EPI>
 struct Cfg {
     static constexpr int CL = MODE;                                   // CTAs per cluster
-    static constexpr int STAGES = (MODE == 2) ? 6 : 4;
+    // the TMA reduce-add epilogue double-buffers its staging tile (the store engine reads smem
+    // asynchronously) and pays for it with one pipeline stage
+    static constexpr int EPI_BUFS = (EPI == EPI_RESID_TMA) ? 2 : 1;
+    static constexpr int STAGES = (MODE == 2) ? (EPI_BUFS == 2 ? 5 : 6) : (EPI_BUFS == 2 ? 3 : 4);
     static constexpr int A_STAGE_BYTES = BM * BK * 2;                 // 16 KB: my 128 rows of A
     static constexpr int B_STAGE_BYTES = (MODE == 2 ? BN / 2 : BN) * BK * 2;   // 16 KB (my W half) / 32 KB
     static constexpr int OFF_A = 0;
     static constexpr int OFF_B = OFF_A + STAGES * A_STAGE_BYTES;
     static constexpr int OFF_EPI = OFF_B + STAGES * B_STAGE_BYTES;
-    static constexpr int OFF_BAR = OFF_EPI + EPI_WARPS * EPI_STAGE_BYTES;
+    static constexpr int OFF_BAR = OFF_EPI + EPI_WARPS * EPI_BUFS * EPI_STAGE_BYTES;
     static constexpr int NUM_BARS = 2 * STAGES + 2 * ACC_STAGES;
     static constexpr int SMEM_BYTES = OFF_BAR + NUM_BARS * 8 + 16 + 1024;   // + tmem slot + alignment slack
 };
@@ -77,8 +82,8 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 template <int EPI, int MODE>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                 const GemmArgs g) {
-    using C = Cfg<MODE>;
+                 const __grid_constant__ CUtensorMap tmap_out, const GemmArgs g) {
+    using C = Cfg<MODE, EPI>;
     constexpr int CL = C::CL, STAGES = C::STAGES;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -101,6 +106,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmap_a);
         prefetch_tmap(&tmap_b);
+        if constexpr (EPI == EPI_RESID_TMA) prefetch_tmap(&tmap_out);
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
@@ -178,7 +184,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         const int e = warp - 4;
         const int q = warp & 3;                  // TMEM lane quarter this warp may access
         const int hh = e >> 2;                   // which 128-column half of the tile
-        uint8_t* stg = smem + C::OFF_EPI + e * EPI_STAGE_BYTES;
+        uint8_t* stg0 = smem + C::OFF_EPI + e * C::EPI_BUFS * EPI_STAGE_BYTES;
+        uint8_t* stg = stg0;
         int as = 0; uint32_t aphase = 0;
         for (int w = unit; w < num_work; w += num_units) {
             const int mg = w / n_tiles, n_blk = w - mg * n_tiles, m_blk = mg * CL + rank;
@@ -217,6 +224,31 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     }
                 }
                 const int col0 = n_blk * BN + hh * 128 + ch * 32;
+                if constexpr (EPI == EPI_RESID_TMA) {
+                    // X[tile] += acc + bias as a TMA reduce-add: the SM never reads the residual; the
+                    // fp32 add happens in L2 and rows >= M are clipped by the TMA unit.
+                    if (col0 < g.N) {
+                        stg = stg0 + (ch & 1) * EPI_STAGE_BYTES;       // ping-pong: chunk ch-1's store may still be reading
+                        if (lane == 0) bulk_wait_group_read<1>();      // the store issued two chunks ago has drained stg
+                        __syncwarp();
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const float4 bb = __ldg(reinterpret_cast<const float4*>(g.bias + col0 + 4 * j));   // warp-uniform
+                            float4 o;
+                            o.x = __uint_as_float(v[4 * j]) + bb.x;     o.y = __uint_as_float(v[4 * j + 1]) + bb.y;
+                            o.z = __uint_as_float(v[4 * j + 2]) + bb.z; o.w = __uint_as_float(v[4 * j + 3]) + bb.w;
+                            // thread = row; the XOR pattern is exactly the TMA 128-byte swizzle of a 32x32 fp32 box
+                            *reinterpret_cast<float4*>(stg + lane * 128 + ((j ^ (lane & 7)) << 4)) = o;
+                        }
+                        fence_proxy_async_smem();                      // generic-proxy writes -> visible to the TMA
+                        __syncwarp();
+                        if (lane == 0) {
+                            tma_reduce_add_2d(&tmap_out, smem_u32(stg), col0, row_base);
+                            bulk_commit_group();
+                        }
+                    }
+                    continue;
+                }
                 if constexpr (EPI == CLIPPPO_EPI_BIAS_BF16 || EPI == CLIPPPO_EPI_BIAS_GELU_BF16) {
                     // bias (+ QuickGELU) in the row-per-thread layout, pack to bf16, THEN transpose:
                     // the staging tile is 32 rows x 64 B, half the shared-memory traffic of fp32 staging.
@@ -296,6 +328,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             }
             if (++as == ACC_STAGES) { as = 0; aphase ^= 1; }
         }
+        if constexpr (EPI == EPI_RESID_TMA) {
+            if (lane == 0) bulk_wait_group<0>();                       // all reduce-adds issued by this warp are complete
+        }
     }
 
     tc_fence_before();
@@ -335,8 +370,9 @@ int cluster_mode() {
 }
 
 template <int EPI, int MODE>
-int launch_gemm_mode(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& g, cudaStream_t stream) {
-    using C = Cfg<MODE>;
+int launch_gemm_mode(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tout, const GemmArgs& g,
+                     cudaStream_t stream) {
+    using C = Cfg<MODE, EPI>;
     static bool configured = false;
     if (!configured) {
         CLIPPPO_CUDA_TRY(cudaFuncSetAttribute(gemm_bf16_kernel<EPI, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
@@ -360,7 +396,7 @@ int launch_gemm_mode(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArg
     void* span = nullptr;
     const bool timed = prof_timing_enabled();
     if (timed) prof_span_begin(stream, 2.0 * g.M * static_cast<double>(g.N) * g.K, &span);
-    cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<EPI, MODE>, ta, tb, g);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<EPI, MODE>, ta, tb, tout, g);
     if (timed) prof_span_end(stream, span);
     prof_count_launch();
     CLIPPPO_CUDA_TRY(e);
@@ -368,8 +404,34 @@ int launch_gemm_mode(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArg
 }
 
 template <int EPI>
-int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& g, cudaStream_t stream) {
-    return cluster_mode() == 2 ? launch_gemm_mode<EPI, 2>(ta, tb, g, stream) : launch_gemm_mode<EPI, 1>(ta, tb, g, stream);
+int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tout, const GemmArgs& g,
+                cudaStream_t stream) {
+    return cluster_mode() == 2 ? launch_gemm_mode<EPI, 2>(ta, tb, tout, g, stream)
+                               : launch_gemm_mode<EPI, 1>(ta, tb, tout, g, stream);
+}
+
+// CLIPPPO_GEMM_RESID=ldst selects the load/add/store residual epilogue instead of the TMA reduce-add
+bool resid_via_tma() {
+    static int mode = -1;
+    if (mode < 0) {
+        const char* e = getenv("CLIPPPO_GEMM_RESID");
+        mode = (e && e[0] == 'l') ? 0 : 1;
+    }
+    return mode == 1;
+}
+
+// fp32 [rows, cols] output as 32 x 32 boxes under the 128-byte swizzle (one epilogue sub-tile)
+int make_f32_out_tmap(CUtensorMap* map, void* ptr, int rows, int cols, long long ld_elems) {
+    EncodeTiledFn enc = get_encode_fn();
+    if (!enc) { last_cuda_error_ref() = static_cast<int>(cudaErrorNotSupported); return CLIPPPO_ERR_CUDA; }
+    cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+    cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld_elems) * 4};
+    cuuint32_t box[2] = {32, 32};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { last_cuda_error_ref() = 10000 + static_cast<int>(r); return CLIPPPO_ERR_CUDA; }
+    return CLIPPPO_OK;
 }
 
 }  // namespace
@@ -402,18 +464,24 @@ int gemm_bf16_launch(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N,
     switch (epilogue) {
         case CLIPPPO_EPI_BIAS_BF16:
             if (!bias) return CLIPPPO_ERR_NULL;
-            return launch_gemm<CLIPPPO_EPI_BIAS_BF16>(ta, tb, g, stream);
+            return launch_gemm<CLIPPPO_EPI_BIAS_BF16>(ta, tb, ta, g, stream);
         case CLIPPPO_EPI_BIAS_GELU_BF16:
             if (!bias) return CLIPPPO_ERR_NULL;
-            return launch_gemm<CLIPPPO_EPI_BIAS_GELU_BF16>(ta, tb, g, stream);
+            return launch_gemm<CLIPPPO_EPI_BIAS_GELU_BF16>(ta, tb, ta, g, stream);
         case CLIPPPO_EPI_BIAS_RESID_F32:
             if (!bias) return CLIPPPO_ERR_NULL;
-            return launch_gemm<CLIPPPO_EPI_BIAS_RESID_F32>(ta, tb, g, stream);
+            if (resid_via_tma()) {
+                CUtensorMap tout;
+                const int st = make_f32_out_tmap(&tout, out, M, N, ldo);
+                if (st) return st;
+                return launch_gemm<EPI_RESID_TMA>(ta, tb, tout, g, stream);
+            }
+            return launch_gemm<CLIPPPO_EPI_BIAS_RESID_F32>(ta, tb, ta, g, stream);
         case CLIPPPO_EPI_PATCH_F32:
             if (!pos || tokens < 2) return CLIPPPO_ERR_NULL;
-            return launch_gemm<CLIPPPO_EPI_PATCH_F32>(ta, tb, g, stream);
+            return launch_gemm<CLIPPPO_EPI_PATCH_F32>(ta, tb, ta, g, stream);
         case CLIPPPO_EPI_F32:
-            return launch_gemm<CLIPPPO_EPI_F32>(ta, tb, g, stream);
+            return launch_gemm<CLIPPPO_EPI_F32>(ta, tb, ta, g, stream);
     }
     return CLIPPPO_ERR_UNSUPPORTED;
 }

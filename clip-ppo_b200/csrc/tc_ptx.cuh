@@ -69,6 +69,20 @@ __device__ __forceinline__ void tma_load_2d_mcast(uint32_t dst, const CUtensorMa
         ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "h"(cta_mask), "r"(c0), "r"(c1) : "memory");
 }
 
+// 2-D tiled REDUCTION shared -> global: global[box] += smem[box] (fp32 add performed in L2; rows /
+// columns outside the tensor are clipped by the TMA unit).  Tracked by bulk async-groups.
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* m, uint32_t src, int c0, int c1) {
+    asm volatile(
+        "cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
+        ::"l"(reinterpret_cast<uint64_t>(m)), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all but the N most recent bulk groups of this thread have finished READING their smem source
+template <int N>
+__device__ __forceinline__ void bulk_wait_group_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_group() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
+
 // ---- clusters -------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;

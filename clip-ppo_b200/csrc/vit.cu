@@ -8,6 +8,8 @@
 // Residual stream X is fp32 [n*T, D]; GEMM operands are bf16.  Images are processed in chunks so
 // the activation workspace stays bounded (and mostly L2-resident) whatever N is; buffers that are
 // never live together (im2col patches / QKV / MLP hidden) share one allocation.
+#include <stdlib.h>
+
 #include <new>
 #include <vector>
 
@@ -27,9 +29,22 @@ namespace clipppo {
 
 namespace {
 
-// 501 images = 25050 token rows = 196 M-tiles = 98 CTA-pair work rows: 98 x {3, 9, 12} N-tiles fill
-// 3.97 / 11.92 / 15.89 waves of 74 CTA pairs, so no GEMM of the block ends on a nearly empty wave.
-constexpr int kChunkImages = 501;
+// 1002 images = 50100 token rows = 392 M-tiles = 196 CTA-pair work rows: 196 x {3, 9, 12} N-tiles fill
+// 7.95 / 23.8 / 31.8 waves of 74 CTA pairs, so no GEMM of the block ends on a nearly empty wave
+// (501 images gives 3.97 / 11.92 / 15.89 with twice the launches; measured 1.8 % slower end to end).
+constexpr int kDefaultChunkImages = 1002;
+
+// images per tower pass; CLIPPPO_VIT_CHUNK overrides (tuning experiments)
+int chunk_images() {
+    static int v = 0;
+    if (!v) {
+        const char* e = getenv("CLIPPPO_VIT_CHUNK");
+        const int x = e ? atoi(e) : 0;
+        v = x > 0 ? x : kDefaultChunkImages;
+    }
+    return v;
+}
+#define kChunkImages chunk_images()
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
