@@ -79,6 +79,8 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv, int n_items, int T, int 
     const uint32_t smem0 = ptx_smem(att_smem);
     const int row0 = warp * 16;
 
+    pdl_launch_dependents();
+    pdl_wait();
     int item = blockIdx.x;
     if (item < n_items) prefetch_item(qkv, item, heads, T, D, smem0, tid);
     cp_async_commit();
@@ -205,10 +207,10 @@ int attention_launch(const void* qkv_bf16, int n_images, int tokens, int heads, 
     }
     const long long items = static_cast<long long>(n_images) * heads;
     const int grid = static_cast<int>(items < kNumSMs * ATT_CTAS_PER_SM ? items : kNumSMs * ATT_CTAS_PER_SM);
-    attention_kernel<<<grid, ATT_THREADS, ATT_SMEM_BYTES, stream>>>(
-        static_cast<const __nv_bfloat16*>(qkv_bf16), static_cast<int>(items), tokens, heads,
-        static_cast<__nv_bfloat16*>(out_bf16));
-    CLIPPPO_CHECK_LAUNCH();
+    CLIPPPO_CUDA_TRY(launch_pdl(attention_kernel, grid, ATT_THREADS, ATT_SMEM_BYTES, stream, 1,
+                                static_cast<const __nv_bfloat16*>(qkv_bf16), static_cast<int>(items), tokens, heads,
+                                static_cast<__nv_bfloat16*>(out_bf16)));
+    prof_count_launch();
     return CLIPPPO_OK;
 }
 

@@ -34,6 +34,33 @@ inline int record_cuda(cudaError_t e) {
 
 inline cudaStream_t as_stream(clipppo_stream_t s) { return static_cast<cudaStream_t>(s); }
 
+// Launch with the programmatic-stream-serialization attribute (PDL) and an optional cluster size.
+// Only for kernels that call pdl_wait() before touching global memory.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              int cluster_x, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[2];
+    int n = 0;
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+    if (cluster_x > 1) {
+        attr[n].id = cudaLaunchAttributeClusterDimension;
+        attr[n].val.clusterDim.x = cluster_x;
+        attr[n].val.clusterDim.y = 1;
+        attr[n].val.clusterDim.z = 1;
+        ++n;
+    }
+    cfg.attrs = attr;
+    cfg.numAttrs = n;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 constexpr int kNumSMs = 148;   // B200: 2 dies x 74 SMs
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -53,6 +80,13 @@ __device__ __forceinline__ float block_sum(float v, float* scratch) {
     float t = (lane < nwarps) ? scratch[lane] : 0.0f;
     return warp_sum(t);
 }
+
+// Programmatic dependent launch (PDL).  Every kernel of the tower calls pdl_launch_dependents() first
+// (the next kernel of the stream may begin its prologue - barrier init, TMEM alloc, descriptor
+// prefetch - as soon as all CTAs of this one are running) and pdl_wait() before its first access to
+// global memory (blocks until the previous grid has completed and its writes are visible).
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 __device__ __forceinline__ uint32_t ptx_smem(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));

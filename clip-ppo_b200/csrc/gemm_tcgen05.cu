@@ -95,6 +95,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * STAGES + ACC_STAGES + a); };
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + C::OFF_BAR + C::NUM_BARS * 8);
 
+    pdl_launch_dependents();                  // the next kernel may start its prologue under our tail
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m_tiles = (g.M + BM - 1) / BM, n_tiles = (g.N + BN - 1) / BN;
     const int num_kb = g.K / BK;
@@ -123,6 +124,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     if constexpr (CL == 2) cluster_sync_all(); else __syncthreads();   // peer barriers are initialised too
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();                               // everything above overlapped the previous kernel; its data is needed now
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -386,13 +388,15 @@ int launch_gemm_mode(const CUtensorMap& ta, const CUtensorMap& tb, const CUtenso
     cfg.blockDim = dim3(NUM_THREADS);
     cfg.dynamicSmemBytes = C::SMEM_BYTES;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = C::CL;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = 2;
     void* span = nullptr;
     const bool timed = prof_timing_enabled();
     if (timed) prof_span_begin(stream, 2.0 * g.M * static_cast<double>(g.N) * g.K, &span);

@@ -16,6 +16,8 @@ template <int NV, typename OutT>
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* x, const float* __restrict__ gamma, const float* __restrict__ beta,
                  int rows, long long row_stride, OutT* y) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (row >= rows) return;
@@ -66,13 +68,13 @@ static int layernorm_dispatch(const float* x, const float* gamma, const float* b
     const int warps_per_block = 8;
     const unsigned grid = (rows + warps_per_block - 1) / warps_per_block;
     switch (width / 128) {
-        case 4: layernorm_kernel<4, OutT><<<grid, 256, 0, stream>>>(x, gamma, beta, rows, row_stride, y); break;
-        case 6: layernorm_kernel<6, OutT><<<grid, 256, 0, stream>>>(x, gamma, beta, rows, row_stride, y); break;
-        case 8: layernorm_kernel<8, OutT><<<grid, 256, 0, stream>>>(x, gamma, beta, rows, row_stride, y); break;
-        case 10: layernorm_kernel<10, OutT><<<grid, 256, 0, stream>>>(x, gamma, beta, rows, row_stride, y); break;
+        case 4: CLIPPPO_CUDA_TRY(launch_pdl(layernorm_kernel<4, OutT>, grid, 256, 0, stream, 1, x, gamma, beta, rows, row_stride, y)); break;
+        case 6: CLIPPPO_CUDA_TRY(launch_pdl(layernorm_kernel<6, OutT>, grid, 256, 0, stream, 1, x, gamma, beta, rows, row_stride, y)); break;
+        case 8: CLIPPPO_CUDA_TRY(launch_pdl(layernorm_kernel<8, OutT>, grid, 256, 0, stream, 1, x, gamma, beta, rows, row_stride, y)); break;
+        case 10: CLIPPPO_CUDA_TRY(launch_pdl(layernorm_kernel<10, OutT>, grid, 256, 0, stream, 1, x, gamma, beta, rows, row_stride, y)); break;
         default: return CLIPPPO_ERR_UNSUPPORTED;
     }
-    CLIPPPO_CHECK_LAUNCH();
+    prof_count_launch();
     return CLIPPPO_OK;
 }
 

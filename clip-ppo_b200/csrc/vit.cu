@@ -29,23 +29,6 @@ namespace clipppo {
 
 namespace {
 
-// 1002 images = 50100 token rows = 392 M-tiles = 196 CTA-pair work rows: 196 x {3, 9, 12} N-tiles fill
-// 7.95 / 23.8 / 31.8 waves of 74 CTA pairs, so no GEMM of the block ends on a nearly empty wave
-// (501 images gives 3.97 / 11.92 / 15.89 with twice the launches; measured 1.8 % slower end to end).
-constexpr int kDefaultChunkImages = 1002;
-
-// images per tower pass; CLIPPPO_VIT_CHUNK overrides (tuning experiments)
-int chunk_images() {
-    static int v = 0;
-    if (!v) {
-        const char* e = getenv("CLIPPPO_VIT_CHUNK");
-        const int x = e ? atoi(e) : 0;
-        v = x > 0 ? x : kDefaultChunkImages;
-    }
-    return v;
-}
-#define kChunkImages chunk_images()
-
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct Workspace {
@@ -185,10 +168,42 @@ extern "C" int clipppo_vit_destroy(clipppo_vit_t handle) {
     return CLIPPPO_OK;
 }
 
+// Images per tower pass for a batch of N.  The batch is cut into near-equal chunks (no tiny tail
+// chunk whose 90 launches are pure latency), and among the few chunk counts that keep a chunk
+// below kMaxChunkImages the one is taken whose GEMMs waste the least of their last wave of 74
+// CTA pairs (weighted by the FLOPs of the N = 768 / 2304 / 3072 GEMMs of a block).
+static int plan_chunk(const clipppo_vit_s* h, int N) {
+    const char* e = getenv("CLIPPPO_VIT_CHUNK");
+    if (e && atoi(e) > 0) return N < atoi(e) ? N : atoi(e);
+    constexpr int kMaxChunkImages = 1400;
+    if (N <= kMaxChunkImages) return N;
+    const int T = h->tokens;
+    const int kmin = (N + kMaxChunkImages - 1) / kMaxChunkImages;
+    int best = (N + kmin - 1) / kmin;
+    double best_score = -1.0;
+    for (int k = kmin; k < kmin + 4; ++k) {
+        const int c = (N + k - 1) / k;
+        double score = 0.0;
+        for (int n0 = 0; n0 < N; n0 += c) {
+            const int n = (N - n0 < c) ? (N - n0) : c;
+            const int pair_rows = ((n * T + 127) / 128 + 1) / 2;
+            auto eff = [&](int n_tiles) {
+                const double waves = pair_rows * n_tiles / 74.0;
+                return waves / static_cast<double>(static_cast<long long>(waves + 0.999999));
+            };
+            score += n * (0.41 * eff(3) + 0.25 * eff(9) + 0.34 * eff(12));
+        }
+        score /= N;
+        score -= 0.004 * (k - kmin);                 // more chunks = more launches
+        if (score > best_score) { best_score = score; best = c; }
+    }
+    return best;
+}
+
 extern "C" int clipppo_vit_workspace_bytes(clipppo_vit_t handle, int n_images, size_t* bytes) {
     if (!handle || !bytes) return CLIPPPO_ERR_NULL;
     if (n_images <= 0) return CLIPPPO_ERR_BAD_SHAPE;
-    const int n = n_images < kChunkImages ? n_images : kChunkImages;
+    const int n = plan_chunk(handle, n_images);
     *bytes = carve(handle, n, nullptr).bytes;
     return CLIPPPO_OK;
 }
@@ -203,7 +218,7 @@ extern "C" int clipppo_vit_encode(clipppo_vit_t handle, const void* images, int 
     if (reinterpret_cast<uintptr_t>(workspace) % 256) return CLIPPPO_ERR_ALIGN;
     long long s[4] = {static_cast<long long>(C) * h * w, static_cast<long long>(h) * w, w, 1};
     if (img_strides_host) for (int i = 0; i < 4; ++i) s[i] = img_strides_host[i];
-    const int chunk = N < kChunkImages ? N : kChunkImages;
+    const int chunk = plan_chunk(handle, N);
     const Workspace ws = carve(handle, chunk, workspace);
     if (ws.bytes > workspace_bytes) return CLIPPPO_ERR_WORKSPACE;
     const size_t esz = (img_dtype == CLIPPPO_IMG_U8) ? 1 : 4;

@@ -166,12 +166,13 @@ def test_embeddings_vs_oracle(native, n, hw):
 def test_chunked_batch_and_uint8_input(native):
     eng = _engine(0)
     gen = torch.Generator().manual_seed(4)
-    u8 = torch.randint(0, 256, (1100, 3, 84, 84), generator=gen, dtype=torch.uint8).cuda()    # > one 1002-image chunk
+    u8 = torch.randint(0, 256, (1500, 3, 84, 84), generator=gen, dtype=torch.uint8).cuda()    # > 1400 images: cut into chunks
     a = eng.encode(u8, pre_scale=1 / 255.0, l2norm=True)
     b = eng.encode(u8.float(), pre_scale=1 / 255.0, l2norm=True)
     assert torch.equal(a, b)
-    c = eng.encode(u8[990:1015], pre_scale=1 / 255.0, l2norm=True)
-    assert torch.equal(a[990:1015], c)
+    for lo in (490, 740, 990):                          # whatever chunk size the planner picks, a boundary is crossed
+        c = eng.encode(u8[lo:lo + 25], pre_scale=1 / 255.0, l2norm=True)
+        assert torch.equal(a[lo:lo + 25], c)
     assert torch.isfinite(a).all()
 
 
