@@ -251,6 +251,14 @@ def main():
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     launches, gemm_ms, gemm_flops, gemm_launches = C.c_longlong(), C.c_double(), C.c_double(), C.c_longlong()
     N.check(L.clipppo_prof_end(C.byref(launches), C.byref(gemm_ms), C.byref(gemm_flops), C.byref(gemm_launches)))
+    by_shape = []
+    for bi in range(64):
+        tag, bms, bfl, bn = C.c_longlong(), C.c_double(), C.c_double(), C.c_longlong()
+        if L.clipppo_prof_bucket(bi, C.byref(tag), C.byref(bms), C.byref(bfl), C.byref(bn)) != 0:
+            break
+        by_shape.append({"epilogue": tag.value >> 40, "N": (tag.value >> 20) & 0xFFFFF, "K": tag.value & 0xFFFFF,
+                         "launches": bn.value, "ms": round(bms.value, 3),
+                         "tflops": round(bfl.value / (bms.value * 1e-3) / 1e12, 1) if bms.value > 0 else 0.0})
     clocks = sampler.stop() if rank == 0 else None
     loss_value = float(loss.item())
     value = world * B * args.steps / (ms_total * 1e-3)
@@ -335,7 +343,7 @@ def main():
                      "achieved": tf_ach, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
                      "frac": tf_ach / pk["tf_sustained"], "traffic": ncu_traffic,
                      "peak_source": f"{pk['source']} bf16 sustained (kernel timed inside a long step)",
-                     "launches_timed": int(gemm_launches.value), "share_of_step": tower_share,
+                     "launches_timed": int(gemm_launches.value), "share_of_step": tower_share, "by_shape": by_shape,
                      "tower_tflops_incl_all_kernels": world * B * args.steps * FLOPS_PER_IMAGE / (ms_total * 1e-3) / 1e12 / world},
         "loss": loss_value,
     }

@@ -18,6 +18,8 @@
 //   phase 4  halo rows (reflect at the image border) copied from the owning CTA's smem
 //   phase 5  separable blur: horizontal taps from smem, vertical taps from a register ring;
 //            cutout predicate on the store                                         [HBM write]
+#include <stdlib.h>
+
 #include <cooperative_groups.h>
 
 #include "common.cuh"
@@ -38,6 +40,7 @@ struct DisturbParams {
     int sh, sw, ph, pw;
     int S, R;       // stripes per image (= cluster size), rows per stripe
     int nsplit;     // row splits of a stripe in the blur phase (balances the 4-column tasks over the CTA)
+    int p1_mode;    // phase-1 variant: 0 = register-staged loads, 1 = cp.async for x (tuning knob)
     int fast;       // x / noise contiguous NCHW fp32, W % 4 == 0, 16-byte aligned
     int io_mode;    // 0: fp32 strided in, fp32 NCHW out.  1: u8 NHWC in / u8 NHWC out.
                     // 2: fp32 (0..255) NHWC in / u8 NHWC out.
@@ -148,7 +151,7 @@ disturb_kernel(const __grid_constant__ DisturbParams p) {
 
     // ---- phase 1: stripe -> smem -----------------------------------------------------------
     float gsum = 0.0f;
-    if (p.fast) {
+    if (p.fast && p.p1_mode == 0) {
         const int n4 = (rows * W) >> 2;       // float4 per channel of this stripe (contiguous in global)
         constexpr int UNR = 4;
         for (int c_ = 0; c_ < C; ++c_) {
@@ -186,6 +189,57 @@ disturb_kernel(const __grid_constant__ DisturbParams p) {
             }
             gsum = fmaf(wc, csum, gsum);
         }
+    } else if (p.fast) {
+        // The whole stripe is requested up front: x goes straight into the tile with cp.async (no
+        // registers), the matching noise values wait in registers, NB float4 per thread at a time.
+        // One memory round trip per batch instead of one per (channel, unroll group).
+        const int n4 = (rows * W) >> 2;       // float4 per channel of this stripe (contiguous in global)
+        const int total4 = C * n4;
+        const size_t chan = static_cast<size_t>(H) * W;
+        const float* xb = static_cast<const float*>(p.x) + static_cast<size_t>(b) * C * chan + static_cast<size_t>(r0) * W;
+        const float* nb = do_noise ? p.noise + static_cast<size_t>(b) * C * chan + static_cast<size_t>(r0) * W : nullptr;
+        const uint32_t tile_s = ptx_smem(tile + P * W);
+        {
+            int c_ = 0, i = tid;
+            for (int idx = tid; idx < total4; idx += nth) {
+                while (i >= n4) { i -= n4; ++c_; }
+                cpa16(tile_s + (c_ * plane + 4 * i) * 4, xb + c_ * chan + 4 * i);
+                i += nth;
+            }
+            cpa_commit();
+        }
+        constexpr int NB = 8;
+        int c_ = 0, i = tid;
+        bool x_ready = false;
+        for (int idx0 = tid; idx0 < total4; idx0 += nth * NB) {
+            float4 nv[NB];
+            int cc[NB], ii[NB];
+#pragma unroll
+            for (int u = 0; u < NB; ++u) {
+                while (i >= n4 && c_ < C) { i -= n4; ++c_; }
+                cc[u] = c_; ii[u] = i;
+                if (idx0 + u * nth < total4 && do_noise) nv[u] = ld_stream_f4(nb + c_ * chan + 4 * i);
+                i += nth;
+            }
+            if (!x_ready) { cpa_wait_all(); x_ready = true; }    // my own copies have landed in the tile
+#pragma unroll
+            for (int u = 0; u < NB; ++u) {
+                if (idx0 + u * nth < total4) {
+                    float4* q = reinterpret_cast<float4*>(tile + cc[u] * plane + P * W) + ii[u];
+                    float4 v = *q;
+                    if (do_noise) {
+                        v.x = noisy(v.x, nv[u].x, sigma);
+                        v.y = noisy(v.y, nv[u].y, sigma);
+                        v.z = noisy(v.z, nv[u].z, sigma);
+                        v.w = noisy(v.w, nv[u].w, sigma);
+                        *q = v;
+                    }
+                    const float wc = (C == 3) ? (cc[u] == 0 ? 0.2989f : (cc[u] == 1 ? 0.587f : 0.114f)) : 1.0f;
+                    gsum = fmaf(wc, (v.x + v.y) + (v.z + v.w), gsum);
+                }
+            }
+        }
+        cpa_wait_all();
     } else {
         const int n = rows * W;
         const int total = C * n;
@@ -248,8 +302,10 @@ disturb_kernel(const __grid_constant__ DisturbParams p) {
     if (K > 1) {
         if (S > 1) cluster.sync(); else __syncthreads();
         if (rows > 0) {
-            // 2P halo rows per channel; one (channel, halo row) pair per loop trip, columns by thread
-            for (int hr_c = 0; hr_c < C * 2 * P; ++hr_c) {
+            // 2P halo rows per channel; one WARP per (channel, halo row), columns by lane - the
+            // row bookkeeping (reflect, owner CTA) is paid once per row per warp, not per thread block
+            const int hwarp = tid >> 5, hlane = tid & 31, hnw = nth >> 5;
+            for (int hr_c = hwarp; hr_c < C * 2 * P; hr_c += hnw) {
                 const int c_ = hr_c / (2 * P), hr = hr_c - c_ * (2 * P);
                 const int lr = hr < P ? hr : rows + hr;              // below the last own row
                 int ir = r0 - P + lr;                                // image row before reflection
@@ -260,10 +316,10 @@ disturb_kernel(const __grid_constant__ DisturbParams p) {
                 const float* src = ((owner == s) ? tile : cluster.map_shared_rank(tile, owner)) + c_ * plane + olr * W;
                 float* dstrow = tile + c_ * plane + lr * W;
                 if (vec4) {
-                    for (int j = tid; j < (W >> 2); j += nth)
+                    for (int j = hlane; j < (W >> 2); j += 32)
                         reinterpret_cast<float4*>(dstrow)[j] = reinterpret_cast<const float4*>(src)[j];
                 } else {
-                    for (int j = tid; j < W; j += nth) dstrow[j] = src[j];
+                    for (int j = hlane; j < W; j += 32) dstrow[j] = src[j];
                 }
             }
         }
@@ -282,8 +338,14 @@ disturb_kernel(const __grid_constant__ DisturbParams p) {
         const int rps = (rows + nsplit - 1) / nsplit;
         const int ntasks = C * nsplit * nq;
         const int sh_end = p.sh + p.ph, sw_end = p.sw + p.pw;
+        // Task order: all interior quads first, the 2 edge quads of every (channel, split) last, so a
+        // warp runs either the 128-bit interior code or the reflect-indexed edge code, never both.
+        const int nqi = nq > 2 ? nq - 2 : 0, nint = C * nsplit * nqi;
         for (int task = tid; task < ntasks; task += nth) {
-            const int q = task % nq, rest = task / nq;
+            int q, rest;
+            if (task < nint) { rest = task / nqi; q = 1 + (task - rest * nqi); }
+            else if (nq >= 2) { const int e = task - nint; rest = e >> 1; q = (e & 1) ? nq - 1 : 0; }
+            else { rest = task - nint; q = 0; }
             const int sp = rest % nsplit, c_ = rest / nsplit;
             const int ra = sp * rps, rb = min(ra + rps, rows);
             if (ra >= rb) continue;
@@ -348,6 +410,7 @@ static int launch_disturb(const DisturbParams& p, size_t smem, cudaStream_t stre
     static bool configured = false;     // opt in to > 48 KB dynamic smem once per instantiation
     if (!configured) {
         CLIPPPO_CUDA_TRY(cudaFuncSetAttribute(disturb_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        CLIPPPO_CUDA_TRY(cudaFuncSetAttribute(disturb_kernel<K>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
         configured = true;
     }
     cudaLaunchConfig_t cfg = {};
@@ -367,7 +430,16 @@ static int launch_disturb(const DisturbParams& p, size_t smem, cudaStream_t stre
     return CLIPPPO_OK;
 }
 
-static int run_disturb(DisturbParams& p, const float* k1d_host, int k, cudaStream_t stream) {
+static int env_int(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
+
+static int run_disturb(DisturbParams& p, const float* k1d_host, int k, cudaStream_t stream, int max_cluster = 0) {
+    static const int env_cl = env_int("CLIPPPO_DISTURB_MAXCL", 8), env_p1 = env_int("CLIPPPO_DISTURB_P1", 0);
+    static const int env_budget = env_int("CLIPPPO_DISTURB_SMEM_KB", 56);
+    if (max_cluster == 0) max_cluster = env_cl;
+    p.p1_mode = env_p1;
     if (p.B <= 0 || p.C <= 0 || p.H <= 0 || p.W <= 0) return CLIPPPO_ERR_BAD_SHAPE;
     if (!p.x || !p.out) return CLIPPPO_ERR_NULL;
     if ((p.stages & CLIPPPO_STAGE_NOISE) && !p.noise) return CLIPPPO_ERR_NULL;
@@ -391,10 +463,12 @@ static int run_disturb(DisturbParams& p, const float* k1d_host, int k, cudaStrea
         const int R = (p.H + S - 1) / S;
         return (size_t)(kSmemHeaderFloats + (size_t)p.C * (R + 2 * P) * p.W) * sizeof(float);
     };
-    const size_t budgets[3] = {56 * 1024, 113 * 1024, 227 * 1024};
+    // 16-CTA clusters are "non-portable" (opt-in attribute) but schedulable on B200's 16-20-SM GPCs;
+    // they bring a 224x224x3 stripe down to 48 KB, i.e. 4 resident CTAs per SM instead of 2.
+    const size_t budgets[3] = {static_cast<size_t>(env_budget) * 1024, 113 * 1024, 227 * 1024};
     int S = 0;
     for (int bi = 0; bi < 3 && !S; ++bi)
-        for (int cand = 1; cand <= 8; cand *= 2)
+        for (int cand = 1; cand <= max_cluster; cand *= 2)
             if (smem_for(cand) <= budgets[bi]) { S = cand; break; }
     if (!S) return CLIPPPO_ERR_UNSUPPORTED;
     p.S = S;
@@ -411,17 +485,22 @@ static int run_disturb(DisturbParams& p, const float* k1d_host, int k, cudaStrea
         }
     }
     const size_t smem = smem_for(S);
+    int st = CLIPPPO_ERR_UNSUPPORTED;
     switch (K) {
-        case 1:  return launch_disturb<1>(p, smem, stream);
-        case 3:  return launch_disturb<3>(p, smem, stream);
-        case 5:  return launch_disturb<5>(p, smem, stream);
-        case 7:  return launch_disturb<7>(p, smem, stream);
-        case 9:  return launch_disturb<9>(p, smem, stream);
-        case 11: return launch_disturb<11>(p, smem, stream);
-        case 13: return launch_disturb<13>(p, smem, stream);
-        case 15: return launch_disturb<15>(p, smem, stream);
+        case 1:  st = launch_disturb<1>(p, smem, stream); break;
+        case 3:  st = launch_disturb<3>(p, smem, stream); break;
+        case 5:  st = launch_disturb<5>(p, smem, stream); break;
+        case 7:  st = launch_disturb<7>(p, smem, stream); break;
+        case 9:  st = launch_disturb<9>(p, smem, stream); break;
+        case 11: st = launch_disturb<11>(p, smem, stream); break;
+        case 13: st = launch_disturb<13>(p, smem, stream); break;
+        case 15: st = launch_disturb<15>(p, smem, stream); break;
     }
-    return CLIPPPO_ERR_UNSUPPORTED;
+    if (st == CLIPPPO_ERR_CUDA && S > 8) {          // 16-CTA cluster refused on this device / partition: portable size
+        cudaGetLastError();
+        return run_disturb(p, k1d_host, k, stream, 8);
+    }
+    return st;
 }
 
 static bool is_contig_nchw(const long long s[4], int C, int H, int W) {

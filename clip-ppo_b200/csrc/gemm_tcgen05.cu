@@ -399,7 +399,8 @@ int launch_gemm_mode(const CUtensorMap& ta, const CUtensorMap& tb, const CUtenso
     cfg.numAttrs = 2;
     void* span = nullptr;
     const bool timed = prof_timing_enabled();
-    if (timed) prof_span_begin(stream, 2.0 * g.M * static_cast<double>(g.N) * g.K, &span);
+    if (timed) prof_span_begin(stream, 2.0 * g.M * static_cast<double>(g.N) * g.K,
+                               (static_cast<long long>(EPI) << 40) | (static_cast<long long>(g.N) << 20) | g.K, &span);
     cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<EPI, MODE>, ta, tb, tout, g);
     if (timed) prof_span_end(stream, span);
     prof_count_launch();

@@ -47,6 +47,8 @@ int         clipppo_last_cuda_error(void);
  * prof_end returns their summed duration (ms) and algorithmic FLOPs.  Off by default. */
 int clipppo_prof_begin(int time_gemms);
 int clipppo_prof_end(long long* launches, double* gemm_ms, double* gemm_flops, long long* gemm_launches);
+/* Per-shape totals of the last prof_end: tag = epilogue << 40 | N << 20 | K; returns non-zero past the end. */
+int clipppo_prof_bucket(int index, long long* tag, double* ms, double* flops, long long* launches);
 
 /* ------------------------------------------------------------------------------------------
  * D1  fused visual disturbance: noise -> contrast -> blur -> cutout in ONE launch.
