@@ -18,6 +18,7 @@ ERR_WORKSPACE, ERR_UNSUPPORTED, ERR_ALIGN, ERR_CUDA, ERR_DIM_MISMATCH = -5, -6, 
 STAGE_NOISE, STAGE_CONTRAST, STAGE_BLUR, STAGE_CUTOUT, STAGE_ALL = 1, 2, 4, 8, 15
 IMG_F32, IMG_U8 = 0, 1
 VIT_L2NORM, VIT_PRENORMALIZED = 1, 2
+EPI_ROWAFFINE_BF16, EPI_ROWAFFINE_GELU_BF16, EPI_RESID_BF16 = 6, 7, 8
 EPI_BIAS_BF16, EPI_BIAS_GELU_BF16, EPI_BIAS_RESID_F32, EPI_PATCH_F32, EPI_F32 = 0, 1, 2, 3, 4
 
 # every symbol the header declares; tests/test_abi.py checks the .so exports all of them
@@ -26,7 +27,7 @@ SYMBOLS = (
     "clipppo_disturb_f32", "clipppo_disturb_nhwc_u8",
     "clipppo_cosine_loss_fwd", "clipppo_cosine_loss_bwd", "clipppo_gae_f32", "clipppo_ppo_loss_f32",
     "clipppo_vit_create", "clipppo_vit_destroy", "clipppo_vit_workspace_bytes", "clipppo_vit_encode",
-    "clipppo_preprocess_bf16", "clipppo_layernorm_bf16", "clipppo_gemm_bf16", "clipppo_attention_bf16",
+    "clipppo_preprocess_bf16", "clipppo_layernorm_bf16", "clipppo_gemm_bf16", "clipppo_gemm_bf16_fused", "clipppo_gemm_bf16_probe", "clipppo_rowstats_bf16", "clipppo_attention_bf16",
 )
 
 
@@ -38,14 +39,14 @@ class VitConfig(C.Structure):
     _fields_ = [(n, C.c_int) for n in ("width", "layers", "heads", "patch", "image", "out_dim")]
 
 
-class VitLayer(C.Structure):
-    _fields_ = [(n, C.c_void_p) for n in ("w_qkv", "b_qkv", "w_out", "b_out", "w_fc", "b_fc", "w_proj", "b_proj",
-                                          "ln1_g", "ln1_b", "ln2_g", "ln2_b")]
+class VitLayer(C.Structure):          # fp32 device pointers, openai/CLIP state-dict layout (include/clipppo_b200.h)
+    _fields_ = [(n, C.c_void_p) for n in ("ln1_g", "ln1_b", "w_qkv", "b_qkv", "w_out", "b_out",
+                                          "ln2_g", "ln2_b", "w_fc", "b_fc", "w_proj", "b_proj")]
 
 
 class VitWeights(C.Structure):
-    _fields_ = [(n, C.c_void_p) for n in ("w_patch", "cls_pos0", "pos", "ln_pre_g", "ln_pre_b", "ln_post_g",
-                                          "ln_post_b", "w_head")] + [("layers_host", C.POINTER(VitLayer))]
+    _fields_ = [(n, C.c_void_p) for n in ("conv1", "class_embedding", "positional_embedding", "ln_pre_g", "ln_pre_b",
+                                          "ln_post_g", "ln_post_b", "proj")] + [("layers_host", C.POINTER(VitLayer))]
 
 
 _lib = None
@@ -82,6 +83,9 @@ def lib() -> C.CDLL:
     L.clipppo_preprocess_bf16.argtypes = [vp, i, i64p, i, i, i, i, f, i, i, i, vp, vp]
     L.clipppo_layernorm_bf16.argtypes = [vp, vp, vp, i, i, C.c_int64, vp, vp]
     L.clipppo_gemm_bf16.argtypes = [vp, vp, i, i, i, i, vp, vp, i, vp, C.c_int64, vp]
+    L.clipppo_gemm_bf16_fused.argtypes = [vp, vp, i, i, i, i, vp, vp, vp, vp, C.c_int64, vp]
+    L.clipppo_rowstats_bf16.argtypes = [vp, i, i, C.c_int64, vp, vp]
+    L.clipppo_gemm_bf16_probe.argtypes = [vp, vp, i, i, i, i, vp, vp, C.c_int64, i, vp]
     L.clipppo_attention_bf16.argtypes = [vp, i, i, i, i, vp, vp]
     for name in SYMBOLS:
         fn = getattr(L, name)

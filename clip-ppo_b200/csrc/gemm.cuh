@@ -13,7 +13,8 @@ int gemm_a_box_rows();
 int gemm_b_box_rows();
 
 int gemm_bf16_launch(const CUtensorMap& tmap_a, const CUtensorMap& tmap_w, int M, int N, int K, int epilogue,
-                     const float* bias, const float* pos, int tokens, void* out, long long ldo, cudaStream_t stream);
+                     const float* bias, const float* pos, int tokens, void* out, long long ldo, cudaStream_t stream,
+                     const float* row_stats = nullptr, const float* colsum = nullptr);
 
 // tower building blocks (preprocess.cu / layernorm.cu / attention.cu)
 int preprocess_launch(const void* images, int img_dtype, const long long strides[4], int N, int C, int h, int w,
@@ -22,6 +23,9 @@ int layernorm_launch(const float* x, const float* gamma, const float* beta, int 
                      long long row_stride, void* y_bf16, cudaStream_t stream);
 int layernorm_inplace_f32_launch(float* x, const float* gamma, const float* beta, int rows, int width,
                                  long long row_stride, cudaStream_t stream);
+int layernorm_bf16in_launch(const void* x_bf16, const float* gamma, const float* beta, int rows, int width,
+                            long long row_stride, void* y_bf16, cudaStream_t stream);
+int rowstats_launch(const void* x_bf16, int rows, int width, long long row_stride, float* stats, cudaStream_t stream);
 int attention_launch(const void* qkv_bf16, int n_images, int tokens, int heads, int head_dim, void* out_bf16,
                      cudaStream_t stream);
 

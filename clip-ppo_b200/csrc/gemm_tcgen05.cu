@@ -38,12 +38,18 @@ constexpr uint32_t TMEM_COLS = ACC_STAGES * BN;         // 512: the whole TMEM o
 
 constexpr int EPI_RESID_TMA = 5;    // internal: CLIPPPO_EPI_BIAS_RESID_F32 executed as a TMA reduce-add
 
+// bf16 outputs that leave through the TMA unit (store, or reduce-add into the bf16 residual stream):
+// the epilogue warps only write a swizzled 32 x 64 staging tile; no LDS / STG on the SM.
+constexpr bool is_bf16_tma(int epi) {
+    return epi == CLIPPPO_EPI_ROWAFFINE_BF16 || epi == CLIPPPO_EPI_ROWAFFINE_GELU_BF16 || epi == CLIPPPO_EPI_RESID_BF16;
+}
+
 template <int MODE, int EPI>
 struct Cfg {
     static constexpr int CL = MODE;                                   // CTAs per cluster
     // the TMA reduce-add epilogue double-buffers its staging tile (the store engine reads smem
     // asynchronously) and pays for it with one pipeline stage
-    static constexpr int EPI_BUFS = (EPI == EPI_RESID_TMA) ? 2 : 1;
+    static constexpr int EPI_BUFS = (EPI == EPI_RESID_TMA || is_bf16_tma(EPI)) ? 2 : 1;
     static constexpr int STAGES = (MODE == 2) ? (EPI_BUFS == 2 ? 5 : 6) : (EPI_BUFS == 2 ? 3 : 4);
     static constexpr int A_STAGE_BYTES = BM * BK * 2;                 // 16 KB: my 128 rows of A
     static constexpr int B_STAGE_BYTES = (MODE == 2 ? BN / 2 : BN) * BK * 2;   // 16 KB (my W half) / 32 KB
@@ -62,6 +68,8 @@ struct GemmArgs {
     int tokens;            // EPI_PATCH: tokens per image (patch rows + 1)
     void* out;
     long long ldo;         // elements
+    const float2* stats;   // ROWAFFINE: per-row (mean, rstd) of the un-normalised A rows, or null (=> 0, 1)
+    const float* colsum;   // ROWAFFINE: s[n] = sum_k W[n,k] (LayerNorm gamma already folded into W)
 };
 
 // QuickGELU x * sigmoid(1.702 x) = 0.5 x (1 + tanh(0.851 x)): one MUFU op (tanh.approx, rel. error
@@ -79,7 +87,9 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
     return *reinterpret_cast<uint32_t*>(&h);
 }
 
-template <int EPI, int MODE>
+// DBG (probe builds only, never on the product path): bit 0 = the epilogue drains TMEM but neither
+// computes nor stores, bit 1 = the producer signals "stage full" without issuing the TMA loads.
+template <int EPI, int MODE, int DBG = 0>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const __grid_constant__ CUtensorMap tmap_out, const GemmArgs g) {
@@ -107,7 +117,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmap_a);
         prefetch_tmap(&tmap_b);
-        if constexpr (EPI == EPI_RESID_TMA) prefetch_tmap(&tmap_out);
+        if constexpr (EPI == EPI_RESID_TMA || is_bf16_tma(EPI)) prefetch_tmap(&tmap_out);
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
@@ -136,7 +146,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     mbar_wait(empty_bar(stage), phase ^ 1);
                     const uint32_t sa = sbase + C::OFF_A + stage * C::A_STAGE_BYTES;
                     const uint32_t sb = sbase + C::OFF_B + stage * C::B_STAGE_BYTES;
-                    if constexpr (CL == 2) {
+                    if constexpr ((DBG & 2) != 0) {
+                        if (rank == 0) mbar_arrive(full_bar(stage));
+                    } else if constexpr (CL == 2) {
                         // the leader's barrier expects both CTAs' A tile and W half
                         if (rank == 0) mbar_arrive_expect_tx(full_bar(stage), 2 * (C::A_STAGE_BYTES + C::B_STAGE_BYTES));
                         tma_load_2d_2sm(sa, &tmap_a, full_bar(stage), kb * BK, m_blk * BM);
@@ -192,6 +204,91 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         for (int w = unit; w < num_work; w += num_units) {
             const int mg = w / n_tiles, n_blk = w - mg * n_tiles, m_blk = mg * CL + rank;
             const int row_base = m_blk * BM + q * 32;
+            if constexpr (is_bf16_tma(EPI)) {
+                // thread = accumulator row.  Two 64-column chunks per warp and tile; each becomes one
+                // 32 x 64 bf16 box (128-byte rows under the TMA 128-byte swizzle) that the TMA unit
+                // stores - or adds into the bf16 residual stream - while the warp drains the next chunk.
+                //   ROWAFFINE: out = rstd_row * (acc - mean_row * colsum_col) + bias_col   [+ QuickGELU]
+                //   is LayerNorm folded through the GEMM: A holds the UN-normalised rows, gamma lives
+                //   in W, beta in the bias; with stats == null it is the plain bias epilogue.
+                float mean = 0.0f, rstd = 1.0f;
+                if constexpr (EPI != CLIPPPO_EPI_RESID_BF16) {
+                    if (g.stats != nullptr && row_base + lane < g.M) {
+                        const float2 st = __ldg(g.stats + row_base + lane);
+                        mean = st.x; rstd = st.y;
+                    }
+                }
+                const float nmean = -mean;
+                mbar_wait(tfull_bar(as), aphase);
+                tc_fence_after();
+                const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN + hh * 128;
+#pragma unroll
+                for (int ch = 0; ch < 2; ++ch) {
+                    uint32_t v[2][32];
+                    tmem_ld_32x32(trow + ch * 64, v[0]);
+                    tmem_ld_32x32(trow + ch * 64 + 32, v[1]);
+                    tmem_ld_wait();
+                    if (ch == 1) {                   // all TMEM reads of this tile done: hand it back
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) {
+                            if constexpr (CL == 2) mbar_arrive_leader(tempty_bar(as)); else mbar_arrive(tempty_bar(as));
+                        }
+                    }
+                    if constexpr ((DBG & 1) != 0) {
+                        if (v[0][0] == 0x7fc12345u && v[1][31] == 0x7fc54321u) static_cast<float*>(g.out)[0] = 1.0f;
+                        continue;
+                    }
+                    const int col0 = n_blk * BN + hh * 128 + ch * 64;
+                    if (col0 < g.N) {
+                        uint8_t* buf = stg0 + (ch & 1) * EPI_STAGE_BYTES;
+                        if (lane == 0) bulk_wait_group_read<1>();      // the box issued two chunks ago has left buf
+                        __syncwarp();
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {                  // 16-byte piece j = columns 8j .. 8j+7
+                            const uint32_t* vv = &v[j >> 2][(j & 3) * 8];
+                            const float4 b0 = __ldg(reinterpret_cast<const float4*>(g.bias + col0 + 8 * j));      // warp-uniform
+                            const float4 b1 = __ldg(reinterpret_cast<const float4*>(g.bias + col0 + 8 * j + 4));
+                            float o[8];
+                            if constexpr (EPI == CLIPPPO_EPI_RESID_BF16) {
+                                o[0] = __uint_as_float(vv[0]) + b0.x; o[1] = __uint_as_float(vv[1]) + b0.y;
+                                o[2] = __uint_as_float(vv[2]) + b0.z; o[3] = __uint_as_float(vv[3]) + b0.w;
+                                o[4] = __uint_as_float(vv[4]) + b1.x; o[5] = __uint_as_float(vv[5]) + b1.y;
+                                o[6] = __uint_as_float(vv[6]) + b1.z; o[7] = __uint_as_float(vv[7]) + b1.w;
+                            } else {
+                                float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0;
+                                if (g.colsum != nullptr) {
+                                    s0 = __ldg(reinterpret_cast<const float4*>(g.colsum + col0 + 8 * j));
+                                    s1 = __ldg(reinterpret_cast<const float4*>(g.colsum + col0 + 8 * j + 4));
+                                }
+                                o[0] = fmaf(rstd, fmaf(nmean, s0.x, __uint_as_float(vv[0])), b0.x);
+                                o[1] = fmaf(rstd, fmaf(nmean, s0.y, __uint_as_float(vv[1])), b0.y);
+                                o[2] = fmaf(rstd, fmaf(nmean, s0.z, __uint_as_float(vv[2])), b0.z);
+                                o[3] = fmaf(rstd, fmaf(nmean, s0.w, __uint_as_float(vv[3])), b0.w);
+                                o[4] = fmaf(rstd, fmaf(nmean, s1.x, __uint_as_float(vv[4])), b1.x);
+                                o[5] = fmaf(rstd, fmaf(nmean, s1.y, __uint_as_float(vv[5])), b1.y);
+                                o[6] = fmaf(rstd, fmaf(nmean, s1.z, __uint_as_float(vv[6])), b1.z);
+                                o[7] = fmaf(rstd, fmaf(nmean, s1.w, __uint_as_float(vv[7])), b1.w);
+                                if constexpr (EPI == CLIPPPO_EPI_ROWAFFINE_GELU_BF16) {
+#pragma unroll
+                                    for (int t = 0; t < 8; ++t) o[t] = quick_gelu(o[t]);
+                                }
+                            }
+                            // the XOR is the TMA 128-byte swizzle of a box with 128-byte rows; conflict-free STS.128
+                            *reinterpret_cast<uint4*>(buf + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+                                make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7]));
+                        }
+                        fence_proxy_async_smem();                      // generic-proxy writes -> visible to the TMA
+                        __syncwarp();
+                        if (lane == 0) {
+                            if constexpr (EPI == CLIPPPO_EPI_RESID_BF16) tma_reduce_add_2d(&tmap_out, smem_u32(buf), col0, row_base);
+                            else tma_store_2d(&tmap_out, smem_u32(buf), col0, row_base);
+                            bulk_commit_group();
+                        }
+                    }
+                }
+                if (++as == ACC_STAGES) { as = 0; aphase ^= 1; }
+            } else {
             // RESID: the fp32 residual sub-tile of chunk ch+1 is fetched while chunk ch is drained
             // from TMEM (and chunk 0 while the MMAs of this tile are still running).
             float4 xres[2][8];
@@ -226,6 +323,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     }
                 }
                 const int col0 = n_blk * BN + hh * 128 + ch * 32;
+                if constexpr ((DBG & 1) != 0) {
+                    if (v[0] == 0x7fc12345u && v[31] == 0x7fc54321u) static_cast<float*>(g.out)[0] = 1.0f;   // keep the loads alive
+                    continue;
+                }
                 if constexpr (EPI == EPI_RESID_TMA) {
                     // X[tile] += acc + bias as a TMA reduce-add: the SM never reads the residual; the
                     // fp32 add happens in L2 and rows >= M are clipped by the TMA unit.
@@ -329,9 +430,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 __syncwarp();                    // staging buffer is reused by the next chunk
             }
             if (++as == ACC_STAGES) { as = 0; aphase ^= 1; }
+            }   // legacy (non-TMA-output) epilogues
         }
-        if constexpr (EPI == EPI_RESID_TMA) {
-            if (lane == 0) bulk_wait_group<0>();                       // all reduce-adds issued by this warp are complete
+        if constexpr (EPI == EPI_RESID_TMA || is_bf16_tma(EPI)) {
+            if (lane == 0) bulk_wait_group<0>();                       // all boxes issued by this warp are complete
         }
     }
 
@@ -371,13 +473,13 @@ int cluster_mode() {
     return mode;
 }
 
-template <int EPI, int MODE>
+template <int EPI, int MODE, int DBG = 0>
 int launch_gemm_mode(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tout, const GemmArgs& g,
                      cudaStream_t stream) {
     using C = Cfg<MODE, EPI>;
     static bool configured = false;
     if (!configured) {
-        CLIPPPO_CUDA_TRY(cudaFuncSetAttribute(gemm_bf16_kernel<EPI, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+        CLIPPPO_CUDA_TRY(cudaFuncSetAttribute(gemm_bf16_kernel<EPI, MODE, DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
         configured = true;
     }
     const int m_tiles = (g.M + BM - 1) / BM, n_tiles = (g.N + BN - 1) / BN;
@@ -401,7 +503,7 @@ int launch_gemm_mode(const CUtensorMap& ta, const CUtensorMap& tb, const CUtenso
     const bool timed = prof_timing_enabled();
     if (timed) prof_span_begin(stream, 2.0 * g.M * static_cast<double>(g.N) * g.K,
                                (static_cast<long long>(EPI) << 40) | (static_cast<long long>(g.N) << 20) | g.K, &span);
-    cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<EPI, MODE>, ta, tb, tout, g);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<EPI, MODE, DBG>, ta, tb, tout, g);
     if (timed) prof_span_end(stream, span);
     prof_count_launch();
     CLIPPPO_CUDA_TRY(e);
@@ -439,6 +541,20 @@ int make_f32_out_tmap(CUtensorMap* map, void* ptr, int rows, int cols, long long
     return CLIPPPO_OK;
 }
 
+// bf16 [rows, cols] output as 32-row x 64-column boxes (128-byte rows) under the 128-byte swizzle
+int make_bf16_out_tmap(CUtensorMap* map, void* ptr, int rows, int cols, long long ld_elems) {
+    EncodeTiledFn enc = get_encode_fn();
+    if (!enc) { last_cuda_error_ref() = static_cast<int>(cudaErrorNotSupported); return CLIPPPO_ERR_CUDA; }
+    cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+    cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld_elems) * 2};
+    cuuint32_t box[2] = {64, 32};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { last_cuda_error_ref() = 10000 + static_cast<int>(r); return CLIPPPO_ERR_CUDA; }
+    return CLIPPPO_OK;
+}
+
 }  // namespace
 
 int make_bf16_kmajor_tmap(CUtensorMap* map, const void* ptr, int rows, int K, long long ld_elems, int box_rows) {
@@ -456,16 +572,60 @@ int make_bf16_kmajor_tmap(CUtensorMap* map, const void* ptr, int rows, int K, lo
     return CLIPPPO_OK;
 }
 
+// Probe-only dispatcher (clipppo_gemm_bf16_probe): pair mode, the three hot epilogues, DBG 1..3.
+template <int DBG>
+int launch_gemm_dbg(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& g, int epilogue, cudaStream_t stream) {
+    if (epilogue == CLIPPPO_EPI_BIAS_BF16) return launch_gemm_mode<CLIPPPO_EPI_BIAS_BF16, 2, DBG>(ta, tb, ta, g, stream);
+    if (epilogue == CLIPPPO_EPI_BIAS_GELU_BF16) return launch_gemm_mode<CLIPPPO_EPI_BIAS_GELU_BF16, 2, DBG>(ta, tb, ta, g, stream);
+    if (is_bf16_tma(epilogue)) {
+        CUtensorMap tout;
+        const int st = make_bf16_out_tmap(&tout, g.out, g.M, g.N, g.ldo);
+        if (st) return st;
+        if (epilogue == CLIPPPO_EPI_ROWAFFINE_BF16) return launch_gemm_mode<CLIPPPO_EPI_ROWAFFINE_BF16, 2, DBG>(ta, tb, tout, g, stream);
+        if (epilogue == CLIPPPO_EPI_ROWAFFINE_GELU_BF16) return launch_gemm_mode<CLIPPPO_EPI_ROWAFFINE_GELU_BF16, 2, DBG>(ta, tb, tout, g, stream);
+        return launch_gemm_mode<CLIPPPO_EPI_RESID_BF16, 2, DBG>(ta, tb, tout, g, stream);
+    }
+    if (epilogue == CLIPPPO_EPI_BIAS_RESID_F32) {
+        CUtensorMap tout;
+        const int st = make_f32_out_tmap(&tout, g.out, g.M, g.N, g.ldo);
+        if (st) return st;
+        return launch_gemm_mode<EPI_RESID_TMA, 2, DBG>(ta, tb, tout, g, stream);
+    }
+    return CLIPPPO_ERR_UNSUPPORTED;
+}
+
+int gemm_probe_launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& g, int epilogue, int dbg, cudaStream_t stream) {
+    switch (dbg) {
+        case 1: return launch_gemm_dbg<1>(ta, tb, g, epilogue, stream);
+        case 2: return launch_gemm_dbg<2>(ta, tb, g, epilogue, stream);
+        case 3: return launch_gemm_dbg<3>(ta, tb, g, epilogue, stream);
+    }
+    return CLIPPPO_ERR_UNSUPPORTED;
+}
+
 int gemm_a_box_rows() { return BM; }
 int gemm_b_box_rows() { return BN / 2; }   // W is fetched as two 128-row halves (one per CTA of a pair)
 
 int gemm_bf16_launch(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, int epilogue,
-                     const float* bias, const float* pos, int tokens, void* out, long long ldo, cudaStream_t stream) {
+                     const float* bias, const float* pos, int tokens, void* out, long long ldo, cudaStream_t stream,
+                     const float* row_stats, const float* colsum) {
     if (M <= 0 || N <= 0 || K <= 0 || (K % BK) || (N % 32)) return CLIPPPO_ERR_BAD_SHAPE;
     if (!out) return CLIPPPO_ERR_NULL;
-    GemmArgs g{M, N, K, bias, pos, tokens, out, ldo};
-    const bool bf16_out = epilogue == CLIPPPO_EPI_BIAS_BF16 || epilogue == CLIPPPO_EPI_BIAS_GELU_BF16;
+    GemmArgs g{M, N, K, bias, pos, tokens, out, ldo, reinterpret_cast<const float2*>(row_stats), colsum};
+    const bool bf16_out = epilogue == CLIPPPO_EPI_BIAS_BF16 || epilogue == CLIPPPO_EPI_BIAS_GELU_BF16 || is_bf16_tma(epilogue);
     if ((reinterpret_cast<uintptr_t>(out) & 15) || ((ldo * (bf16_out ? 2 : 4)) & 15)) return CLIPPPO_ERR_ALIGN;
+    if (is_bf16_tma(epilogue)) {
+        if (!bias) return CLIPPPO_ERR_NULL;
+        if (N % 64) return CLIPPPO_ERR_BAD_SHAPE;                       // 64-column output boxes
+        if ((row_stats != nullptr) != (colsum != nullptr)) return CLIPPPO_ERR_NULL;
+        if (row_stats && (reinterpret_cast<uintptr_t>(row_stats) & 7)) return CLIPPPO_ERR_ALIGN;
+        CUtensorMap tout;
+        const int st = make_bf16_out_tmap(&tout, out, M, N, ldo);
+        if (st) return st;
+        if (epilogue == CLIPPPO_EPI_ROWAFFINE_BF16) return launch_gemm<CLIPPPO_EPI_ROWAFFINE_BF16>(ta, tb, tout, g, stream);
+        if (epilogue == CLIPPPO_EPI_ROWAFFINE_GELU_BF16) return launch_gemm<CLIPPPO_EPI_ROWAFFINE_GELU_BF16>(ta, tb, tout, g, stream);
+        return launch_gemm<CLIPPPO_EPI_RESID_BF16>(ta, tb, tout, g, stream);
+    }
     switch (epilogue) {
         case CLIPPPO_EPI_BIAS_BF16:
             if (!bias) return CLIPPPO_ERR_NULL;
@@ -505,5 +665,36 @@ extern "C" int clipppo_gemm_bf16(const void* a_bf16, const void* w_bf16, int M, 
     if (st) return st;
     st = make_bf16_kmajor_tmap(&tb, w_bf16, N, K, K, gemm_b_box_rows());
     if (st) return st;
-    return gemm_bf16_launch(ta, tb, M, N, K, epilogue, bias, pos, tokens, out, ldo, as_stream(stream));
+    return gemm_bf16_launch(ta, tb, M, N, K, epilogue, bias, pos, tokens, out, ldo, as_stream(stream), nullptr, nullptr);
+}
+
+extern "C" int clipppo_gemm_bf16_fused(const void* a_bf16, const void* w_bf16, int M, int N, int K, int epilogue,
+                                       const float* bias, const float* row_stats, const float* colsum,
+                                       void* out_bf16, int64_t ldo, clipppo_stream_t stream) {
+    if (!a_bf16 || !w_bf16) return CLIPPPO_ERR_NULL;
+    if (M <= 0 || N <= 0 || K <= 0 || (K % 64)) return CLIPPPO_ERR_BAD_SHAPE;
+    if (epilogue != CLIPPPO_EPI_ROWAFFINE_BF16 && epilogue != CLIPPPO_EPI_ROWAFFINE_GELU_BF16 && epilogue != CLIPPPO_EPI_RESID_BF16)
+        return CLIPPPO_ERR_UNSUPPORTED;
+    CUtensorMap ta, tb;
+    int st = make_bf16_kmajor_tmap(&ta, a_bf16, M, K, K, gemm_a_box_rows());
+    if (st) return st;
+    st = make_bf16_kmajor_tmap(&tb, w_bf16, N, K, K, gemm_b_box_rows());
+    if (st) return st;
+    return gemm_bf16_launch(ta, tb, M, N, K, epilogue, bias, nullptr, 0, out_bf16, ldo, as_stream(stream), row_stats, colsum);
+}
+
+// Measurement probe, not part of the product path: the same GEMM with parts of the kernel switched
+// off (dbg bit 0: epilogue only drains TMEM; bit 1: no TMA loads), to attribute time to the TMA feed,
+// the MMA issue and the epilogue.  Results are garbage by construction.
+extern "C" int clipppo_gemm_bf16_probe(const void* a_bf16, const void* w_bf16, int M, int N, int K, int epilogue,
+                                       const float* bias, void* out, int64_t ldo, int dbg, clipppo_stream_t stream) {
+    if (!a_bf16 || !w_bf16 || !out || !bias) return CLIPPPO_ERR_NULL;
+    if (M <= 0 || N <= 0 || K <= 0 || (K % 64) || (N % 32)) return CLIPPPO_ERR_BAD_SHAPE;
+    CUtensorMap ta, tb;
+    int st = make_bf16_kmajor_tmap(&ta, a_bf16, M, K, K, gemm_a_box_rows());
+    if (st) return st;
+    st = make_bf16_kmajor_tmap(&tb, w_bf16, N, K, K, gemm_b_box_rows());
+    if (st) return st;
+    GemmArgs g{M, N, K, bias, nullptr, 0, out, ldo, nullptr, nullptr};
+    return gemm_probe_launch(ta, tb, g, epilogue, dbg, as_stream(stream));
 }

@@ -1,8 +1,13 @@
-// V2 - LayerNorm over the fp32 residual stream, bf16 output for the next GEMM's A operand.
+// V2 - LayerNorm of the tower.
 //
 // Replaces [clip] LayerNorm (fp32 upcast -> F.layer_norm(eps=1e-5) -> downcast) as used for
-// ln_pre / ln_1 / ln_2 / ln_post in VisionTransformer.forward.  One warp per row, the row is held
-// in registers (two-pass mean / biased variance like ATen), 128-bit loads, 64-bit bf16 stores.
+// ln_pre / ln_1 / ln_2 / ln_post in VisionTransformer.forward.
+//   layernorm_kernel  ln_pre (fp32 patch-embed rows -> bf16 residual stream) and ln_post (bf16 CLS rows):
+//                     one warp per row, the row is held in registers (two-pass mean / biased variance
+//                     like ATen), 128-bit loads, 64-bit bf16 stores.
+//   rowstats_kernel   ln_1 / ln_2 are folded through the GEMM that consumes them (gemm_tcgen05.cu,
+//                     ROWAFFINE epilogue); all that is left of them is the per-row (mean, rstd) of the
+//                     bf16 residual stream: 1.5 KB read and 8 B written per row.
 #include "common.cuh"
 #include "gemm.cuh"
 
@@ -12,9 +17,53 @@ namespace {
 
 // width = NV * 128; lane owns float4 chunks lane, lane+32, ...
 // OutT = __nv_bfloat16 (dense rows of `width`) or float (written back in place over x: ln_pre).
-template <int NV, typename OutT>
+__device__ __forceinline__ float4 load4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float4 load4(const __nv_bfloat16* p) {
+    const uint2 u = *reinterpret_cast<const uint2*>(p);
+    const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
+    const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+    return make_float4(a.x, a.y, b.x, b.y);
+}
+
+// Per-row (mean, 1/sqrt(biased var + 1e-5)) of bf16 rows of width NV*256; lane owns 8-element pieces
+// lane, lane+32, ...  Two passes over registers: exact mean first, then centred squares.
+template <int NV>
 __global__ void __launch_bounds__(256)
-layernorm_kernel(const float* x, const float* __restrict__ gamma, const float* __restrict__ beta,
+rowstats_kernel(const __nv_bfloat16* __restrict__ x, int rows, long long row_stride, float2* __restrict__ stats) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    constexpr int width = NV * 256;
+    const uint4* xr = reinterpret_cast<const uint4*>(x + static_cast<size_t>(row) * row_stride);
+    float v[NV][8];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const uint4 u = xr[lane + 32 * i];
+        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[t]));
+            v[i][2 * t] = f.x; v[i][2 * t + 1] = f.y;
+        }
+        s += ((v[i][0] + v[i][1]) + (v[i][2] + v[i][3])) + ((v[i][4] + v[i][5]) + (v[i][6] + v[i][7]));
+    }
+    const float mean = warp_sum(s) * (1.0f / width);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+#pragma unroll
+        for (int t = 0; t < 8; ++t) { const float d = v[i][t] - mean; q = fmaf(d, d, q); }
+    }
+    const float rstd = rsqrtf(warp_sum(q) * (1.0f / width) + 1e-5f);
+    if (lane == 0) stats[row] = make_float2(mean, rstd);
+}
+
+template <int NV, typename OutT, typename InT = float>
+__global__ void __launch_bounds__(256)
+layernorm_kernel(const InT* x, const float* __restrict__ gamma, const float* __restrict__ beta,
                  int rows, long long row_stride, OutT* y) {
     pdl_launch_dependents();
     pdl_wait();
@@ -22,12 +71,12 @@ layernorm_kernel(const float* x, const float* __restrict__ gamma, const float* _
     const int lane = threadIdx.x & 31;
     if (row >= rows) return;
     constexpr int width = NV * 128;
-    const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * row_stride);
+    const InT* xr = x + static_cast<size_t>(row) * row_stride;
     float4 v[NV];
     float s = 0.f;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
-        v[i] = xr[lane + 32 * i];
+        v[i] = load4(xr + 4 * (lane + 32 * i));
         s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
     }
     const float mean = warp_sum(s) * (1.0f / width);
@@ -97,7 +146,52 @@ int layernorm_launch(const float* x, const float* gamma, const float* beta, int 
                                              static_cast<__nv_bfloat16*>(y_bf16), stream);
 }
 
+// ln_post: bf16 rows (the CLS token of every image, row_stride = T*D) -> dense bf16 rows
+int layernorm_bf16in_launch(const void* x_bf16, const float* gamma, const float* beta, int rows, int width,
+                            long long row_stride, void* y_bf16, cudaStream_t stream) {
+    if (!x_bf16 || !gamma || !beta || !y_bf16) return CLIPPPO_ERR_NULL;
+    if (rows <= 0 || width <= 0) return CLIPPPO_ERR_BAD_SHAPE;
+    if (width % 128 || (row_stride % 4) || (reinterpret_cast<uintptr_t>(x_bf16) % 8) || (reinterpret_cast<uintptr_t>(y_bf16) % 8))
+        return CLIPPPO_ERR_ALIGN;
+    const __nv_bfloat16* x = static_cast<const __nv_bfloat16*>(x_bf16);
+    __nv_bfloat16* y = static_cast<__nv_bfloat16*>(y_bf16);
+    const unsigned grid = (rows + 7) / 8;
+    switch (width / 128) {
+        case 4: CLIPPPO_CUDA_TRY(launch_pdl(layernorm_kernel<4, __nv_bfloat16, __nv_bfloat16>, grid, 256, 0, stream, 1, x, gamma, beta, rows, row_stride, y)); break;
+        case 6: CLIPPPO_CUDA_TRY(launch_pdl(layernorm_kernel<6, __nv_bfloat16, __nv_bfloat16>, grid, 256, 0, stream, 1, x, gamma, beta, rows, row_stride, y)); break;
+        case 8: CLIPPPO_CUDA_TRY(launch_pdl(layernorm_kernel<8, __nv_bfloat16, __nv_bfloat16>, grid, 256, 0, stream, 1, x, gamma, beta, rows, row_stride, y)); break;
+        case 10: CLIPPPO_CUDA_TRY(launch_pdl(layernorm_kernel<10, __nv_bfloat16, __nv_bfloat16>, grid, 256, 0, stream, 1, x, gamma, beta, rows, row_stride, y)); break;
+        default: return CLIPPPO_ERR_UNSUPPORTED;
+    }
+    prof_count_launch();
+    return CLIPPPO_OK;
+}
+
+int rowstats_launch(const void* x_bf16, int rows, int width, long long row_stride, float* stats, cudaStream_t stream) {
+    if (!x_bf16 || !stats) return CLIPPPO_ERR_NULL;
+    if (rows <= 0 || width <= 0) return CLIPPPO_ERR_BAD_SHAPE;
+    if (width % 256 || (row_stride % 8) || (reinterpret_cast<uintptr_t>(x_bf16) % 16) || (reinterpret_cast<uintptr_t>(stats) % 8))
+        return CLIPPPO_ERR_ALIGN;
+    const __nv_bfloat16* x = static_cast<const __nv_bfloat16*>(x_bf16);
+    float2* st = reinterpret_cast<float2*>(stats);
+    const unsigned grid = (rows + 7) / 8;
+    switch (width / 256) {
+        case 2: CLIPPPO_CUDA_TRY(launch_pdl(rowstats_kernel<2>, grid, 256, 0, stream, 1, x, rows, row_stride, st)); break;
+        case 3: CLIPPPO_CUDA_TRY(launch_pdl(rowstats_kernel<3>, grid, 256, 0, stream, 1, x, rows, row_stride, st)); break;
+        case 4: CLIPPPO_CUDA_TRY(launch_pdl(rowstats_kernel<4>, grid, 256, 0, stream, 1, x, rows, row_stride, st)); break;
+        case 5: CLIPPPO_CUDA_TRY(launch_pdl(rowstats_kernel<5>, grid, 256, 0, stream, 1, x, rows, row_stride, st)); break;
+        default: return CLIPPPO_ERR_UNSUPPORTED;
+    }
+    prof_count_launch();
+    return CLIPPPO_OK;
+}
+
 }  // namespace clipppo
+
+extern "C" int clipppo_rowstats_bf16(const void* x_bf16, int rows, int width, int64_t row_stride, float* stats,
+                                     clipppo_stream_t stream) {
+    return clipppo::rowstats_launch(x_bf16, rows, width, row_stride, stats, clipppo::as_stream(stream));
+}
 
 extern "C" int clipppo_layernorm_bf16(const float* x, const float* gamma, const float* beta, int rows,
                                       int width, int64_t row_stride, void* y_bf16, clipppo_stream_t stream) {

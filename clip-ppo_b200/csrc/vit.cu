@@ -1,13 +1,18 @@
 // Frozen CLIP image tower driver: owns the weight TMA descriptors and sequences the kernels
 //   V0 preprocess+im2col -> V1 patch-embed GEMM (+pos) -> ln_pre ->
-//   L x [ ln_1 -> QKV GEMM -> attention -> out-proj GEMM (+residual) -> ln_2 -> c_fc GEMM (+QuickGELU)
-//         -> c_proj GEMM (+residual) ] -> ln_post(CLS) -> head GEMM -> optional L2 normalise
+//   L x [ row stats -> QKV GEMM (ln_1 folded) -> attention -> out-proj GEMM (+= residual) ->
+//         row stats -> c_fc GEMM (ln_2 folded, +QuickGELU) -> c_proj GEMM (+= residual) ]
+//   -> ln_post(CLS) -> head GEMM -> optional L2 normalise
 // Replaces [clip] VisionTransformer.forward / CLIP.encode_image as called by reference
 // shared/clip_ppo_utils.py:163-164 and :212-217 (spec: SURVEY.md Appendix B).
 //
-// Residual stream X is fp32 [n*T, D]; GEMM operands are bf16.  Images are processed in chunks so
-// the activation workspace stays bounded (and mostly L2-resident) whatever N is; buffers that are
-// never live together (im2col patches / QKV / MLP hidden) share one allocation.
+// The residual stream X is bf16 [n*T, D] and is the A operand of the QKV / c_fc GEMMs as it stands:
+// ln_1 / ln_2 are folded through those GEMMs (gamma in the weights, beta in the bias, mean / rstd
+// applied per row in the epilogue), so a block is  rowstats -> QKV -> attention -> out_proj(+=) ->
+// rowstats -> c_fc(+GELU) -> c_proj(+=)  with both residual updates done by TMA reduce-adds in L2.
+// Accumulation is fp32 everywhere; patch embedding + ln_pre run in fp32.  Images are processed in
+// chunks so the activation workspace stays bounded whatever N is; buffers that are never live
+// together (im2col patches / QKV / MLP hidden) share one allocation.
 #include <stdlib.h>
 
 #include <new>
@@ -18,11 +23,18 @@
 
 struct clipppo_vit_s {
     clipppo_vit_config cfg;
-    clipppo_vit_weights w;
-    std::vector<clipppo_vit_layer> layers;
     int tokens, grid, kpatch;
+    // handle-owned device arena with the repacked frozen weights
+    void* arena = nullptr;
+    struct Layer {
+        const __nv_bfloat16 *w_qkv, *w_out, *w_fc, *w_proj;     // w_qkv / w_fc carry ln_1 / ln_2 gamma
+        const float *b_qkv, *s_qkv, *b_out, *b_fc, *s_fc, *b_proj;
+        CUtensorMap tm_qkv, tm_out, tm_fc, tm_proj;
+    };
+    std::vector<Layer> layers;
+    const __nv_bfloat16 *w_patch, *w_head;
+    const float *cls_pos0, *pos, *ln_pre_g, *ln_pre_b, *ln_post_g, *ln_post_b;
     CUtensorMap tm_patch, tm_head;
-    std::vector<CUtensorMap> tm_qkv, tm_out, tm_fc, tm_proj;
 };
 
 namespace clipppo {
@@ -31,9 +43,54 @@ namespace {
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// ---- one-off weight repacking (clipppo_vit_create) ------------------------------------------
+// fp32 [rows, k_src] -> bf16 [rows, k_dst], zero-padded columns (conv1 of ViT-L/14: 588 -> 640)
+__global__ void convert_pad_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int rows, int k_src, int k_dst) {
+    const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= static_cast<size_t>(rows) * k_dst) return;
+    const int r = static_cast<int>(i / k_dst), k = static_cast<int>(i - static_cast<size_t>(r) * k_dst);
+    dst[i] = __float2bfloat16_rn(k < k_src ? src[static_cast<size_t>(r) * k_src + k] : 0.0f);
+}
+// proj fp32 [D, O] -> bf16 [O, D] (K-major B operand of the head GEMM)
+__global__ void transpose_convert_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int D, int O) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= D * O) return;
+    const int o = i / D, d = i - o * D;
+    dst[i] = __float2bfloat16_rn(src[static_cast<size_t>(d) * O + o]);
+}
+__global__ void add_vec_kernel(const float* a, const float* b, float* out, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = a[i] + b[i];
+}
+// LayerNorm folded into the linear layer that consumes it ([clip] ln_1 -> attn.in_proj, ln_2 -> mlp.c_fc):
+//   LN(x) W^T + b = rstd * (x W'^T - mean * s) + b'   with  W' = W diag(gamma),  s = W' 1,  b' = b + W beta.
+// s is summed over the bf16-ROUNDED W' - the values the tensor core multiplies - so the mean term
+// cancels exactly what the GEMM accumulated.  One block per output row.
+__global__ void __launch_bounds__(128)
+fold_ln_kernel(const float* __restrict__ W, const float* __restrict__ gamma, const float* __restrict__ beta,
+               const float* __restrict__ bias, int K, __nv_bfloat16* __restrict__ Wf, float* __restrict__ colsum,
+               float* __restrict__ bias2) {
+    __shared__ float red[64];
+    const int n = blockIdx.x;
+    const float* w = W + static_cast<size_t>(n) * K;
+    float s = 0.f, bb = 0.f;
+    for (int k = threadIdx.x; k < K; k += blockDim.x) {
+        const float wv = w[k];
+        const __nv_bfloat16 h = __float2bfloat16_rn(wv * gamma[k]);
+        Wf[static_cast<size_t>(n) * K + k] = h;
+        s += __bfloat162float(h);
+        bb = fmaf(wv, beta[k], bb);
+    }
+    s = block_sum(s, red);
+    bb = block_sum(bb, red + 32);
+    if (threadIdx.x == 0) { colsum[n] = s; bias2[n] = bias[n] + bb; }
+}
+
 struct Workspace {
-    float* X;                 // [n*T, D] fp32 residual stream
-    __nv_bfloat16* Y;         // [n*T, D] LN output / attention output
+    float* X0;                // [n*T, D] fp32: patch embedding + positional embedding, input of ln_pre
+    __nv_bfloat16* X;         // [n*T, D] bf16 residual stream (A operand of the QKV / c_fc GEMMs as is)
+    float* stats;             // [n*T, 2] (mean, rstd) of the rows of X
+    __nv_bfloat16* Y;         // [n*T, D] attention output
     __nv_bfloat16* H;         // max(patches [n*G*G, kpatch], QKV [n*T, 3D], hidden [n*T, 4D])
     __nv_bfloat16* Ycls;      // [n, D]
     size_t bytes;
@@ -49,7 +106,9 @@ Workspace carve(const clipppo_vit_s* h, int n, void* base) {
     Workspace ws;
     size_t off = 0;
     uint8_t* b = static_cast<uint8_t*>(base);
-    ws.X = reinterpret_cast<float*>(b + off);            off += align_up(rows * D * 4, 1024);
+    ws.X0 = reinterpret_cast<float*>(b + off);           off += align_up(rows * D * 4, 1024);
+    ws.X = reinterpret_cast<__nv_bfloat16*>(b + off);    off += align_up(rows * D * 2, 1024);
+    ws.stats = reinterpret_cast<float*>(b + off);        off += align_up(rows * 2 * 4, 1024);
     ws.Y = reinterpret_cast<__nv_bfloat16*>(b + off);    off += align_up(rows * D * 2, 1024);
     ws.H = reinterpret_cast<__nv_bfloat16*>(b + off);    off += align_up(h_elems * 2, 1024);
     ws.Ycls = reinterpret_cast<__nv_bfloat16*>(b + off); off += align_up(static_cast<size_t>(n) * D * 2, 1024);
@@ -57,7 +116,7 @@ Workspace carve(const clipppo_vit_s* h, int n, void* base) {
     return ws;
 }
 
-// X[img*T + 0, :] = class_embedding + positional_embedding[0]
+// X0[img*T + 0, :] = class_embedding + positional_embedding[0]
 __global__ void cls_init_kernel(float* __restrict__ X, const float* __restrict__ cls_pos0, int n, int T, int D) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;      // float4 index
     const int d4 = D >> 2;
@@ -84,8 +143,9 @@ int encode_chunk(const clipppo_vit_s* h, const void* images, int img_dtype, cons
                  int ih, int iw, float pre_scale, int flags, float* out, const Workspace& ws, cudaStream_t stream) {
     const int D = h->cfg.width, T = h->tokens, G = h->grid, O = h->cfg.out_dim, L = h->cfg.layers;
     const int rows = n * T, prow = n * G * G;
-    CUtensorMap tmY, tmH, tmP, tmC;
+    CUtensorMap tmX, tmY, tmH, tmP, tmC;
     VIT_TRY(make_bf16_kmajor_tmap(&tmP, ws.H, prow, h->kpatch, h->kpatch, gemm_a_box_rows()));
+    VIT_TRY(make_bf16_kmajor_tmap(&tmX, ws.X, rows, D, D, gemm_a_box_rows()));
     VIT_TRY(make_bf16_kmajor_tmap(&tmY, ws.Y, rows, D, D, gemm_a_box_rows()));
     VIT_TRY(make_bf16_kmajor_tmap(&tmH, ws.H, rows, 4 * D, 4 * D, gemm_a_box_rows()));
     VIT_TRY(make_bf16_kmajor_tmap(&tmC, ws.Ycls, n, D, D, gemm_a_box_rows()));
@@ -93,26 +153,28 @@ int encode_chunk(const clipppo_vit_s* h, const void* images, int img_dtype, cons
     VIT_TRY(preprocess_launch(images, img_dtype, strides, n, C, ih, iw, pre_scale,
                               (flags & CLIPPPO_VIT_PRENORMALIZED) ? 0 : 1, h->cfg.patch, h->cfg.image,
                               h->kpatch, ws.H, stream));
-    cls_init_kernel<<<(n * (D / 4) + 255) / 256, 256, 0, stream>>>(ws.X, h->w.cls_pos0, n, T, D);
+    cls_init_kernel<<<(n * (D / 4) + 255) / 256, 256, 0, stream>>>(ws.X0, h->cls_pos0, n, T, D);
     CLIPPPO_CHECK_LAUNCH();
-    VIT_TRY(gemm_bf16_launch(tmP, h->tm_patch, prow, D, h->kpatch, CLIPPPO_EPI_PATCH_F32, nullptr, h->w.pos, T,
-                             ws.X, D, stream));
-    VIT_TRY(layernorm_inplace_f32_launch(ws.X, h->w.ln_pre_g, h->w.ln_pre_b, rows, D, D, stream));
+    VIT_TRY(gemm_bf16_launch(tmP, h->tm_patch, prow, D, h->kpatch, CLIPPPO_EPI_PATCH_F32, nullptr, h->pos, T,
+                             ws.X0, D, stream));
+    VIT_TRY(layernorm_launch(ws.X0, h->ln_pre_g, h->ln_pre_b, rows, D, D, ws.X, stream));          // ln_pre -> bf16 residual
     for (int l = 0; l < L; ++l) {
-        const clipppo_vit_layer& w = h->layers[l];
-        VIT_TRY(layernorm_launch(ws.X, w.ln1_g, w.ln1_b, rows, D, D, ws.Y, stream));
-        VIT_TRY(gemm_bf16_launch(tmY, h->tm_qkv[l], rows, 3 * D, D, CLIPPPO_EPI_BIAS_BF16, w.b_qkv, nullptr, 0,
-                                 ws.H, 3 * D, stream));
+        const clipppo_vit_s::Layer& w = h->layers[l];
+        // x += out_proj(attn(ln_1(x)))   - ln_1 lives in the QKV GEMM's epilogue
+        VIT_TRY(rowstats_launch(ws.X, rows, D, D, ws.stats, stream));
+        VIT_TRY(gemm_bf16_launch(tmX, w.tm_qkv, rows, 3 * D, D, CLIPPPO_EPI_ROWAFFINE_BF16, w.b_qkv, nullptr, 0,
+                                 ws.H, 3 * D, stream, ws.stats, w.s_qkv));
         VIT_TRY(attention_launch(ws.H, n, T, h->cfg.heads, D / h->cfg.heads, ws.Y, stream));
-        VIT_TRY(gemm_bf16_launch(tmY, h->tm_out[l], rows, D, D, CLIPPPO_EPI_BIAS_RESID_F32, w.b_out, nullptr, 0,
+        VIT_TRY(gemm_bf16_launch(tmY, w.tm_out, rows, D, D, CLIPPPO_EPI_RESID_BF16, w.b_out, nullptr, 0,
                                  ws.X, D, stream));
-        VIT_TRY(layernorm_launch(ws.X, w.ln2_g, w.ln2_b, rows, D, D, ws.Y, stream));
-        VIT_TRY(gemm_bf16_launch(tmY, h->tm_fc[l], rows, 4 * D, D, CLIPPPO_EPI_BIAS_GELU_BF16, w.b_fc, nullptr, 0,
-                                 ws.H, 4 * D, stream));
-        VIT_TRY(gemm_bf16_launch(tmH, h->tm_proj[l], rows, D, 4 * D, CLIPPPO_EPI_BIAS_RESID_F32, w.b_proj, nullptr, 0,
+        // x += c_proj(QuickGELU(c_fc(ln_2(x))))
+        VIT_TRY(rowstats_launch(ws.X, rows, D, D, ws.stats, stream));
+        VIT_TRY(gemm_bf16_launch(tmX, w.tm_fc, rows, 4 * D, D, CLIPPPO_EPI_ROWAFFINE_GELU_BF16, w.b_fc, nullptr, 0,
+                                 ws.H, 4 * D, stream, ws.stats, w.s_fc));
+        VIT_TRY(gemm_bf16_launch(tmH, w.tm_proj, rows, D, 4 * D, CLIPPPO_EPI_RESID_BF16, w.b_proj, nullptr, 0,
                                  ws.X, D, stream));
     }
-    VIT_TRY(layernorm_launch(ws.X, h->w.ln_post_g, h->w.ln_post_b, n, D, static_cast<long long>(T) * D, ws.Ycls, stream));
+    VIT_TRY(layernorm_bf16in_launch(ws.X, h->ln_post_g, h->ln_post_b, n, D, static_cast<long long>(T) * D, ws.Ycls, stream));
     VIT_TRY(gemm_bf16_launch(tmC, h->tm_head, n, O, D, CLIPPPO_EPI_F32, nullptr, nullptr, 0, out, O, stream));
     if (flags & CLIPPPO_VIT_L2NORM) {
         l2norm_rows_kernel<<<(n + 7) / 8, 256, 0, stream>>>(out, n, O);
@@ -126,45 +188,105 @@ int encode_chunk(const clipppo_vit_s* h, const void* images, int img_dtype, cons
 
 using namespace clipppo;
 
+// Repack the caller's fp32 openai/CLIP weights into the handle-owned arena (bf16 K-major GEMM
+// operands, LayerNorm-folded in_proj / c_fc, fp32 vectors) and build the weight TMA descriptors.
 extern "C" int clipppo_vit_create(clipppo_vit_t* handle, const clipppo_vit_config* cfg,
                                   const clipppo_vit_weights* weights_host) {
     if (!handle || !cfg || !weights_host || !weights_host->layers_host) return CLIPPPO_ERR_NULL;
-    const int D = cfg->width, P = cfg->patch;
-    if (D <= 0 || cfg->layers <= 0 || cfg->heads <= 0 || P <= 0 || cfg->image <= 0 || cfg->out_dim <= 0) return CLIPPPO_ERR_BAD_SHAPE;
+    const int D = cfg->width, P = cfg->patch, O = cfg->out_dim, L = cfg->layers;
+    if (D <= 0 || L <= 0 || cfg->heads <= 0 || P <= 0 || cfg->image <= 0 || O <= 0) return CLIPPPO_ERR_BAD_SHAPE;
     if (cfg->image % P || D % cfg->heads) return CLIPPPO_ERR_BAD_SHAPE;
-    if (D / cfg->heads != 64 || D % 128 || D % 64 || cfg->out_dim % 32) return CLIPPPO_ERR_UNSUPPORTED;
+    if (D / cfg->heads != 64 || D % 256 || O % 32) return CLIPPPO_ERR_UNSUPPORTED;
     const clipppo_vit_weights& w = *weights_host;
-    if (!w.w_patch || !w.cls_pos0 || !w.pos || !w.ln_pre_g || !w.ln_pre_b || !w.ln_post_g || !w.ln_post_b || !w.w_head)
+    if (!w.conv1 || !w.class_embedding || !w.positional_embedding || !w.ln_pre_g || !w.ln_pre_b || !w.ln_post_g ||
+        !w.ln_post_b || !w.proj)
         return CLIPPPO_ERR_NULL;
+    for (int l = 0; l < L; ++l) {
+        const clipppo_vit_layer& lw = w.layers_host[l];
+        if (!lw.w_qkv || !lw.b_qkv || !lw.w_out || !lw.b_out || !lw.w_fc || !lw.b_fc || !lw.w_proj || !lw.b_proj ||
+            !lw.ln1_g || !lw.ln1_b || !lw.ln2_g || !lw.ln2_b)
+            return CLIPPPO_ERR_NULL;
+    }
     clipppo_vit_s* h = new (std::nothrow) clipppo_vit_s();
     if (!h) return CLIPPPO_ERR_WORKSPACE;
     h->cfg = *cfg;
-    h->w = w;
-    h->layers.assign(w.layers_host, w.layers_host + cfg->layers);
-    h->w.layers_host = nullptr;
     h->grid = cfg->image / P;
     h->tokens = h->grid * h->grid + 1;
-    h->kpatch = (3 * P * P + 63) / 64 * 64;
-    const int nb = gemm_b_box_rows();
-    int st = make_bf16_kmajor_tmap(&h->tm_patch, w.w_patch, D, h->kpatch, h->kpatch, nb);
-    if (!st) st = make_bf16_kmajor_tmap(&h->tm_head, w.w_head, cfg->out_dim, D, D, nb);
-    h->tm_qkv.resize(cfg->layers); h->tm_out.resize(cfg->layers); h->tm_fc.resize(cfg->layers); h->tm_proj.resize(cfg->layers);
-    for (int l = 0; l < cfg->layers && !st; ++l) {
-        const clipppo_vit_layer& lw = h->layers[l];
-        if (!lw.w_qkv || !lw.b_qkv || !lw.w_out || !lw.b_out || !lw.w_fc || !lw.b_fc || !lw.w_proj || !lw.b_proj ||
-            !lw.ln1_g || !lw.ln1_b || !lw.ln2_g || !lw.ln2_b) { st = CLIPPPO_ERR_NULL; break; }
-        st = make_bf16_kmajor_tmap(&h->tm_qkv[l], lw.w_qkv, 3 * D, D, D, nb);
-        if (!st) st = make_bf16_kmajor_tmap(&h->tm_out[l], lw.w_out, D, D, D, nb);
-        if (!st) st = make_bf16_kmajor_tmap(&h->tm_fc[l], lw.w_fc, 4 * D, D, D, nb);
-        if (!st) st = make_bf16_kmajor_tmap(&h->tm_proj[l], lw.w_proj, D, 4 * D, 4 * D, nb);
+    const int T = h->tokens, kreal = 3 * P * P;
+    h->kpatch = (kreal + 63) / 64 * 64;
+    h->layers.resize(L);
+
+    // ---- arena layout ----
+    size_t off = 0;
+    auto take = [&](size_t bytes) { const size_t o = off; off += align_up(bytes, 256); return o; };
+    const size_t o_patch = take(static_cast<size_t>(D) * h->kpatch * 2), o_head = take(static_cast<size_t>(O) * D * 2);
+    const size_t o_cls = take(D * 4), o_pos = take(static_cast<size_t>(T) * D * 4);
+    const size_t o_lnv = take(4 * static_cast<size_t>(D) * 4);
+    struct LOff { size_t qkv, out, fc, proj, vec; };
+    std::vector<LOff> lo(L);
+    const size_t vec_floats = 3 * D + 3 * D + D + 4 * D + 4 * D + D;      // b_qkv s_qkv b_out b_fc s_fc b_proj
+    for (int l = 0; l < L; ++l) {
+        lo[l].qkv = take(static_cast<size_t>(3) * D * D * 2);
+        lo[l].out = take(static_cast<size_t>(D) * D * 2);
+        lo[l].fc = take(static_cast<size_t>(4) * D * D * 2);
+        lo[l].proj = take(static_cast<size_t>(4) * D * D * 2);
+        lo[l].vec = take(vec_floats * 4);
     }
+    int st = record_cuda(cudaMalloc(&h->arena, off));
     if (st) { delete h; return st; }
+    uint8_t* A = static_cast<uint8_t*>(h->arena);
+    auto bf = [&](size_t o) { return reinterpret_cast<__nv_bfloat16*>(A + o); };
+    auto fp = [&](size_t o) { return reinterpret_cast<float*>(A + o); };
+    cudaStream_t s0 = nullptr;
+    auto blocks = [](size_t n) { return static_cast<unsigned>((n + 255) / 256); };
+    auto copyf = [&](float* dst, const float* src, size_t n) { return cudaMemcpyAsync(dst, src, n * 4, cudaMemcpyDeviceToDevice, s0); };
+
+    convert_pad_kernel<<<blocks(static_cast<size_t>(D) * h->kpatch), 256, 0, s0>>>(w.conv1, bf(o_patch), D, kreal, h->kpatch);
+    transpose_convert_kernel<<<blocks(static_cast<size_t>(D) * O), 256, 0, s0>>>(w.proj, bf(o_head), D, O);
+    add_vec_kernel<<<blocks(D), 256, 0, s0>>>(w.class_embedding, w.positional_embedding, fp(o_cls), D);
+    copyf(fp(o_pos), w.positional_embedding, static_cast<size_t>(T) * D);
+    copyf(fp(o_lnv), w.ln_pre_g, D); copyf(fp(o_lnv) + D, w.ln_pre_b, D);
+    copyf(fp(o_lnv) + 2 * D, w.ln_post_g, D); copyf(fp(o_lnv) + 3 * D, w.ln_post_b, D);
+    h->w_patch = bf(o_patch); h->w_head = bf(o_head);
+    h->cls_pos0 = fp(o_cls); h->pos = fp(o_pos);
+    h->ln_pre_g = fp(o_lnv); h->ln_pre_b = fp(o_lnv) + D; h->ln_post_g = fp(o_lnv) + 2 * D; h->ln_post_b = fp(o_lnv) + 3 * D;
+    for (int l = 0; l < L; ++l) {
+        const clipppo_vit_layer& lw = w.layers_host[l];
+        clipppo_vit_s::Layer& hl = h->layers[l];
+        float* v = fp(lo[l].vec);
+        float *b_qkv = v, *s_qkv = v + 3 * D, *b_out = v + 6 * D, *b_fc = v + 7 * D, *s_fc = v + 11 * D, *b_proj = v + 15 * D;
+        fold_ln_kernel<<<3 * D, 128, 0, s0>>>(lw.w_qkv, lw.ln1_g, lw.ln1_b, lw.b_qkv, D, bf(lo[l].qkv), s_qkv, b_qkv);
+        fold_ln_kernel<<<4 * D, 128, 0, s0>>>(lw.w_fc, lw.ln2_g, lw.ln2_b, lw.b_fc, D, bf(lo[l].fc), s_fc, b_fc);
+        convert_pad_kernel<<<blocks(static_cast<size_t>(D) * D), 256, 0, s0>>>(lw.w_out, bf(lo[l].out), D, D, D);
+        convert_pad_kernel<<<blocks(static_cast<size_t>(4) * D * D), 256, 0, s0>>>(lw.w_proj, bf(lo[l].proj), D, 4 * D, 4 * D);
+        copyf(b_out, lw.b_out, D);
+        copyf(b_proj, lw.b_proj, D);
+        hl.w_qkv = bf(lo[l].qkv); hl.w_out = bf(lo[l].out); hl.w_fc = bf(lo[l].fc); hl.w_proj = bf(lo[l].proj);
+        hl.b_qkv = b_qkv; hl.s_qkv = s_qkv; hl.b_out = b_out; hl.b_fc = b_fc; hl.s_fc = s_fc; hl.b_proj = b_proj;
+    }
+    st = record_cuda(cudaGetLastError());
+    if (!st) st = record_cuda(cudaStreamSynchronize(s0));      // the caller may free its fp32 weights on return
+
+    const int nb = gemm_b_box_rows();
+    if (!st) st = make_bf16_kmajor_tmap(&h->tm_patch, h->w_patch, D, h->kpatch, h->kpatch, nb);
+    if (!st) st = make_bf16_kmajor_tmap(&h->tm_head, h->w_head, O, D, D, nb);
+    for (int l = 0; l < L && !st; ++l) {
+        clipppo_vit_s::Layer& hl = h->layers[l];
+        st = make_bf16_kmajor_tmap(&hl.tm_qkv, hl.w_qkv, 3 * D, D, D, nb);
+        if (!st) st = make_bf16_kmajor_tmap(&hl.tm_out, hl.w_out, D, D, D, nb);
+        if (!st) st = make_bf16_kmajor_tmap(&hl.tm_fc, hl.w_fc, 4 * D, D, D, nb);
+        if (!st) st = make_bf16_kmajor_tmap(&hl.tm_proj, hl.w_proj, D, 4 * D, 4 * D, nb);
+    }
+    if (st) { cudaFree(h->arena); delete h; return st; }
     *handle = h;
     return CLIPPPO_OK;
 }
 
 extern "C" int clipppo_vit_destroy(clipppo_vit_t handle) {
-    delete handle;
+    if (handle) {
+        if (handle->arena) cudaFree(handle->arena);
+        delete handle;
+    }
     return CLIPPPO_OK;
 }
 

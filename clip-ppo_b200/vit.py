@@ -1,8 +1,9 @@
 """Host side of the frozen CLIP image tower: weight repacking + the C-ABI encode call.
 
 ``VitEngine`` takes a state dict in openai/CLIP ``visual.*`` key layout (what
-``clip.load(...).state_dict()`` holds), repacks it once into the bf16 / fp32 device tensors the
-kernels want, creates the native handle (``clipppo_vit_create``) and then serves
+``clip.load(...).state_dict()`` holds), stages it on the device as fp32, lets the native side repack
+it into handle-owned bf16 operands (``clipppo_vit_create``: K-major GEMM weights, ln_1 / ln_2 folded
+into in_proj / c_fc) and then serves
 ``encode(images, pre_scale, l2norm)`` = preprocessing + tower + optional L2 normalise in one
 C-ABI call (``clipppo_vit_encode``).
 """
@@ -47,7 +48,7 @@ def config_from_state_dict(sd: Dict[str, torch.Tensor], prefix: str = "visual.")
 
 
 class VitEngine:
-    """Frozen tower on one GPU.  Owns the repacked weights; the native handle only borrows them."""
+    """Frozen tower on one GPU.  The native handle owns the repacked weights."""
 
     def __init__(self, state_dict: Dict[str, torch.Tensor], device: torch.device | str = "cuda",
                  prefix: str = "visual."):
@@ -58,53 +59,37 @@ class VitEngine:
             self.device = torch.device("cuda", torch.cuda.current_device())
         self.cfg = config_from_state_dict(state_dict, prefix)
         cfg = self.cfg
-        D, P = cfg.width, cfg.patch
-        self._keep = []          # every tensor the native handle points into
+        keep = []                # fp32 staging copies: only needed until clipppo_vit_create returns
 
-        def dev(t, dtype):
-            t = t.detach().to(device=self.device, dtype=dtype).contiguous()
-            self._keep.append(t)
-            return t
+        def dev(name):
+            t = state_dict[prefix + name].detach().to(device=self.device, dtype=torch.float32).contiguous()
+            keep.append(t)
+            return t.data_ptr()
 
-        def g(name):
-            return state_dict[prefix + name]
-
-        kreal = 3 * P * P
-        kpad = (kreal + 63) // 64 * 64
-        wp = g("conv1.weight").detach().float().reshape(D, kreal)
-        if kpad != kreal:
-            wp = torch.nn.functional.pad(wp, (0, kpad - kreal))
         W = N.VitWeights()
-        W.w_patch = dev(wp, torch.bfloat16).data_ptr()
-        pos = g("positional_embedding").detach().float()
-        W.cls_pos0 = dev(g("class_embedding").detach().float() + pos[0], torch.float32).data_ptr()
-        W.pos = dev(pos, torch.float32).data_ptr()
-        W.ln_pre_g = dev(g("ln_pre.weight"), torch.float32).data_ptr()
-        W.ln_pre_b = dev(g("ln_pre.bias"), torch.float32).data_ptr()
-        W.ln_post_g = dev(g("ln_post.weight"), torch.float32).data_ptr()
-        W.ln_post_b = dev(g("ln_post.bias"), torch.float32).data_ptr()
-        W.w_head = dev(g("proj").detach().float().t(), torch.bfloat16).data_ptr()      # [out, D], K-major
+        W.conv1 = dev("conv1.weight")
+        W.class_embedding = dev("class_embedding")
+        W.positional_embedding = dev("positional_embedding")
+        W.ln_pre_g, W.ln_pre_b = dev("ln_pre.weight"), dev("ln_pre.bias")
+        W.ln_post_g, W.ln_post_b = dev("ln_post.weight"), dev("ln_post.bias")
+        W.proj = dev("proj")
         layers = (N.VitLayer * cfg.layers)()
         for i in range(cfg.layers):
             p = f"transformer.resblocks.{i}."
             L = layers[i]
-            L.w_qkv = dev(g(p + "attn.in_proj_weight"), torch.bfloat16).data_ptr()
-            L.b_qkv = dev(g(p + "attn.in_proj_bias"), torch.float32).data_ptr()
-            L.w_out = dev(g(p + "attn.out_proj.weight"), torch.bfloat16).data_ptr()
-            L.b_out = dev(g(p + "attn.out_proj.bias"), torch.float32).data_ptr()
-            L.w_fc = dev(g(p + "mlp.c_fc.weight"), torch.bfloat16).data_ptr()
-            L.b_fc = dev(g(p + "mlp.c_fc.bias"), torch.float32).data_ptr()
-            L.w_proj = dev(g(p + "mlp.c_proj.weight"), torch.bfloat16).data_ptr()
-            L.b_proj = dev(g(p + "mlp.c_proj.bias"), torch.float32).data_ptr()
-            L.ln1_g = dev(g(p + "ln_1.weight"), torch.float32).data_ptr()
-            L.ln1_b = dev(g(p + "ln_1.bias"), torch.float32).data_ptr()
-            L.ln2_g = dev(g(p + "ln_2.weight"), torch.float32).data_ptr()
-            L.ln2_b = dev(g(p + "ln_2.bias"), torch.float32).data_ptr()
+            L.ln1_g, L.ln1_b = dev(p + "ln_1.weight"), dev(p + "ln_1.bias")
+            L.w_qkv, L.b_qkv = dev(p + "attn.in_proj_weight"), dev(p + "attn.in_proj_bias")
+            L.w_out, L.b_out = dev(p + "attn.out_proj.weight"), dev(p + "attn.out_proj.bias")
+            L.ln2_g, L.ln2_b = dev(p + "ln_2.weight"), dev(p + "ln_2.bias")
+            L.w_fc, L.b_fc = dev(p + "mlp.c_fc.weight"), dev(p + "mlp.c_fc.bias")
+            L.w_proj, L.b_proj = dev(p + "mlp.c_proj.weight"), dev(p + "mlp.c_proj.bias")
         W.layers_host = C.cast(layers, C.POINTER(N.VitLayer))
         ncfg = N.VitConfig(cfg.width, cfg.layers, cfg.heads, cfg.patch, cfg.image, cfg.out_dim)
         self._handle = C.c_void_p()
         with torch.cuda.device(self.device):
+            torch.cuda.synchronize(self.device)          # staging copies above ran on torch's stream
             N.check(N.lib().clipppo_vit_create(C.byref(self._handle), C.byref(ncfg), C.byref(W)), "clipppo_vit_create")
+        del keep                                         # create() has repacked into handle-owned memory
         self._workspace: Optional[torch.Tensor] = None
 
     def __del__(self):

@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define CLIPPPO_ABI_VERSION 1
+#define CLIPPPO_ABI_VERSION 2
 
 typedef enum clipppo_status {
     CLIPPPO_OK = 0,
@@ -129,39 +129,42 @@ int clipppo_ppo_loss_f32(const float* newlogprob, const float* entropy, const fl
                          clipppo_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
- * V*  frozen CLIP image tower (ViT-B/32, ViT-L/14 ...), bf16 tcgen05 GEMMs, fp32 residual.
+ * V*  frozen CLIP image tower (ViT-B/32, ...): bf16 tcgen05 GEMMs with fp32 accumulation, bf16
+ * residual stream, ln_1 / ln_2 folded through the GEMMs that consume them.
  * Replaces clip_model.encode_image / clip.model.VisionTransformer.forward as called from
  * generate_clip_embeddings (shared/clip_ppo_utils.py:141-164) and get_frozen_clip_features
  * (:185-217), including their resize / normalise preprocessing and the final L2 normalise.
+ *
+ * Weights are handed over as they sit in the checkpoint: fp32 DEVICE pointers in openai/CLIP
+ * state-dict layout (`visual.*`).  clipppo_vit_create repacks them once
+ * into device memory owned by the handle; the caller may free its copies when create returns.
  * ---------------------------------------------------------------------------------------- */
 typedef struct clipppo_vit_config {
     int width, layers, heads, patch, image, out_dim;
 } clipppo_vit_config;
 
-typedef struct clipppo_vit_layer {
-    const void*  w_qkv;   /* bf16 [3D, D]  (in_proj_weight)      */
-    const float* b_qkv;   /* fp32 [3D]                            */
-    const void*  w_out;   /* bf16 [D, D]   (attn.out_proj.weight) */
-    const float* b_out;   /* fp32 [D]                             */
-    const void*  w_fc;    /* bf16 [4D, D]  (mlp.c_fc.weight)      */
-    const float* b_fc;    /* fp32 [4D]                            */
-    const void*  w_proj;  /* bf16 [D, 4D]  (mlp.c_proj.weight)    */
-    const float* b_proj;  /* fp32 [D]                             */
-    const float *ln1_g, *ln1_b, *ln2_g, *ln2_b;   /* fp32 [D] */
+typedef struct clipppo_vit_layer {          /* visual.transformer.resblocks.{i}.*            */
+    const float *ln1_g, *ln1_b;             /* ln_1.weight / bias            [D]             */
+    const float *w_qkv, *b_qkv;             /* attn.in_proj_weight / bias    [3D, D], [3D]   */
+    const float *w_out, *b_out;             /* attn.out_proj.weight / bias   [D, D],  [D]    */
+    const float *ln2_g, *ln2_b;             /* ln_2.weight / bias            [D]             */
+    const float *w_fc, *b_fc;               /* mlp.c_fc.weight / bias        [4D, D], [4D]   */
+    const float *w_proj, *b_proj;           /* mlp.c_proj.weight / bias      [D, 4D], [D]    */
 } clipppo_vit_layer;
 
 typedef struct clipppo_vit_weights {
-    const void*  w_patch;   /* bf16 [D, 3*P*P]   (conv1.weight flattened, K-major)   */
-    const float* cls_pos0;  /* fp32 [D]          class_embedding + positional_embedding[0] */
-    const float* pos;       /* fp32 [T, D]       positional_embedding                 */
-    const float *ln_pre_g, *ln_pre_b, *ln_post_g, *ln_post_b;   /* fp32 [D] */
-    const void*  w_head;    /* bf16 [out_dim, D] (proj transposed, K-major)           */
-    const clipppo_vit_layer* layers_host;   /* HOST array of `layers` entries          */
+    const float* conv1;                     /* visual.conv1.weight           [D, 3, P, P]    */
+    const float* class_embedding;           /* visual.class_embedding        [D]             */
+    const float* positional_embedding;      /* visual.positional_embedding   [T, D]          */
+    const float *ln_pre_g, *ln_pre_b, *ln_post_g, *ln_post_b;   /*           [D]             */
+    const float* proj;                      /* visual.proj                   [D, out_dim]    */
+    const clipppo_vit_layer* layers_host;   /* HOST array of `layers` entries                */
 } clipppo_vit_weights;
 
 typedef struct clipppo_vit_s* clipppo_vit_t;
 
-/* The handle stores pointers + TMA descriptors of the caller-owned weights; no device alloc. */
+/* Allocates the handle's weight arena (one cudaMalloc, ~2 bytes per parameter), repacks on the
+ * default stream and synchronises it once; the only entry point that allocates or synchronises. */
 int clipppo_vit_create(clipppo_vit_t* handle, const clipppo_vit_config* cfg,
                        const clipppo_vit_weights* weights_host);
 int clipppo_vit_destroy(clipppo_vit_t handle);
@@ -189,15 +192,35 @@ int clipppo_preprocess_bf16(const void* images, int img_dtype, const int64_t img
                             int patch, int image, void* patches_bf16 /* [N*G*G, 3*P*P] */, clipppo_stream_t stream);
 int clipppo_layernorm_bf16(const float* x, const float* gamma, const float* beta, int rows,
                            int width, int64_t row_stride, void* y_bf16, clipppo_stream_t stream);
+/* fp32 [rows,2] (mean, 1/sqrt(biased var + 1e-5)) of bf16 rows: what is left of ln_1 / ln_2 once their
+ * affine part is folded into the next GEMM (CLIPPPO_EPI_ROWAFFINE_*).  width % 256 == 0. */
+int clipppo_rowstats_bf16(const void* x_bf16, int rows, int width, int64_t row_stride, float* stats,
+                          clipppo_stream_t stream);
 #define CLIPPPO_EPI_BIAS_BF16       0   /* out bf16 = acc + bias                       */
 #define CLIPPPO_EPI_BIAS_GELU_BF16  1   /* out bf16 = quickgelu(acc + bias)            */
 #define CLIPPPO_EPI_BIAS_RESID_F32  2   /* out fp32 += acc + bias (in place residual)  */
 #define CLIPPPO_EPI_PATCH_F32       3   /* token rows of X = acc + pos                 */
 #define CLIPPPO_EPI_F32             4   /* out fp32 = acc                              */
+#define CLIPPPO_EPI_ROWAFFINE_BF16      6   /* out bf16 = rstd[m]*(acc - mean[m]*colsum[n]) + bias[n]          */
+#define CLIPPPO_EPI_ROWAFFINE_GELU_BF16 7   /* ... followed by QuickGELU                                        */
+#define CLIPPPO_EPI_RESID_BF16          8   /* out bf16 += bf16(acc + bias)  (in-place bf16 residual stream)    */
 /* out[M,N] = epilogue(A[M,K] @ W[N,K]^T); A, W bf16 K-major, 16-byte aligned rows. */
 int clipppo_gemm_bf16(const void* a_bf16, const void* w_bf16, int M, int N, int K, int epilogue,
                       const float* bias, const float* pos, int tokens, void* out, int64_t ldo,
                       clipppo_stream_t stream);
+/* The three epilogues the tower runs on (6..8).  ROWAFFINE is LayerNorm folded through the GEMM
+ * ([clip] ln_1 -> in_proj, ln_2 -> c_fc): A holds the UN-normalised residual rows, W the weight with
+ * gamma multiplied into its columns, bias = b + W beta, colsum[n] = sum_k W'[n,k], and row_stats the
+ * fp32 [M,2] (mean, 1/sqrt(var+eps)) of the A rows; row_stats = colsum = NULL gives the plain bias
+ * epilogue.  N must be a multiple of 64.  Outputs leave through TMA stores / TMA reduce-adds. */
+int clipppo_gemm_bf16_fused(const void* a_bf16, const void* w_bf16, int M, int N, int K, int epilogue,
+                            const float* bias, const float* row_stats, const float* colsum,
+                            void* out_bf16, int64_t ldo, clipppo_stream_t stream);
+/* Measurement probe (profiles/ only, never on the product path): the GEMM above with parts switched
+ * off - dbg bit 0: the epilogue drains TMEM but does not compute or store; bit 1: no TMA operand
+ * loads.  Output is garbage by construction; only the duration means anything. */
+int clipppo_gemm_bf16_probe(const void* a_bf16, const void* w_bf16, int M, int N, int K, int epilogue,
+                            const float* bias, void* out, int64_t ldo, int dbg, clipppo_stream_t stream);
 int clipppo_attention_bf16(const void* qkv_bf16, int n_images, int tokens, int heads, int head_dim,
                            void* out_bf16, clipppo_stream_t stream);
 

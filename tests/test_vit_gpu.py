@@ -50,6 +50,79 @@ def test_gemm_epilogues_vs_torch(native, M, N, K, epi):
     assert err <= tol, err
 
 
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (1000, 768, 768), (6400, 2304, 768), (12800, 3072, 768), (77, 64, 128)])
+@pytest.mark.parametrize("epi,with_stats", [(6, True), (6, False), (7, True)])
+def test_gemm_rowaffine_epilogue_is_folded_layernorm(native, M, N, K, epi, with_stats):
+    """ROWAFFINE (ln_1 / ln_2 folded through the GEMM, [clip] ResidualAttentionBlock): the kernel output must
+    equal LayerNorm(x) @ W^T + b computed the ordinary way in fp32 on the same bf16-rounded x."""
+    from clip_ppo_b200 import _native as Nn
+    gen = torch.Generator(device="cuda").manual_seed(M + N + K + epi)
+    x = (torch.randn(M, K, device="cuda", generator=gen) * 1.5 + 0.7).bfloat16()          # un-normalised rows, non-zero mean
+    W = torch.randn(N, K, device="cuda", generator=gen) * (K ** -0.5)
+    b = torch.randn(N, device="cuda", generator=gen) * 0.1
+    out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    if with_stats:
+        gamma = 1 + 0.1 * torch.randn(K, device="cuda", generator=gen)
+        beta = 0.1 * torch.randn(K, device="cuda", generator=gen)
+        Wf = (W * gamma).bfloat16()
+        colsum = Wf.float().sum(1).contiguous()
+        bias2 = (b + W @ beta).contiguous()
+        xf = x.float()
+        mean = xf.mean(1)
+        rstd = torch.rsqrt(xf.var(1, unbiased=False) + 1e-5)
+        stats = torch.stack([mean, rstd], 1).contiguous()
+        ref = torch.nn.functional.layer_norm(xf, (K,), gamma, beta, 1e-5) @ W.t() + b
+        st = native.clipppo_gemm_bf16_fused(x.data_ptr(), Wf.data_ptr(), M, N, K, epi, bias2.data_ptr(), stats.data_ptr(),
+                                            colsum.data_ptr(), out.data_ptr(), N, _stream())
+        tol = 4e-2               # bf16 rounding of W*gamma (2^-9 relative per weight) + bf16 output
+    else:
+        Wf = W.bfloat16()
+        ref = x.float() @ Wf.float().t() + b
+        st = native.clipppo_gemm_bf16_fused(x.data_ptr(), Wf.data_ptr(), M, N, K, epi, b.data_ptr(), None, None,
+                                            out.data_ptr(), N, _stream())
+        tol = 3e-2
+    Nn.check(st)
+    if epi == 7:
+        ref = ref * torch.sigmoid(1.702 * ref)
+    torch.cuda.synchronize()
+    err = (out.float() - ref).abs()
+    assert err.max().item() <= tol * max(1.0, ref.abs().max().item() / 4), err.max().item()
+    assert err.mean().item() <= 4e-3
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (1000, 768, 768), (6400, 768, 3072), (19000, 768, 768), (50, 64, 64)])
+def test_gemm_bf16_residual_reduce_add(native, M, N, K):
+    """RESID_BF16: X (bf16, in place) += bf16(acc + bias), added by the TMA unit in L2."""
+    from clip_ppo_b200 import _native as Nn
+    gen = torch.Generator(device="cuda").manual_seed(M + N + K)
+    a = (torch.randn(M, K, device="cuda", generator=gen) * 0.5).bfloat16()
+    w = (torch.randn(N, K, device="cuda", generator=gen) * (K ** -0.5)).bfloat16()
+    bias = torch.randn(N, device="cuda", generator=gen) * 0.1
+    x0 = torch.randn(M, N, device="cuda", generator=gen).bfloat16()
+    X = x0.clone()
+    Nn.check(native.clipppo_gemm_bf16_fused(a.data_ptr(), w.data_ptr(), M, N, K, 8, bias.data_ptr(), None, None,
+                                            X.data_ptr(), N, _stream()))
+    torch.cuda.synchronize()
+    delta = (a.float() @ w.float().t() + bias).bfloat16()
+    ref = (x0.float() + delta.float()).bfloat16()
+    # two bf16 roundings (the delta, then the sum); allow one bf16 ulp of the result for accumulate-order noise
+    err = (X.float() - ref.float()).abs()
+    assert err.max().item() <= 2 ** -7 * max(1.0, ref.float().abs().max().item()), err.max().item()
+    assert (err > 0).float().mean().item() < 0.05
+
+
+@pytest.mark.parametrize("rows,width", [(50, 768), (6401, 768), (257, 1024)])
+def test_rowstats_vs_torch(native, rows, width):
+    from clip_ppo_b200 import _native as Nn
+    gen = torch.Generator(device="cuda").manual_seed(rows)
+    x = (torch.randn(rows, width, device="cuda", generator=gen) * 3 + 0.5).bfloat16()
+    stats = torch.empty(rows, 2, device="cuda")
+    Nn.check(native.clipppo_rowstats_bf16(x.data_ptr(), rows, width, width, stats.data_ptr(), _stream()))
+    xf = x.float()
+    assert torch.allclose(stats[:, 0], xf.mean(1), atol=1e-5, rtol=1e-5)
+    assert torch.allclose(stats[:, 1], torch.rsqrt(xf.var(1, unbiased=False) + 1e-5), atol=0, rtol=1e-5)
+
+
 def test_gemm_patch_epilogue(native):
     from clip_ppo_b200 import _native as Nn
     n, G2, T, D, K = 5, 49, 50, 768, 3072
