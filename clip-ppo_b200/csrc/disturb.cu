@@ -20,6 +20,8 @@
 //            cutout predicate on the store                                         [HBM write]
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include <cooperative_groups.h>
 
 #include "common.cuh"
@@ -44,6 +46,11 @@ struct DisturbParams {
     int fast;       // x / noise contiguous NCHW fp32, W % 4 == 0, 16-byte aligned
     int io_mode;    // 0: fp32 strided in, fp32 NCHW out.  1: u8 NHWC in / u8 NHWC out.
                     // 2: fp32 (0..255) NHWC in / u8 NHWC out.
+    int nthreads;   // fast path: CTA size (covers the blur tasks in one round when it can)
+    int log2S;      // fast path: S is a power of two
+    int fake_mean;  // EXPERIMENT ONLY (CLIPPPO_DISTURB_FAKE): skip the cluster-wide mean exchange (wrong results)
+    unsigned magic_nq, magic_nsplit, magic_rs;   // fast path: ceil(2^32 / d), so that __umulhi(n, magic) == n / d for n < 2^16
+    __device__ __forceinline__ float* out_f32() const { return static_cast<float*>(out); }
 };
 
 constexpr int kDisturbThreads = 256;
@@ -125,6 +132,313 @@ __device__ __forceinline__ void blur_task(const float* __restrict__ base, float*
             }
         }
     }
+}
+
+
+// =============================================================================================
+// Fast path: x / noise contiguous fp32 NCHW, W % 4 == 0, k <= 7, fp32 NCHW out - every shape the
+// reference's call sites and BASELINE.json's configs use.  Same phase structure as the general
+// kernel below, built for instruction count (the general kernel is issue-bound at ~100 thread
+// instructions per element):
+//   * smem rows carry kPad reflected columns on either side (pitch W + 8), filled by a tiny pass
+//     of their own, so the horizontal filter is three aligned 128-bit loads for EVERY quad - no
+//     edge variant, no reflect arithmetic in the hot loop;
+//   * halo rows are re-read from global memory (L2) and perturbed again instead of being copied
+//     over DSMEM: the only cluster-wide dependency left is the gray mean (one barrier; the second
+//     one, which keeps CTAs resident until their partial sum has been read, is split around the blur);
+//   * clamps are the .sat modifier of the add (2 instructions per element for noise, 2 for contrast);
+//   * thread -> (row, quad) positions advance incrementally (no division in any loop);
+//   * the cutout is a warp-uniform row test plus a per-thread column mask.
+// =============================================================================================
+static int env_int(const char* name, int dflt);
+
+constexpr int kPad = 4;
+
+template <int N, typename F>
+__device__ __forceinline__ void static_for(F&& f) {
+    if constexpr (N > 0) {
+        static_for<N - 1>(f);
+        f(std::integral_constant<int, N - 1>{});
+    }
+}
+
+__device__ __forceinline__ float sat_add(float a, float b) {      // clamp(a + b, 0, 1)
+    float r;
+    asm("add.rn.sat.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+    return r;
+}
+
+// Horizontal K-tap filter of one quad.  Blackwell's packed fp32 pipe (FFMA2: two independent
+// round-to-nearest FMAs per instruction, bit-identical to two FFMAs) halves the instruction count.
+template <int K>
+__device__ __forceinline__ void hfilter4p(const float* __restrict__ rowq, const float2 (&t2)[K], float2 (&h)[2]) {
+    constexpr int P = K / 2;
+    const float4 a = *reinterpret_cast<const float4*>(rowq - 4);
+    const float4 m = *reinterpret_cast<const float4*>(rowq);
+    const float4 z = *reinterpret_cast<const float4*>(rowq + 4);
+    const float v[12] = {a.x, a.y, a.z, a.w, m.x, m.y, m.z, m.w, z.x, z.y, z.z, z.w};
+#pragma unroll
+    for (int o = 0; o < 2; ++o) {
+        float2 acc = __fmul2_rn(t2[0], make_float2(v[4 + 2 * o - P], v[5 + 2 * o - P]));
+#pragma unroll
+        for (int u = 1; u < K; ++u) acc = __ffma2_rn(t2[u], make_float2(v[4 + 2 * o + u - P], v[5 + 2 * o + u - P]), acc);
+        h[o] = acc;
+    }
+}
+
+// WT = compile-time image width (84 / 224: the reference's frame sizes; strides, quad counts and the
+// index divisions become immediates) or 0 for a run-time width.
+template <int K, int WT>
+__global__ void __launch_bounds__(512)
+disturb_fast_kernel(const __grid_constant__ DisturbParams p) {
+    constexpr int P = K / 2;
+    extern __shared__ __align__(16) float smem[];
+    float* red = smem;
+    float* partial = smem + 32;
+    float* tile = smem + kSmemHeaderFloats;
+
+    cg::cluster_group cluster = cg::this_cluster();
+    const int S = p.S, R = p.R, C = p.C, H = p.H, W = WT ? WT : p.W;
+    const int b = blockIdx.x >> p.log2S, s = blockIdx.x & (S - 1);
+    const int r0 = min(s * R, H), r1 = min(r0 + R, H), rows = r1 - r0;
+    const int WP = W + 2 * kPad;              // smem row pitch (floats)
+    const int RS = R + 2 * P;                 // smem rows per channel: P halo rows above, R own rows, P below
+    const int plane = RS * WP;                // smem floats per channel
+    const int nq = W >> 2;
+    auto div_nq = [&](int i) { return WT ? i / (WT >> 2 ? WT >> 2 : 1) : static_cast<int>(__umulhi(i, p.magic_nq)); };
+    const int tid = threadIdx.x, nth = blockDim.x;
+    const bool do_noise = (p.stages & CLIPPPO_STAGE_NOISE) != 0;
+    const bool do_contrast = (p.stages & CLIPPPO_STAGE_CONTRAST) != 0;
+    const float sigma = p.sigma_n;
+    // Phases 1 and 3 walk a channel's stripe linearly (it is contiguous in global memory), one quad
+    // per thread and step; quad index -> (row, quad-in-row) is a multiply-high by a host-computed
+    // reciprocal; global offsets are 32-bit from one per-image base pointer.
+    const int n4 = rows * nq;
+    const size_t img_off = static_cast<size_t>(b) * C * H * W;
+    const float* __restrict__ xi = static_cast<const float*>(p.x) + img_off;
+    const float* __restrict__ ni = do_noise ? p.noise + img_off : xi;
+    const int HW = H * W;
+    float* const tile0 = tile + P * WP + kPad;          // first own row, first real column
+
+    auto noisy4 = [&](float4 v, const float4& nz) {     // [tv] gaussian_noise_image: mul, add, clamp - no FMA contraction (bit-exact)
+        if (do_noise) {
+            v.x = sat_add(v.x, __fmul_rn(nz.x, sigma));
+            v.y = sat_add(v.y, __fmul_rn(nz.y, sigma));
+            v.z = sat_add(v.z, __fmul_rn(nz.z, sigma));
+            v.w = sat_add(v.w, __fmul_rn(nz.w, sigma));
+        }
+        return v;
+    };
+
+    // ---- phase 1: x (+ sigma * noise, clamp) -> smem, gray sum over the OWN rows --------------
+    float gsum = 0.0f;
+    if (p.p1_mode == 1) {
+        // x goes straight into the tile with cp.async: the whole stripe (own + halo rows) is requested
+        // up front without holding a register, the noise follows through registers 8 quads at a time.
+        // Bytes in flight per CTA: all of x plus 8 x 16 B of noise per thread.
+        for (int c_ = 0; c_ < C; ++c_) {
+            const float* xs = xi + c_ * HW + r0 * W;
+            const uint32_t tcs = ptx_smem(tile0 + c_ * plane);
+            for (int i = tid; i < n4; i += nth) {
+                const int row = div_nq(i), quad = i - row * nq;
+                cpa16(tcs + (row * WP + 4 * quad) * 4, xs + 4 * i);
+            }
+        }
+        cpa_commit();
+        constexpr int UNR = 8;
+        bool landed = false;
+        for (int c_ = 0; c_ < C; ++c_) {
+            const float* ns = ni + c_ * HW + r0 * W;
+            int tco = c_ * plane;
+            asm volatile("" : "+l"(ns), "+r"(tco));
+            float* tc = tile0 + tco;
+            float csum = 0.0f;
+            for (int i0 = tid; i0 < n4; i0 += nth * UNR) {
+                float4 nv[UNR];
+                if (do_noise) {
+#pragma unroll
+                    for (int u = 0; u < UNR; ++u)
+                        if (i0 + u * nth < n4) nv[u] = ld_stream_f4(ns + 4 * (i0 + u * nth));
+                }
+                if (!landed) { cpa_wait_all(); landed = true; }          // my own x quads are in the tile
+#pragma unroll
+                for (int u = 0; u < UNR; ++u) {
+                    const int i = i0 + u * nth;
+                    if (i < n4) {
+                        const int row = div_nq(i), quad = i - row * nq;
+                        float4* q4 = reinterpret_cast<float4*>(tc + row * WP + 4 * quad);
+                        const float4 v = noisy4(*q4, nv[u]);
+                        csum += (v.x + v.y) + (v.z + v.w);
+                        if (do_noise) *q4 = v;
+                    }
+                }
+            }
+            const float wc = (C == 3) ? (c_ == 0 ? 0.2989f : (c_ == 1 ? 0.587f : 0.114f)) : 1.0f;
+            gsum = fmaf(wc, csum, gsum);
+        }
+        cpa_wait_all();
+    } else {
+        constexpr int UNR = 4;                          // 8 independent 128-bit loads in flight per thread
+        for (int c_ = 0; c_ < C; ++c_) {
+            const float* xs = xi + c_ * HW + r0 * W;
+            const float* ns = ni + c_ * HW + r0 * W;
+            int tco = c_ * plane;
+            asm volatile("" : "+l"(xs), "+l"(ns), "+r"(tco));    // keep the bases in registers (no rematerialisation)
+            float* tc = tile0 + tco;
+            float csum = 0.0f;
+            int i0 = tid;
+            for (; i0 + (UNR - 1) * nth < n4; i0 += nth * UNR) {   // full trips: no bounds tests
+                float4 xv[UNR], nv[UNR];
+#pragma unroll
+                for (int u = 0; u < UNR; ++u) {
+                    xv[u] = ld_stream_f4(xs + 4 * (i0 + u * nth));
+                    if (do_noise) nv[u] = ld_stream_f4(ns + 4 * (i0 + u * nth));
+                }
+#pragma unroll
+                for (int u = 0; u < UNR; ++u) {
+                    const float4 v = noisy4(xv[u], nv[u]);
+                    csum += (v.x + v.y) + (v.z + v.w);
+                    const int i = i0 + u * nth, row = div_nq(i), quad = i - row * nq;
+                    *reinterpret_cast<float4*>(tc + row * WP + 4 * quad) = v;
+                }
+            }
+            for (; i0 < n4; i0 += nth) {
+                const float4 xv = ld_stream_f4(xs + 4 * i0);
+                float4 nv = xv;
+                if (do_noise) nv = ld_stream_f4(ns + 4 * i0);
+                const float4 v = noisy4(xv, nv);
+                csum += (v.x + v.y) + (v.z + v.w);
+                const int row = div_nq(i0), quad = i0 - row * nq;
+                *reinterpret_cast<float4*>(tc + row * WP + 4 * quad) = v;
+            }
+            const float wc = (C == 3) ? (c_ == 0 ? 0.2989f : (c_ == 1 ? 0.587f : 0.114f)) : 1.0f;
+            gsum = fmaf(wc, csum, gsum);
+        }
+    }
+    {
+        // Halo rows: the P image rows above and below the stripe (reflected at the image border) are
+        // fetched and perturbed again by this CTA instead of being copied from the neighbour's shared
+        // memory - 2P/R more (mostly L2-resident) reads, but no cluster barrier before the blur.
+        if constexpr (K > 1) {
+            const int nh4 = rows > 0 ? C * 2 * P * nq : 0;
+            for (int i = tid; i < nh4; i += nth) {
+                const int hr_c = div_nq(i), quad = i - hr_c * nq;
+                const int c_ = hr_c / (2 * P), hr = hr_c - c_ * (2 * P);     // compile-time divisor
+                const int lr = hr < P ? hr : rows + hr;                      // smem row: above the first / below the last own row
+                int ir = r0 - P + lr;                                        // image row before reflection
+                if (ir < 0) ir = -ir;
+                if (ir >= H) ir = 2 * (H - 1) - ir;
+                const int goff = c_ * HW + ir * W + 4 * quad;
+                const float4 xv = ld_stream_f4(xi + goff);
+                float4 nv = xv;
+                if (do_noise) nv = ld_stream_f4(ni + goff);
+                *reinterpret_cast<float4*>(tile + c_ * plane + lr * WP + kPad + 4 * quad) = noisy4(xv, nv);
+            }
+        }
+    }
+
+    // ---- phase 2 + 3: per-image gray mean, contrast blend in place (own + halo rows) ----------
+    if (do_contrast) {
+        float tot = block_sum(gsum, red);
+        if (S > 1 && !p.fake_mean) {
+            if (tid == 0) *partial = tot;
+            cluster.sync();
+            tot = 0.0f;
+            for (int q = 0; q < S; ++q) tot += *cluster.map_shared_rank(partial, q);
+            // peers must not exit before everyone has read their partial: arrive now, wait at the very end
+            asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+        }
+        const float m = tot / static_cast<float>(H * W);
+        const float cm = __fmul_rn(p.omc, m);
+        const float cf = p.c;
+        __syncthreads();
+        const int n43 = (rows > 0 ? rows + 2 * P : 0) * nq;                   // halo rows included
+        float* const tfirst = tile + kPad;
+        for (int c_ = 0; c_ < C; ++c_) {
+            float* tc = tfirst + c_ * plane;
+            for (int i = tid; i < n43; i += nth) {
+                const int row = div_nq(i), quad = i - row * nq;
+                float4* q4 = reinterpret_cast<float4*>(tc + row * WP + 4 * quad);
+                float4 v = *q4;
+                v.x = sat_add(__fmul_rn(cf, v.x), cm);       // [tv] _blend: c*x + (1-c)*mean, clamp
+                v.y = sat_add(__fmul_rn(cf, v.y), cm);
+                v.z = sat_add(__fmul_rn(cf, v.z), cm);
+                v.w = sat_add(__fmul_rn(cf, v.w), cm);
+                *q4 = v;
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- phase 4: reflected pad columns of every smem row (own + halo) ------------------------
+    if constexpr (K > 1) {
+        for (int i = tid; i < C * RS * 2; i += nth) {
+            const int side = i & 1, cr = i >> 1;
+            const int c_ = __umulhi(cr, p.magic_rs), row = cr - c_ * RS;
+            float* rowp = tile + c_ * plane + row * WP + kPad;
+            if (side == 0) { rowp[-1] = rowp[1]; rowp[-2] = rowp[2]; rowp[-3] = rowp[3]; }                       // x[-j] = x[j]
+            else { rowp[W] = rowp[W - 2]; rowp[W + 1] = rowp[W - 3]; rowp[W + 2] = rowp[W - 4]; }                // x[W-1+j] = x[W-1-j]
+        }
+        __syncthreads();
+    }
+
+    // ---- phase 5: separable blur (horizontal from smem, vertical in a register ring), cutout, store
+    float2 t2[K];
+#pragma unroll
+    for (int u = 0; u < K; ++u) t2[u] = make_float2(p.taps[u], p.taps[u]);
+    const int nsplit = p.nsplit;
+    const int rps = (rows + nsplit - 1) / nsplit;
+    const int ntasks = C * nsplit * nq;
+    const bool do_cut = (p.stages & CLIPPPO_STAGE_CUTOUT) != 0;
+    const int sw_end = p.sw + p.pw;
+    for (int task = tid; task < ntasks; task += nth) {
+        const int rest = div_nq(task), q = task - rest * nq;
+        const int c_ = nsplit == 1 ? rest : __umulhi(rest, p.magic_nsplit), sp = rest - c_ * nsplit;
+        const int ra = sp * rps, rb = min(ra + rps, rows);
+        if (ra >= rb) continue;
+        const int j0 = q * 4;
+        float2 keep01 = make_float2(1.0f, 1.0f), keep23 = keep01;
+        bool any_cut = false;
+        if (do_cut) {
+            if (j0 >= p.sw && j0 < sw_end) { keep01.x = 0.0f; any_cut = true; }
+            if (j0 + 1 >= p.sw && j0 + 1 < sw_end) { keep01.y = 0.0f; any_cut = true; }
+            if (j0 + 2 >= p.sw && j0 + 2 < sw_end) { keep23.x = 0.0f; any_cut = true; }
+            if (j0 + 3 >= p.sw && j0 + 3 < sw_end) { keep23.y = 0.0f; any_cut = true; }
+        }
+        // image rows [cut0, cut1) of this task are inside the window (empty range if the quad is outside)
+        const int cut0 = any_cut ? p.sh : 0x7fffffff, cut1 = any_cut ? p.sh + p.ph : 0;
+        const float* rowq = tile + c_ * plane + ra * WP + kPad + j0;     // tile row ra = first input row of output row ra
+        float* outq = p.out_f32() + ((static_cast<size_t>(b) * C + c_) * H + r0 + ra) * W + j0;
+        float2 ring[K][2];                       // horizontally filtered rows, slots are compile-time
+#pragma unroll
+        for (int i = 0; i < K - 1; ++i) hfilter4p<K>(rowq + i * WP, t2, ring[i]);
+        rowq += (K - 1) * WP;
+        int ir = r0 + ra;
+        // one output row: filter the newest input row into ring slot (rr + K - 1) % K, combine the K slots
+        auto out_row = [&](auto rr_c) {
+            constexpr int rr = decltype(rr_c)::value;
+            hfilter4p<K>(rowq + rr * WP, t2, ring[(rr + K - 1) % K]);
+            float2 o01 = __fmul2_rn(t2[0], ring[rr % K][0]), o23 = __fmul2_rn(t2[0], ring[rr % K][1]);
+#pragma unroll
+            for (int u = 1; u < K; ++u) {
+                o01 = __ffma2_rn(t2[u], ring[(rr + u) % K][0], o01);
+                o23 = __ffma2_rn(t2[u], ring[(rr + u) % K][1], o23);
+            }
+            const int irr = ir + rr;
+            if (irr >= cut0 && irr < cut1) { o01 = __fmul2_rn(o01, keep01); o23 = __fmul2_rn(o23, keep23); }
+            st_stream_f4(outq + rr * W, make_float4(o01.x, o01.y, o23.x, o23.y));
+        };
+        int r = ra;
+        for (; r + K <= rb; r += K) {            // full K-row blocks: the ring rotates back to slot 0, no row tests
+            static_for<K>(out_row);
+            rowq += K * WP; outq += K * W; ir += K;
+        }
+        if constexpr (K > 1) {                   // tail of < K rows
+            const int left = rb - r;
+            static_for<K - 1>([&](auto rr_c) { if ((decltype(rr_c)::value) < left) out_row(rr_c); });
+        }
+    }
+    if (do_contrast && S > 1 && !p.fake_mean) asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");   // pairs with the arrive after the partial-sum reads
 }
 
 template <int K>
@@ -430,6 +744,40 @@ static int launch_disturb(const DisturbParams& p, size_t smem, cudaStream_t stre
     return CLIPPPO_OK;
 }
 
+template <int K, int WT>
+static int launch_disturb_fast_w(const DisturbParams& p, size_t smem, cudaStream_t stream) {
+    static bool configured = false;
+    if (!configured) {
+        CLIPPPO_CUDA_TRY(cudaFuncSetAttribute(disturb_fast_kernel<K, WT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        CLIPPPO_CUDA_TRY(cudaFuncSetAttribute(disturb_fast_kernel<K, WT>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        configured = true;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(static_cast<unsigned>(p.B) * p.S);
+    cfg.blockDim = dim3(p.nthreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = p.S;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    // without the contrast stage the stripes of an image are independent: plain CTAs, no gang scheduling
+    static const int env_fake = env_int("CLIPPPO_DISTURB_FAKE", 0), env_forcecl = env_int("CLIPPPO_DISTURB_FORCECL", 0);
+    cfg.numAttrs = ((((p.stages & CLIPPPO_STAGE_CONTRAST) && p.S > 1) || env_forcecl) && !env_fake) ? 1 : 0;
+    CLIPPPO_CUDA_TRY(cudaLaunchKernelEx(&cfg, disturb_fast_kernel<K, WT>, p));
+    prof_count_launch();
+    return CLIPPPO_OK;
+}
+
+template <int K>
+static int launch_disturb_fast(const DisturbParams& p, size_t smem, cudaStream_t stream) {
+    if (p.W == 224) return launch_disturb_fast_w<K, 224>(p, smem, stream);
+    if (p.W == 84) return launch_disturb_fast_w<K, 84>(p, smem, stream);
+    return launch_disturb_fast_w<K, 0>(p, smem, stream);
+}
+
 static int env_int(const char* name, int dflt) {
     const char* e = getenv(name);
     return e ? atoi(e) : dflt;
@@ -457,14 +805,62 @@ static int run_disturb(DisturbParams& p, const float* k1d_host, int k, cudaStrea
     if (p.stages & CLIPPPO_STAGE_CUTOUT) {
         if (p.sh < 0 || p.sw < 0 || p.ph < 0 || p.pw < 0) return CLIPPPO_ERR_BAD_SHAPE;
     }
-    // stripes per image: the smallest cluster whose stripe fits the occupancy target
     const int P = K / 2;
+    if (p.fast && p.io_mode == 0 && K <= 7 && p.W >= 8) {
+        // ---- fast path (disturb_fast_kernel): padded smem rows ----
+        static const int env_nsplit = env_int("CLIPPPO_DISTURB_NSPLIT", 0);
+        auto smem_fast = [&](int S) {
+            const int R = (p.H + S - 1) / S;
+            return (size_t)(kSmemHeaderFloats + (size_t)p.C * (R + 2 * P) * (p.W + 2 * kPad)) * sizeof(float);
+        };
+        const size_t budgets[3] = {static_cast<size_t>(env_budget) * 1024, 113 * 1024, 227 * 1024};
+        int S = 0;
+        for (int bi = 0; bi < 3 && !S; ++bi)
+            for (int cand = 1; cand <= max_cluster; cand *= 2)
+                if (smem_fast(cand) <= budgets[bi]) { S = cand; break; }
+        if (!S) return CLIPPPO_ERR_UNSUPPORTED;
+        p.S = S;
+        p.R = (p.H + S - 1) / S;
+        // Blur tasks = C x nsplit x (W/4) column quads, one per thread.  A split costs 2P extra
+        // horizontally filtered rows per task; it buys warps (latency hiding) when a stripe has few quads.
+        const int nq = p.W / 4;
+        int nsplit = env_nsplit;
+        if (nsplit <= 0) {
+            nsplit = 1;
+            while (p.C * nq * nsplit < 160 && nsplit < p.R) ++nsplit;
+        }
+        if (nsplit > p.R) nsplit = p.R;
+        p.nsplit = nsplit;
+        int nthreads = (p.C * nq * nsplit + 31) / 32 * 32;
+        if (nthreads > 512) nthreads = 512;
+        if (nthreads < 64) nthreads = 64;
+        p.nthreads = nthreads;
+        p.log2S = 0;
+        while ((1 << p.log2S) < S) ++p.log2S;
+        p.fake_mean = env_int("CLIPPPO_DISTURB_FAKE", 0);
+        p.magic_nq = static_cast<unsigned>((0x100000000ull + nq - 1) / nq);
+        p.magic_nsplit = static_cast<unsigned>((0x100000000ull + nsplit - 1) / nsplit);
+        p.magic_rs = static_cast<unsigned>((0x100000000ull + (p.R + 2 * P) - 1) / (p.R + 2 * P));
+        const size_t smem = smem_fast(S);
+        int st = CLIPPPO_ERR_UNSUPPORTED;
+        switch (K) {
+            case 1: st = launch_disturb_fast<1>(p, smem, stream); break;
+            case 3: st = launch_disturb_fast<3>(p, smem, stream); break;
+            case 5: st = launch_disturb_fast<5>(p, smem, stream); break;
+            case 7: st = launch_disturb_fast<7>(p, smem, stream); break;
+        }
+        if (st == CLIPPPO_ERR_CUDA && S > 8) {      // 16-CTA cluster refused on this device / partition: portable size
+            cudaGetLastError();
+            return run_disturb(p, k1d_host, k, stream, 8);
+        }
+        return st;
+    }
+    // ---- general path (disturb_kernel): any strides, NHWC / uint8 I/O, odd widths, wide kernels ----
+    // stripes per image: the smallest cluster whose stripe fits the occupancy target
     auto smem_for = [&](int S) {
         const int R = (p.H + S - 1) / S;
         return (size_t)(kSmemHeaderFloats + (size_t)p.C * (R + 2 * P) * p.W) * sizeof(float);
     };
-    // 16-CTA clusters are "non-portable" (opt-in attribute) but schedulable on B200's 16-20-SM GPCs;
-    // they bring a 224x224x3 stripe down to 48 KB, i.e. 4 resident CTAs per SM instead of 2.
     const size_t budgets[3] = {static_cast<size_t>(env_budget) * 1024, 113 * 1024, 227 * 1024};
     int S = 0;
     for (int bi = 0; bi < 3 && !S; ++bi)

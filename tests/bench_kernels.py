@@ -42,7 +42,8 @@ def bench_disturb():
         k = D.blur_kernel_size(cfg["blur_sigma"])
         taps = D.gaussian_taps(k, cfg["blur_sigma"])
         ph, pw = D.cutout_patch(H, W, cfg["cutout"])
-        ms = timeit(lambda: D.fused_disturb(x, stages=15, noise=n, noise_sigma=cfg["noise_sigma"], contrast=1.1, taps=taps,
+        stages = int(os.environ.get("DISTURB_STAGES", "15"))
+        ms = timeit(lambda: D.fused_disturb(x, stages=stages, noise=n, noise_sigma=cfg["noise_sigma"], contrast=1.1, taps=taps,
                                             window=(3, 5, ph, pw)), iters=10 if B >= 4096 else 50)
         gb = 12.0 * B * C * H * W / 1e9
         print(f"disturb B={B} C={C} {H}x{W} {sev:8s} k={k}: {ms*1e3:9.1f} us  {gb/ms*1e3:8.1f} GB/s  "
