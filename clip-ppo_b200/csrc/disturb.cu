@@ -48,6 +48,7 @@ struct DisturbParams {
                     // 2: fp32 (0..255) NHWC in / u8 NHWC out.
     int nthreads;   // fast path: CTA size (covers the blur tasks in one round when it can)
     int log2S;      // fast path: S is a power of two
+    int ipc;        // fast path: images per cluster (> 1 => two tile buffers, the mean barrier hides behind the previous blur)
     int fake_mean;  // EXPERIMENT ONLY (CLIPPPO_DISTURB_FAKE): skip the cluster-wide mean exchange (wrong results)
     unsigned magic_nq, magic_nsplit, magic_rs;   // fast path: ceil(2^32 / d), so that __umulhi(n, magic) == n / d for n < 2^16
     __device__ __forceinline__ float* out_f32() const { return static_cast<float*>(out); }
@@ -153,6 +154,7 @@ __device__ __forceinline__ void blur_task(const float* __restrict__ base, float*
 static int env_int(const char* name, int dflt);
 
 constexpr int kPad = 4;
+constexpr int kFastMaxThreads = 384;     // x 2 CTAs / SM => at most 85 registers per thread
 
 template <int N, typename F>
 __device__ __forceinline__ void static_for(F&& f) {
@@ -188,37 +190,40 @@ __device__ __forceinline__ void hfilter4p(const float* __restrict__ rowq, const 
 
 // WT = compile-time image width (84 / 224: the reference's frame sizes; strides, quad counts and the
 // index divisions become immediates) or 0 for a run-time width.
+//
+// A cluster (the S stripe-CTAs of an image) walks `ipc` consecutive images with two tile buffers:
+//     load(i) -> publish my gray sum, cluster-barrier ARRIVE -> blur + store(i-1) -> barrier WAIT ->
+//     read the S partial sums over DSMEM -> contrast(i) -> pads(i)
+// so the only cluster-wide dependency - the per-image gray mean - is waited for while the previous
+// image is being filtered and stored; the skew between the stripe CTAs' loads (25 % of the runtime
+// when the barrier sits directly between load and contrast) disappears.
 template <int K, int WT>
-__global__ void __launch_bounds__(512)
+__global__ void __launch_bounds__(kFastMaxThreads, 2)
 disturb_fast_kernel(const __grid_constant__ DisturbParams p) {
     constexpr int P = K / 2;
     extern __shared__ __align__(16) float smem[];
     float* red = smem;
-    float* partial = smem + 32;
-    float* tile = smem + kSmemHeaderFloats;
+    float* partial = smem + 32;               // [2]: one slot per in-flight image
+    float* tiles = smem + kSmemHeaderFloats;
 
     cg::cluster_group cluster = cg::this_cluster();
     const int S = p.S, R = p.R, C = p.C, H = p.H, W = WT ? WT : p.W;
-    const int b = blockIdx.x >> p.log2S, s = blockIdx.x & (S - 1);
+    const int grp = blockIdx.x >> p.log2S, s = blockIdx.x & (S - 1);
+    const int b_first = grp * p.ipc, n_img = min(p.ipc, p.B - b_first);
     const int r0 = min(s * R, H), r1 = min(r0 + R, H), rows = r1 - r0;
     const int WP = W + 2 * kPad;              // smem row pitch (floats)
     const int RS = R + 2 * P;                 // smem rows per channel: P halo rows above, R own rows, P below
     const int plane = RS * WP;                // smem floats per channel
+    const int tile_floats = C * plane;
     const int nq = W >> 2;
     auto div_nq = [&](int i) { return WT ? i / (WT >> 2 ? WT >> 2 : 1) : static_cast<int>(__umulhi(i, p.magic_nq)); };
     const int tid = threadIdx.x, nth = blockDim.x;
     const bool do_noise = (p.stages & CLIPPPO_STAGE_NOISE) != 0;
     const bool do_contrast = (p.stages & CLIPPPO_STAGE_CONTRAST) != 0;
+    const bool exchange = do_contrast && S > 1 && !p.fake_mean;     // the gray mean spans several CTAs
     const float sigma = p.sigma_n;
-    // Phases 1 and 3 walk a channel's stripe linearly (it is contiguous in global memory), one quad
-    // per thread and step; quad index -> (row, quad-in-row) is a multiply-high by a host-computed
-    // reciprocal; global offsets are 32-bit from one per-image base pointer.
     const int n4 = rows * nq;
-    const size_t img_off = static_cast<size_t>(b) * C * H * W;
-    const float* __restrict__ xi = static_cast<const float*>(p.x) + img_off;
-    const float* __restrict__ ni = do_noise ? p.noise + img_off : xi;
     const int HW = H * W;
-    float* const tile0 = tile + P * WP + kPad;          // first own row, first real column
 
     auto noisy4 = [&](float4 v, const float4& nz) {     // [tv] gaussian_noise_image: mul, add, clamp - no FMA contraction (bit-exact)
         if (do_noise) {
@@ -230,54 +235,16 @@ disturb_fast_kernel(const __grid_constant__ DisturbParams p) {
         return v;
     };
 
-    // ---- phase 1: x (+ sigma * noise, clamp) -> smem, gray sum over the OWN rows --------------
-    float gsum = 0.0f;
-    if (p.p1_mode == 1) {
-        // x goes straight into the tile with cp.async: the whole stripe (own + halo rows) is requested
-        // up front without holding a register, the noise follows through registers 8 quads at a time.
-        // Bytes in flight per CTA: all of x plus 8 x 16 B of noise per thread.
-        for (int c_ = 0; c_ < C; ++c_) {
-            const float* xs = xi + c_ * HW + r0 * W;
-            const uint32_t tcs = ptx_smem(tile0 + c_ * plane);
-            for (int i = tid; i < n4; i += nth) {
-                const int row = div_nq(i), quad = i - row * nq;
-                cpa16(tcs + (row * WP + 4 * quad) * 4, xs + 4 * i);
-            }
-        }
-        cpa_commit();
-        constexpr int UNR = 8;
-        bool landed = false;
-        for (int c_ = 0; c_ < C; ++c_) {
-            const float* ns = ni + c_ * HW + r0 * W;
-            int tco = c_ * plane;
-            asm volatile("" : "+l"(ns), "+r"(tco));
-            float* tc = tile0 + tco;
-            float csum = 0.0f;
-            for (int i0 = tid; i0 < n4; i0 += nth * UNR) {
-                float4 nv[UNR];
-                if (do_noise) {
-#pragma unroll
-                    for (int u = 0; u < UNR; ++u)
-                        if (i0 + u * nth < n4) nv[u] = ld_stream_f4(ns + 4 * (i0 + u * nth));
-                }
-                if (!landed) { cpa_wait_all(); landed = true; }          // my own x quads are in the tile
-#pragma unroll
-                for (int u = 0; u < UNR; ++u) {
-                    const int i = i0 + u * nth;
-                    if (i < n4) {
-                        const int row = div_nq(i), quad = i - row * nq;
-                        float4* q4 = reinterpret_cast<float4*>(tc + row * WP + 4 * quad);
-                        const float4 v = noisy4(*q4, nv[u]);
-                        csum += (v.x + v.y) + (v.z + v.w);
-                        if (do_noise) *q4 = v;
-                    }
-                }
-            }
-            const float wc = (C == 3) ? (c_ == 0 ? 0.2989f : (c_ == 1 ? 0.587f : 0.114f)) : 1.0f;
-            gsum = fmaf(wc, csum, gsum);
-        }
-        cpa_wait_all();
-    } else {
+    // ---- load: x (+ sigma * noise, clamp) -> tile; returns this thread's share of the gray sum over the OWN rows.
+    // The stripe of a channel is contiguous in global memory and is walked linearly, one quad per thread
+    // and step; quad index -> (row, quad-in-row) is a multiply-high by a reciprocal (an immediate when the
+    // width is a template constant); global offsets are 32-bit from one per-image base pointer.
+    auto load_image = [&](int b, float* tile) {
+        const size_t img_off = static_cast<size_t>(b) * C * H * W;
+        const float* __restrict__ xi = static_cast<const float*>(p.x) + img_off;
+        const float* __restrict__ ni = do_noise ? p.noise + img_off : xi;
+        float* const tile0 = tile + P * WP + kPad;      // first own row, first real column
+        float gsum = 0.0f;
         constexpr int UNR = 4;                          // 8 independent 128-bit loads in flight per thread
         for (int c_ = 0; c_ < C; ++c_) {
             const float* xs = xi + c_ * HW + r0 * W;
@@ -314,8 +281,6 @@ disturb_fast_kernel(const __grid_constant__ DisturbParams p) {
             const float wc = (C == 3) ? (c_ == 0 ? 0.2989f : (c_ == 1 ? 0.587f : 0.114f)) : 1.0f;
             gsum = fmaf(wc, csum, gsum);
         }
-    }
-    {
         // Halo rows: the P image rows above and below the stripe (reflected at the image border) are
         // fetched and perturbed again by this CTA instead of being copied from the neighbour's shared
         // memory - 2P/R more (mostly L2-resident) reads, but no cluster barrier before the blur.
@@ -335,54 +300,44 @@ disturb_fast_kernel(const __grid_constant__ DisturbParams p) {
                 *reinterpret_cast<float4*>(tile + c_ * plane + lr * WP + kPad + 4 * quad) = noisy4(xv, nv);
             }
         }
-    }
+        return gsum;
+    };
 
-    // ---- phase 2 + 3: per-image gray mean, contrast blend in place (own + halo rows) ----------
-    if (do_contrast) {
-        float tot = block_sum(gsum, red);
-        if (S > 1 && !p.fake_mean) {
-            if (tid == 0) *partial = tot;
-            cluster.sync();
-            tot = 0.0f;
-            for (int q = 0; q < S; ++q) tot += *cluster.map_shared_rank(partial, q);
-            // peers must not exit before everyone has read their partial: arrive now, wait at the very end
-            asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-        }
+    // ---- contrast blend in place over own + halo rows: [tv] _blend: c*x + (1-c)*mean, clamp ----
+    auto contrast_image = [&](float* tile, float tot) {
         const float m = tot / static_cast<float>(H * W);
         const float cm = __fmul_rn(p.omc, m);
         const float cf = p.c;
-        __syncthreads();
-        const int n43 = (rows > 0 ? rows + 2 * P : 0) * nq;                   // halo rows included
-        float* const tfirst = tile + kPad;
+        const int n43 = (rows > 0 ? rows + 2 * P : 0) * nq;
         for (int c_ = 0; c_ < C; ++c_) {
-            float* tc = tfirst + c_ * plane;
+            float* tc = tile + kPad + c_ * plane;
             for (int i = tid; i < n43; i += nth) {
                 const int row = div_nq(i), quad = i - row * nq;
                 float4* q4 = reinterpret_cast<float4*>(tc + row * WP + 4 * quad);
                 float4 v = *q4;
-                v.x = sat_add(__fmul_rn(cf, v.x), cm);       // [tv] _blend: c*x + (1-c)*mean, clamp
+                v.x = sat_add(__fmul_rn(cf, v.x), cm);
                 v.y = sat_add(__fmul_rn(cf, v.y), cm);
                 v.z = sat_add(__fmul_rn(cf, v.z), cm);
                 v.w = sat_add(__fmul_rn(cf, v.w), cm);
                 *q4 = v;
             }
         }
-    }
-    __syncthreads();
+    };
 
-    // ---- phase 4: reflected pad columns of every smem row (own + halo) ------------------------
-    if constexpr (K > 1) {
-        for (int i = tid; i < C * RS * 2; i += nth) {
-            const int side = i & 1, cr = i >> 1;
-            const int c_ = __umulhi(cr, p.magic_rs), row = cr - c_ * RS;
-            float* rowp = tile + c_ * plane + row * WP + kPad;
-            if (side == 0) { rowp[-1] = rowp[1]; rowp[-2] = rowp[2]; rowp[-3] = rowp[3]; }                       // x[-j] = x[j]
-            else { rowp[W] = rowp[W - 2]; rowp[W + 1] = rowp[W - 3]; rowp[W + 2] = rowp[W - 4]; }                // x[W-1+j] = x[W-1-j]
+    // ---- reflected pad columns of every smem row (own + halo) ----
+    auto pad_image = [&](float* tile) {
+        if constexpr (K > 1) {
+            for (int i = tid; i < C * RS * 2; i += nth) {
+                const int side = i & 1, cr = i >> 1;
+                const int c_ = __umulhi(cr, p.magic_rs), row = cr - c_ * RS;
+                float* rowp = tile + c_ * plane + row * WP + kPad;
+                if (side == 0) { rowp[-1] = rowp[1]; rowp[-2] = rowp[2]; rowp[-3] = rowp[3]; }            // x[-j] = x[j]
+                else { rowp[W] = rowp[W - 2]; rowp[W + 1] = rowp[W - 3]; rowp[W + 2] = rowp[W - 4]; }     // x[W-1+j] = x[W-1-j]
+            }
         }
-        __syncthreads();
-    }
+    };
 
-    // ---- phase 5: separable blur (horizontal from smem, vertical in a register ring), cutout, store
+    // ---- separable blur (horizontal from smem, vertical in a register ring), cutout, store ----
     float2 t2[K];
 #pragma unroll
     for (int u = 0; u < K; ++u) t2[u] = make_float2(p.taps[u], p.taps[u]);
@@ -391,54 +346,87 @@ disturb_fast_kernel(const __grid_constant__ DisturbParams p) {
     const int ntasks = C * nsplit * nq;
     const bool do_cut = (p.stages & CLIPPPO_STAGE_CUTOUT) != 0;
     const int sw_end = p.sw + p.pw;
-    for (int task = tid; task < ntasks; task += nth) {
-        const int rest = div_nq(task), q = task - rest * nq;
-        const int c_ = nsplit == 1 ? rest : __umulhi(rest, p.magic_nsplit), sp = rest - c_ * nsplit;
-        const int ra = sp * rps, rb = min(ra + rps, rows);
-        if (ra >= rb) continue;
-        const int j0 = q * 4;
-        float2 keep01 = make_float2(1.0f, 1.0f), keep23 = keep01;
-        bool any_cut = false;
-        if (do_cut) {
-            if (j0 >= p.sw && j0 < sw_end) { keep01.x = 0.0f; any_cut = true; }
-            if (j0 + 1 >= p.sw && j0 + 1 < sw_end) { keep01.y = 0.0f; any_cut = true; }
-            if (j0 + 2 >= p.sw && j0 + 2 < sw_end) { keep23.x = 0.0f; any_cut = true; }
-            if (j0 + 3 >= p.sw && j0 + 3 < sw_end) { keep23.y = 0.0f; any_cut = true; }
-        }
-        // image rows [cut0, cut1) of this task are inside the window (empty range if the quad is outside)
-        const int cut0 = any_cut ? p.sh : 0x7fffffff, cut1 = any_cut ? p.sh + p.ph : 0;
-        const float* rowq = tile + c_ * plane + ra * WP + kPad + j0;     // tile row ra = first input row of output row ra
-        float* outq = p.out_f32() + ((static_cast<size_t>(b) * C + c_) * H + r0 + ra) * W + j0;
-        float2 ring[K][2];                       // horizontally filtered rows, slots are compile-time
-#pragma unroll
-        for (int i = 0; i < K - 1; ++i) hfilter4p<K>(rowq + i * WP, t2, ring[i]);
-        rowq += (K - 1) * WP;
-        int ir = r0 + ra;
-        // one output row: filter the newest input row into ring slot (rr + K - 1) % K, combine the K slots
-        auto out_row = [&](auto rr_c) {
-            constexpr int rr = decltype(rr_c)::value;
-            hfilter4p<K>(rowq + rr * WP, t2, ring[(rr + K - 1) % K]);
-            float2 o01 = __fmul2_rn(t2[0], ring[rr % K][0]), o23 = __fmul2_rn(t2[0], ring[rr % K][1]);
-#pragma unroll
-            for (int u = 1; u < K; ++u) {
-                o01 = __ffma2_rn(t2[u], ring[(rr + u) % K][0], o01);
-                o23 = __ffma2_rn(t2[u], ring[(rr + u) % K][1], o23);
+    auto blur_image = [&](int b, const float* tile) {
+        for (int task = tid; task < ntasks; task += nth) {
+            const int rest = div_nq(task), q = task - rest * nq;
+            const int c_ = nsplit == 1 ? rest : __umulhi(rest, p.magic_nsplit), sp = rest - c_ * nsplit;
+            const int ra = sp * rps, rb = min(ra + rps, rows);
+            if (ra >= rb) continue;
+            const int j0 = q * 4;
+            float2 keep01 = make_float2(1.0f, 1.0f), keep23 = keep01;
+            bool any_cut = false;
+            if (do_cut) {
+                if (j0 >= p.sw && j0 < sw_end) { keep01.x = 0.0f; any_cut = true; }
+                if (j0 + 1 >= p.sw && j0 + 1 < sw_end) { keep01.y = 0.0f; any_cut = true; }
+                if (j0 + 2 >= p.sw && j0 + 2 < sw_end) { keep23.x = 0.0f; any_cut = true; }
+                if (j0 + 3 >= p.sw && j0 + 3 < sw_end) { keep23.y = 0.0f; any_cut = true; }
             }
-            const int irr = ir + rr;
-            if (irr >= cut0 && irr < cut1) { o01 = __fmul2_rn(o01, keep01); o23 = __fmul2_rn(o23, keep23); }
-            st_stream_f4(outq + rr * W, make_float4(o01.x, o01.y, o23.x, o23.y));
-        };
-        int r = ra;
-        for (; r + K <= rb; r += K) {            // full K-row blocks: the ring rotates back to slot 0, no row tests
-            static_for<K>(out_row);
-            rowq += K * WP; outq += K * W; ir += K;
+            // image rows [cut0, cut1) of this task are inside the window (empty range if the quad is outside)
+            const int cut0 = any_cut ? p.sh : 0x7fffffff, cut1 = any_cut ? p.sh + p.ph : 0;
+            const float* rowq = tile + c_ * plane + ra * WP + kPad + j0;     // tile row ra = first input row of output row ra
+            float* outq = p.out_f32() + ((static_cast<size_t>(b) * C + c_) * H + r0 + ra) * W + j0;
+            float2 ring[K][2];                       // horizontally filtered rows, slots are compile-time
+#pragma unroll
+            for (int i = 0; i < K - 1; ++i) hfilter4p<K>(rowq + i * WP, t2, ring[i]);
+            rowq += (K - 1) * WP;
+            int ir = r0 + ra;
+            // one output row: filter the newest input row into ring slot (rr + K - 1) % K, combine the K slots
+            auto out_row = [&](auto rr_c) {
+                constexpr int rr = decltype(rr_c)::value;
+                hfilter4p<K>(rowq + rr * WP, t2, ring[(rr + K - 1) % K]);
+                float2 o01 = __fmul2_rn(t2[0], ring[rr % K][0]), o23 = __fmul2_rn(t2[0], ring[rr % K][1]);
+#pragma unroll
+                for (int u = 1; u < K; ++u) {
+                    o01 = __ffma2_rn(t2[u], ring[(rr + u) % K][0], o01);
+                    o23 = __ffma2_rn(t2[u], ring[(rr + u) % K][1], o23);
+                }
+                const int irr = ir + rr;
+                if (irr >= cut0 && irr < cut1) { o01 = __fmul2_rn(o01, keep01); o23 = __fmul2_rn(o23, keep23); }
+                st_stream_f4(outq + rr * W, make_float4(o01.x, o01.y, o23.x, o23.y));
+            };
+            int r = ra;
+            for (; r + K <= rb; r += K) {            // full K-row blocks: the ring rotates back to slot 0, no row tests
+                static_for<K>(out_row);
+                rowq += K * WP; outq += K * W; ir += K;
+            }
+            if constexpr (K > 1) {                   // tail of < K rows
+                const int left = rb - r;
+                static_for<K - 1>([&](auto rr_c) { if ((decltype(rr_c)::value) < left) out_row(rr_c); });
+            }
         }
-        if constexpr (K > 1) {                   // tail of < K rows
-            const int left = rb - r;
-            static_for<K - 1>([&](auto rr_c) { if ((decltype(rr_c)::value) < left) out_row(rr_c); });
+    };
+
+    // ---- the pipeline over this cluster's images ----
+    for (int it = 0; it <= n_img; ++it) {
+        float* tcur = tiles + (it & 1) * tile_floats;
+        float tot = 0.0f;
+        if (it < n_img) {
+            const float g = load_image(b_first + it, tcur);
+            if (do_contrast) {
+                tot = block_sum(g, red);
+                if (exchange) {
+                    if (tid == 0) partial[it & 1] = tot;
+                    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+                }
+            }
+        }
+        if (it > 0) blur_image(b_first + it - 1, tiles + ((it - 1) & 1) * tile_floats);
+        if (it < n_img) {
+            if (do_contrast) {
+                if (exchange) {
+                    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+                    tot = 0.0f;
+                    for (int q = 0; q < S; ++q) tot += *cluster.map_shared_rank(partial + (it & 1), q);
+                }
+                __syncthreads();                 // the tile is complete (block_sum's barriers precede the peers' reads only)
+                contrast_image(tcur, tot);
+            }
+            __syncthreads();
+            pad_image(tcur);
+            __syncthreads();
         }
     }
-    if (do_contrast && S > 1 && !p.fake_mean) asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");   // pairs with the arrive after the partial-sum reads
+    if (exchange) cluster.sync();                    // nobody exits while a peer may still read its partial sums
 }
 
 template <int K>
@@ -753,7 +741,7 @@ static int launch_disturb_fast_w(const DisturbParams& p, size_t smem, cudaStream
         configured = true;
     }
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(static_cast<unsigned>(p.B) * p.S);
+    cfg.gridDim = dim3(static_cast<unsigned>((p.B + p.ipc - 1) / p.ipc) * p.S);
     cfg.blockDim = dim3(p.nthreads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
@@ -784,7 +772,7 @@ static int env_int(const char* name, int dflt) {
 }
 
 static int run_disturb(DisturbParams& p, const float* k1d_host, int k, cudaStream_t stream, int max_cluster = 0) {
-    static const int env_cl = env_int("CLIPPPO_DISTURB_MAXCL", 8), env_p1 = env_int("CLIPPPO_DISTURB_P1", 0);
+    static const int env_cl = env_int("CLIPPPO_DISTURB_MAXCL", 16), env_p1 = env_int("CLIPPPO_DISTURB_P1", 0);
     static const int env_budget = env_int("CLIPPPO_DISTURB_SMEM_KB", 56);
     if (max_cluster == 0) max_cluster = env_cl;
     p.p1_mode = env_p1;
@@ -808,19 +796,35 @@ static int run_disturb(DisturbParams& p, const float* k1d_host, int k, cudaStrea
     const int P = K / 2;
     if (p.fast && p.io_mode == 0 && K <= 7 && p.W >= 8) {
         // ---- fast path (disturb_fast_kernel): padded smem rows ----
-        static const int env_nsplit = env_int("CLIPPPO_DISTURB_NSPLIT", 0);
-        auto smem_fast = [&](int S) {
+        static const int env_nsplit = env_int("CLIPPPO_DISTURB_NSPLIT", 0), env_ipc = env_int("CLIPPPO_DISTURB_IPC", 0);
+        auto tile_bytes = [&](int S) {
             const int R = (p.H + S - 1) / S;
-            return (size_t)(kSmemHeaderFloats + (size_t)p.C * (R + 2 * P) * (p.W + 2 * kPad)) * sizeof(float);
+            return (size_t)p.C * (R + 2 * P) * (p.W + 2 * kPad) * sizeof(float);
         };
-        const size_t budgets[3] = {static_cast<size_t>(env_budget) * 1024, 113 * 1024, 227 * 1024};
-        int S = 0;
-        for (int bi = 0; bi < 3 && !S; ++bi)
-            for (int cand = 1; cand <= max_cluster; cand *= 2)
-                if (smem_fast(cand) <= budgets[bi]) { S = cand; break; }
+        const size_t hdr = kSmemHeaderFloats * sizeof(float);
+        const bool contrast = (p.stages & CLIPPPO_STAGE_CONTRAST) != 0;
+        // Stripes per image: the smallest cluster whose stripe (+ halo rows) fits the occupancy budget
+        // (56 KB = 4 CTAs / SM, then 113 KB = 2, then a whole SM).
+        // CLIPPPO_DISTURB_IPC > 1 switches on the two-tile pipeline (a cluster walks `ipc` images and waits
+        // for the gray mean of image i while it filters image i-1).  Measured on B200 (profiles/): it removes
+        // the barrier stall but needs 2 x the shared memory, i.e. half the resident CTAs, and this kernel
+        // lives on resident warps - 36 % of HBM peak against 57 % without it.  Off by default.
+        int S = 0, ipc = 1;
+        if (env_ipc > 1 && contrast) {
+            for (int cand = 2; cand <= max_cluster; cand *= 2)
+                if (2 * tile_bytes(cand) + hdr <= 113 * 1024) { S = cand; break; }
+            if (S) ipc = env_ipc;
+        }
+        if (!S) {
+            const size_t budgets[3] = {static_cast<size_t>(env_budget) * 1024, 113 * 1024, 227 * 1024};
+            for (int bi = 0; bi < 3 && !S; ++bi)
+                for (int cand = 1; cand <= max_cluster; cand *= 2)
+                    if (tile_bytes(cand) + hdr <= budgets[bi]) { S = cand; break; }
+        }
         if (!S) return CLIPPPO_ERR_UNSUPPORTED;
         p.S = S;
         p.R = (p.H + S - 1) / S;
+        p.ipc = ipc;
         // Blur tasks = C x nsplit x (W/4) column quads, one per thread.  A split costs 2P extra
         // horizontally filtered rows per task; it buys warps (latency hiding) when a stripe has few quads.
         const int nq = p.W / 4;
@@ -832,7 +836,7 @@ static int run_disturb(DisturbParams& p, const float* k1d_host, int k, cudaStrea
         if (nsplit > p.R) nsplit = p.R;
         p.nsplit = nsplit;
         int nthreads = (p.C * nq * nsplit + 31) / 32 * 32;
-        if (nthreads > 512) nthreads = 512;
+        if (nthreads > kFastMaxThreads) nthreads = kFastMaxThreads;
         if (nthreads < 64) nthreads = 64;
         p.nthreads = nthreads;
         p.log2S = 0;
@@ -841,7 +845,7 @@ static int run_disturb(DisturbParams& p, const float* k1d_host, int k, cudaStrea
         p.magic_nq = static_cast<unsigned>((0x100000000ull + nq - 1) / nq);
         p.magic_nsplit = static_cast<unsigned>((0x100000000ull + nsplit - 1) / nsplit);
         p.magic_rs = static_cast<unsigned>((0x100000000ull + (p.R + 2 * P) - 1) / (p.R + 2 * P));
-        const size_t smem = smem_fast(S);
+        const size_t smem = hdr + (ipc > 1 ? 2 : 1) * tile_bytes(S);
         int st = CLIPPPO_ERR_UNSUPPORTED;
         switch (K) {
             case 1: st = launch_disturb_fast<1>(p, smem, stream); break;
@@ -864,7 +868,7 @@ static int run_disturb(DisturbParams& p, const float* k1d_host, int k, cudaStrea
     const size_t budgets[3] = {static_cast<size_t>(env_budget) * 1024, 113 * 1024, 227 * 1024};
     int S = 0;
     for (int bi = 0; bi < 3 && !S; ++bi)
-        for (int cand = 1; cand <= max_cluster; cand *= 2)
+        for (int cand = 1; cand <= max_cluster && cand <= 8; cand *= 2)
             if (smem_for(cand) <= budgets[bi]) { S = cand; break; }
     if (!S) return CLIPPPO_ERR_UNSUPPORTED;
     p.S = S;
