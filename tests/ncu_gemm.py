@@ -1,4 +1,5 @@
-"""Not a test: a short GEMM-only run for `ncu --set full` captures (one tower chunk's shapes)."""
+"""Not a test: a short GEMM-only run for `ncu --set full` captures - the four GEMM shapes of one
+tower block at the bench's chunk size, with the epilogues the tower runs them with."""
 import os
 import sys
 
@@ -10,14 +11,18 @@ from clip_ppo_b200 import _native as N
 
 L = N.lib()
 st = torch.cuda.current_stream().cuda_stream
-M = 25050                                            # 501 images x 50 tokens
+M = int(sys.argv[1]) if len(sys.argv) > 1 else 51200          # 1024 images x 50 tokens
 gen = torch.Generator(device="cuda").manual_seed(0)
-for (Nn, K, epi) in ((2304, 768, 0), (3072, 768, 1), (768, 3072, 2), (768, 768, 2)):
+for (Nn, K, epi) in ((2304, 768, 6), (3072, 768, 7), (768, 3072, 8), (768, 768, 8)):
     a = (torch.randn(M, K, device="cuda", generator=gen) * 0.5).bfloat16()
     w = (torch.randn(Nn, K, device="cuda", generator=gen) * (K ** -0.5)).bfloat16()
     bias = torch.randn(Nn, device="cuda", generator=gen) * 0.1
-    out = torch.zeros(M, Nn, device="cuda", dtype=torch.bfloat16 if epi in (0, 1) else torch.float32)
+    out = torch.zeros(M, Nn, device="cuda", dtype=torch.bfloat16)
+    stats = torch.stack([torch.zeros(M, device="cuda"), torch.ones(M, device="cuda")], 1).contiguous()
+    colsum = w.float().sum(1).contiguous()
     for _ in range(2):
-        N.check(L.clipppo_gemm_bf16(a.data_ptr(), w.data_ptr(), M, Nn, K, epi, bias.data_ptr(), None, 0, out.data_ptr(), Nn, st))
+        N.check(L.clipppo_gemm_bf16_fused(a.data_ptr(), w.data_ptr(), M, Nn, K, epi, bias.data_ptr(),
+                                          stats.data_ptr() if epi < 8 else None, colsum.data_ptr() if epi < 8 else None,
+                                          out.data_ptr(), Nn, st))
     torch.cuda.synchronize()
 print("done")
