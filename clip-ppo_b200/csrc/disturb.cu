@@ -239,7 +239,7 @@ disturb_fast_kernel(const __grid_constant__ DisturbParams p) {
     // The stripe of a channel is contiguous in global memory and is walked linearly, one quad per thread
     // and step; quad index -> (row, quad-in-row) is a multiply-high by a reciprocal (an immediate when the
     // width is a template constant); global offsets are 32-bit from one per-image base pointer.
-    auto load_image = [&](int b, float* tile) {
+    auto load_own = [&](int b, float* tile) {
         const size_t img_off = static_cast<size_t>(b) * C * H * W;
         const float* __restrict__ xi = static_cast<const float*>(p.x) + img_off;
         const float* __restrict__ ni = do_noise ? p.noise + img_off : xi;
@@ -281,9 +281,16 @@ disturb_fast_kernel(const __grid_constant__ DisturbParams p) {
             const float wc = (C == 3) ? (c_ == 0 ? 0.2989f : (c_ == 1 ? 0.587f : 0.114f)) : 1.0f;
             gsum = fmaf(wc, csum, gsum);
         }
-        // Halo rows: the P image rows above and below the stripe (reflected at the image border) are
-        // fetched and perturbed again by this CTA instead of being copied from the neighbour's shared
-        // memory - 2P/R more (mostly L2-resident) reads, but no cluster barrier before the blur.
+        return gsum;
+    };
+    // Halo rows: the P image rows above and below the stripe (reflected at the image border) are
+    // fetched and perturbed again by this CTA instead of being copied from the neighbour's shared
+    // memory - 2P/R more (mostly L2-resident) reads, but no cluster barrier before the blur.  They are
+    // not part of the gray sum, so they load between the ARRIVE and the WAIT of the mean barrier.
+    auto load_halo = [&](int b, float* tile) {
+        const size_t img_off = static_cast<size_t>(b) * C * H * W;
+        const float* __restrict__ xi = static_cast<const float*>(p.x) + img_off;
+        const float* __restrict__ ni = do_noise ? p.noise + img_off : xi;
         if constexpr (K > 1) {
             const int nh4 = rows > 0 ? C * 2 * P * nq : 0;
             for (int i = tid; i < nh4; i += nth) {
@@ -300,7 +307,6 @@ disturb_fast_kernel(const __grid_constant__ DisturbParams p) {
                 *reinterpret_cast<float4*>(tile + c_ * plane + lr * WP + kPad + 4 * quad) = noisy4(xv, nv);
             }
         }
-        return gsum;
     };
 
     // ---- contrast blend in place over own + halo rows: [tv] _blend: c*x + (1-c)*mean, clamp ----
@@ -401,7 +407,7 @@ disturb_fast_kernel(const __grid_constant__ DisturbParams p) {
         float* tcur = tiles + (it & 1) * tile_floats;
         float tot = 0.0f;
         if (it < n_img) {
-            const float g = load_image(b_first + it, tcur);
+            const float g = load_own(b_first + it, tcur);
             if (do_contrast) {
                 tot = block_sum(g, red);
                 if (exchange) {
@@ -409,6 +415,7 @@ disturb_fast_kernel(const __grid_constant__ DisturbParams p) {
                     asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
                 }
             }
+            load_halo(b_first + it, tcur);
         }
         if (it > 0) blur_image(b_first + it - 1, tiles + ((it - 1) & 1) * tile_floats);
         if (it < n_img) {
