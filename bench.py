@@ -40,6 +40,7 @@ import torch
 
 METRIC = "CLIP-PPO frames/sec (disturb+ViT-B/32 embed+align loss)"
 FLOPS_PER_IMAGE = 8.8176e9          # SURVEY.md §8d, ViT-B/32, all 50 tokens through 12 layers
+FLOPS_PER_IMAGE_BY_MODEL = {"ViT-B/32": 8.8176e9, "ViT-L/14": 162.03e9}
 AGENT_GRAD_ELEMS = 1_686_180        # MiniGrid NatureCNN agent fp32 grads, 7 actions
 
 
@@ -52,6 +53,8 @@ def parse():
     ap.add_argument("--batch", type=int, default=4096, help="frames per GPU per step")
     ap.add_argument("--hw", type=int, default=224)
     ap.add_argument("--severity", default="MODERATE")
+    ap.add_argument("--model", default="ViT-B/32", choices=["ViT-B/32", "ViT-L/14"],
+                    help="image tower (the headline is ViT-B/32; ViT-L/14 is BASELINE configs[4]'s variant)")
     ap.add_argument("--ref-batch", type=int, default=64, help="frames per step of the CPU reference arm")
     ap.add_argument("--cpu-sample", type=int, default=192, help="frames of the cpu_baseline sample")
     ap.add_argument("--no-e2e", action="store_true")
@@ -167,9 +170,9 @@ def run_reference_arm(args):
 
 def workload_config(args, per_gpu_batch):
     return {"workload": f"BASELINE configs[2]: synthetic {args.hw}x{args.hw} RGB frames, disturb({args.severity}) -> "
-                        f"ViT-B/32 embed -> cosine alignment loss",
+                        f"{args.model} embed -> cosine alignment loss",
             "per_gpu_batch": per_gpu_batch, "frame": [3, args.hw, args.hw], "severity": args.severity,
-            "weights": "seeded random ViT-B/32 (openai key layout)",
+            "weights": f"seeded random {args.model} (openai key layout)",
             "l2_policy": "inputs larger than L2 (x + noise = 4.9 GB per step at 4096 frames); no flush needed",
             "parallelism": f"dp{args.gpus} by observation, frozen tower replicated, grad-bucket all-reduce only"}
 
@@ -201,7 +204,7 @@ def main():
 
     L = N.lib()                                   # raises if the CUDA library is missing: no fallback
     B, hw = args.batch, args.hw
-    model = U.load_clip_model("ViT-B/32", device=dev)
+    model = U.load_clip_model(args.model, device=dev)
     engine = U._engine_for(model)
     disturber = DisturbanceWrapperGPU(device=dev, seed=1234 + rank, severity=DisturbanceSeverity[args.severity])
     ph, pw = D.cutout_patch(hw, hw, disturber.cutout_ratio)
@@ -210,7 +213,7 @@ def main():
     g = torch.Generator(device=dev).manual_seed(rank)
     x = torch.randint(0, 256, (B, 3, hw, hw), device=dev, generator=g, dtype=torch.uint8).float().div_(255.0)
     noise = torch.randn(B, 3, hw, hw, device=dev, generator=g)
-    z = torch.relu(torch.randn(B, 512, device=dev, generator=g))
+    z = torch.relu(torch.randn(B, engine.cfg.out_dim, device=dev, generator=g))
     grad_bucket = torch.zeros(AGENT_GRAD_ELEMS, device=dev) if world > 1 else None
 
     def step_device():
@@ -344,7 +347,7 @@ def main():
                      "frac": tf_ach / pk["tf_sustained"], "traffic": ncu_traffic,
                      "peak_source": f"{pk['source']} bf16 sustained (kernel timed inside a long step)",
                      "launches_timed": int(gemm_launches.value), "share_of_step": tower_share, "by_shape": by_shape,
-                     "tower_tflops_incl_all_kernels": world * B * args.steps * FLOPS_PER_IMAGE / (ms_total * 1e-3) / 1e12 / world},
+                     "tower_tflops_incl_all_kernels": world * B * args.steps * FLOPS_PER_IMAGE_BY_MODEL[args.model] / (ms_total * 1e-3) / 1e12 / world},
         "loss": loss_value,
     }
     if e2e is not None:

@@ -153,10 +153,11 @@ def test_layernorm_vs_torch(native, rows, width):
     assert (y.float() - ref.bfloat16().float()).abs().mean().item() <= 1e-4
 
 
-@pytest.mark.parametrize("n,T", [(1, 50), (37, 50), (3, 17), (2, 64)])
-def test_attention_vs_torch(native, n, T):
+@pytest.mark.parametrize("n,T,H", [(1, 50, 12), (37, 50, 12), (3, 17, 12), (2, 64, 12),
+                                   (2, 257, 16), (3, 65, 12), (1, 128, 16), (2, 200, 12)])      # T > 64: key-block kernel (ViT-L/14)
+def test_attention_vs_torch(native, n, T, H):
     from clip_ppo_b200 import _native as Nn
-    H, dh = 12, 64
+    dh = 64
     D = H * dh
     gen = torch.Generator(device="cuda").manual_seed(n * 100 + T)
     qkv = torch.randn(n * T, 3 * D, device="cuda", generator=gen).bfloat16()
@@ -234,6 +235,23 @@ def test_embeddings_vs_oracle(native, n, hw):
     # batch-size invariance: an image encoded alone == encoded inside the batch (bitwise)
     alone = eng.encode(img[idx[-1:]].cuda(), pre_scale=1 / 255.0, l2norm=True).cpu()
     assert torch.equal(alone[0], emb[idx[-1]])
+
+
+def test_vit_l14_embeddings_vs_oracle(native):
+    """BASELINE configs[4] variant: ViT-L/14 (width 1024, 24 blocks, 16 heads, patch 14, 257 tokens, out 768)."""
+    from clip_ppo_b200.clip_compat.model import random_visual_state_dict
+    from clip_ppo_b200.vit import VitEngine
+    eng = VitEngine(random_visual_state_dict("ViT-L/14", 0), device="cuda")
+    sd = ov.random_state_dict(ov.VIT_L14, 0)
+    gen = torch.Generator().manual_seed(14)
+    img = torch.randint(0, 256, (3, 3, 84, 84), generator=gen).float()
+    emb = eng.encode(img.cuda(), pre_scale=1 / 255.0, l2norm=True).cpu()
+    assert emb.shape == (3, 768)
+    ref = ov.image_embeddings(sd, img[:2])
+    cos = torch.sum(emb[:2] * ref, dim=-1)
+    assert cos.min().item() >= 0.999, cos
+    alone = eng.encode(img[2:].cuda(), pre_scale=1 / 255.0, l2norm=True).cpu()
+    assert torch.equal(alone[0], emb[2])
 
 
 def test_chunked_batch_and_uint8_input(native):
