@@ -297,7 +297,7 @@ extern "C" int clipppo_vit_destroy(clipppo_vit_t handle) {
 static int plan_chunk(const clipppo_vit_s* h, int N) {
     const char* e = getenv("CLIPPPO_VIT_CHUNK");
     if (e && atoi(e) > 0) return N < atoi(e) ? N : atoi(e);
-    constexpr int kMaxChunkImages = 1400;
+    constexpr int kMaxChunkImages = 4096;       // bigger is faster up to here (profiles/r01_chunk_sweep_v5.txt): 2.5 GB of workspace for ViT-B/32
     if (N <= kMaxChunkImages) return N;
     const int T = h->tokens;
     const int kmin = (N + kMaxChunkImages - 1) / kMaxChunkImages;

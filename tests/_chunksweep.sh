@@ -1,7 +1,7 @@
 mkdir -p gpurun_out
-for c in 241 342 512 683 820 1024 1366; do
+for c in 1024 1366 2048 4096; do
   echo "CHUNK=$c"
-  CLIPPPO_VIT_CHUNK=$c python bench.py --no-cpu-baseline --no-e2e --steps 6 --warmup 2 2>&1 | python -c "
+  CLIPPPO_VIT_CHUNK=$c python bench.py --no-cpu-baseline --no-e2e --steps 8 --warmup 3 2>&1 | python -c "
 import sys, json
 for l in sys.stdin:
     if l.startswith('{'):

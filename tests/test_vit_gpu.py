@@ -254,16 +254,20 @@ def test_vit_l14_embeddings_vs_oracle(native):
     assert torch.equal(alone[0], emb[2])
 
 
-def test_chunked_batch_and_uint8_input(native):
+def test_chunked_batch_and_uint8_input(native, monkeypatch):
+    monkeypatch.setenv("CLIPPPO_VIT_CHUNK", "500")      # force several tower passes: chunk boundaries at 500 / 1000
     eng = _engine(0)
     gen = torch.Generator().manual_seed(4)
-    u8 = torch.randint(0, 256, (1500, 3, 84, 84), generator=gen, dtype=torch.uint8).cuda()    # > 1400 images: cut into chunks
+    u8 = torch.randint(0, 256, (1500, 3, 84, 84), generator=gen, dtype=torch.uint8).cuda()    # three chunks of 500
     a = eng.encode(u8, pre_scale=1 / 255.0, l2norm=True)
     b = eng.encode(u8.float(), pre_scale=1 / 255.0, l2norm=True)
     assert torch.equal(a, b)
-    for lo in (490, 740, 990):                          # whatever chunk size the planner picks, a boundary is crossed
+    for lo in (490, 740, 990):                          # slices that straddle / sit inside the chunk boundaries
         c = eng.encode(u8[lo:lo + 25], pre_scale=1 / 255.0, l2norm=True)
         assert torch.equal(a[lo:lo + 25], c)
+    monkeypatch.delenv("CLIPPPO_VIT_CHUNK")
+    whole = eng.encode(u8, pre_scale=1 / 255.0, l2norm=True)                  # one pass over all 1500 images
+    assert torch.equal(whole, a)
     assert torch.isfinite(a).all()
 
 
