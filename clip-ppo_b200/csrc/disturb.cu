@@ -191,12 +191,9 @@ __device__ __forceinline__ void hfilter4p(const float* __restrict__ rowq, const 
 // WT = compile-time image width (84 / 224: the reference's frame sizes; strides, quad counts and the
 // index divisions become immediates) or 0 for a run-time width.
 //
-// A cluster (the S stripe-CTAs of an image) walks `ipc` consecutive images with two tile buffers:
-//     load(i) -> publish my gray sum, cluster-barrier ARRIVE -> blur + store(i-1) -> barrier WAIT ->
-//     read the S partial sums over DSMEM -> contrast(i) -> pads(i)
-// so the only cluster-wide dependency - the per-image gray mean - is waited for while the previous
-// image is being filtered and stored; the skew between the stripe CTAs' loads (25 % of the runtime
-// when the barrier sits directly between load and contrast) disappears.
+// A cluster (the S stripe-CTAs of an image) walks `ipc` consecutive images.  With ipc > 1 the only
+// cluster-wide dependency - the per-image gray mean - is taken one image ahead by a streaming pre-pass
+// (see the pipeline at the end of the kernel), so nobody waits at the barrier.
 template <int K, int WT>
 __global__ void __launch_bounds__(kFastMaxThreads, 2)
 disturb_fast_kernel(const __grid_constant__ DisturbParams p) {
@@ -239,7 +236,8 @@ disturb_fast_kernel(const __grid_constant__ DisturbParams p) {
     // The stripe of a channel is contiguous in global memory and is walked linearly, one quad per thread
     // and step; quad index -> (row, quad-in-row) is a multiply-high by a reciprocal (an immediate when the
     // width is a template constant); global offsets are 32-bit from one per-image base pointer.
-    auto load_own = [&](int b, float* tile) {
+    auto load_own = [&](int b, float* tile, auto store_c) {
+        constexpr bool STORE = decltype(store_c)::value;     // false: the streaming pre-pass (gray sum only)
         const size_t img_off = static_cast<size_t>(b) * C * H * W;
         const float* __restrict__ xi = static_cast<const float*>(p.x) + img_off;
         const float* __restrict__ ni = do_noise ? p.noise + img_off : xi;
@@ -265,8 +263,10 @@ disturb_fast_kernel(const __grid_constant__ DisturbParams p) {
                 for (int u = 0; u < UNR; ++u) {
                     const float4 v = noisy4(xv[u], nv[u]);
                     csum += (v.x + v.y) + (v.z + v.w);
-                    const int i = i0 + u * nth, row = div_nq(i), quad = i - row * nq;
-                    *reinterpret_cast<float4*>(tc + row * WP + 4 * quad) = v;
+                    if constexpr (STORE) {
+                        const int i = i0 + u * nth, row = div_nq(i), quad = i - row * nq;
+                        *reinterpret_cast<float4*>(tc + row * WP + 4 * quad) = v;
+                    }
                 }
             }
             for (; i0 < n4; i0 += nth) {
@@ -275,8 +275,10 @@ disturb_fast_kernel(const __grid_constant__ DisturbParams p) {
                 if (do_noise) nv = ld_stream_f4(ns + 4 * i0);
                 const float4 v = noisy4(xv, nv);
                 csum += (v.x + v.y) + (v.z + v.w);
-                const int row = div_nq(i0), quad = i0 - row * nq;
-                *reinterpret_cast<float4*>(tc + row * WP + 4 * quad) = v;
+                if constexpr (STORE) {
+                    const int row = div_nq(i0), quad = i0 - row * nq;
+                    *reinterpret_cast<float4*>(tc + row * WP + 4 * quad) = v;
+                }
             }
             const float wc = (C == 3) ? (c_ == 0 ? 0.2989f : (c_ == 1 ? 0.587f : 0.114f)) : 1.0f;
             gsum = fmaf(wc, csum, gsum);
@@ -403,34 +405,67 @@ disturb_fast_kernel(const __grid_constant__ DisturbParams p) {
     };
 
     // ---- the pipeline over this cluster's images ----
-    for (int it = 0; it <= n_img; ++it) {
-        float* tcur = tiles + (it & 1) * tile_floats;
-        float tot = 0.0f;
-        if (it < n_img) {
-            const float g = load_own(b_first + it, tcur);
+    using yes = std::true_type;
+    using no = std::false_type;
+    float* const tile = tiles;
+    if (exchange && p.ipc > 1) {
+        // Early-mean pipeline: the gray sum of image i+1 is taken by a streaming pre-pass (same loads,
+        // same summation order, nothing stored) BEFORE image i is filtered, and published with a barrier
+        // ARRIVE; the matching WAIT comes a whole blur + load later, when every stripe CTA has long
+        // arrived.  The image is read twice, the second time from L2 (it was fetched ~one image-time ago).
+        {
+            const float tot0 = block_sum(load_own(b_first, tile, no{}), red);
+            if (tid == 0) partial[0] = tot0;
+            asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+        }
+        for (int it = 0; it < n_img; ++it) {
+            load_own(b_first + it, tile, yes{});
+            load_halo(b_first + it, tile);
+            asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+            float tot = 0.0f;
+            for (int q = 0; q < S; ++q) tot += *cluster.map_shared_rank(partial + (it & 1), q);
+            __syncthreads();
+            contrast_image(tile, tot);
+            __syncthreads();
+            pad_image(tile);
+            __syncthreads();
+            if (it + 1 < n_img) {
+                const float tn = block_sum(load_own(b_first + it + 1, tile, no{}), red);
+                if (tid == 0) partial[(it + 1) & 1] = tn;
+                asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+            }
+            blur_image(b_first + it, tile);
+            __syncthreads();                         // the tile is overwritten by the next image's load
+        }
+    } else {
+        for (int it = 0; it < n_img; ++it) {
+            const float g = load_own(b_first + it, tile, yes{});
+            float tot = 0.0f;
             if (do_contrast) {
                 tot = block_sum(g, red);
                 if (exchange) {
-                    if (tid == 0) partial[it & 1] = tot;
+                    if (tid == 0) partial[0] = tot;
                     asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
                 }
             }
-            load_halo(b_first + it, tcur);
-        }
-        if (it > 0) blur_image(b_first + it - 1, tiles + ((it - 1) & 1) * tile_floats);
-        if (it < n_img) {
+            load_halo(b_first + it, tile);           // not part of the sum: rides between ARRIVE and WAIT
             if (do_contrast) {
                 if (exchange) {
                     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
                     tot = 0.0f;
-                    for (int q = 0; q < S; ++q) tot += *cluster.map_shared_rank(partial + (it & 1), q);
+                    for (int q = 0; q < S; ++q) tot += *cluster.map_shared_rank(partial, q);
                 }
-                __syncthreads();                 // the tile is complete (block_sum's barriers precede the peers' reads only)
-                contrast_image(tcur, tot);
+                __syncthreads();
+                contrast_image(tile, tot);
             }
             __syncthreads();
-            pad_image(tcur);
+            pad_image(tile);
             __syncthreads();
+            blur_image(b_first + it, tile);
+            if (it + 1 < n_img) {
+                if (exchange) cluster.sync();        // partial[0] is rewritten: every peer must have read it
+                else __syncthreads();
+            }
         }
     }
     if (exchange) cluster.sync();                    // nobody exits while a peer may still read its partial sums
@@ -812,22 +847,19 @@ static int run_disturb(DisturbParams& p, const float* k1d_host, int k, cudaStrea
         const bool contrast = (p.stages & CLIPPPO_STAGE_CONTRAST) != 0;
         // Stripes per image: the smallest cluster whose stripe (+ halo rows) fits the occupancy budget
         // (56 KB = 4 CTAs / SM, then 113 KB = 2, then a whole SM).
-        // CLIPPPO_DISTURB_IPC > 1 switches on the two-tile pipeline (a cluster walks `ipc` images and waits
-        // for the gray mean of image i while it filters image i-1).  Measured on B200 (profiles/): it removes
-        // the barrier stall but needs 2 x the shared memory, i.e. half the resident CTAs, and this kernel
-        // lives on resident warps - 36 % of HBM peak against 57 % without it.  Off by default.
         int S = 0, ipc = 1;
-        if (env_ipc > 1 && contrast) {
-            for (int cand = 2; cand <= max_cluster; cand *= 2)
-                if (2 * tile_bytes(cand) + hdr <= 113 * 1024) { S = cand; break; }
-            if (S) ipc = env_ipc;
-        }
-        if (!S) {
+        {
             const size_t budgets[3] = {static_cast<size_t>(env_budget) * 1024, 113 * 1024, 227 * 1024};
             for (int bi = 0; bi < 3 && !S; ++bi)
                 for (int cand = 1; cand <= max_cluster; cand *= 2)
                     if (tile_bytes(cand) + hdr <= budgets[bi]) { S = cand; break; }
         }
+        // CLIPPPO_DISTURB_IPC > 1 switches on the early-mean pipeline (a cluster walks `ipc` images and
+        // takes the gray sum of image i+1 in a streaming pre-pass before it filters image i, so the mean
+        // barrier never waits).  Measured on B200 (profiles/r01_disturb_experiments.txt): the barrier stall
+        // goes away, but the second (L2) read and the repeated noise arithmetic cost more than it saves on a
+        // kernel that is short of resident warps - 48 % of the HBM peak against 57 %.  Off by default.
+        if (S > 1 && contrast && env_ipc > 1) ipc = env_ipc;
         if (!S) return CLIPPPO_ERR_UNSUPPORTED;
         p.S = S;
         p.R = (p.H + S - 1) / S;
@@ -852,7 +884,7 @@ static int run_disturb(DisturbParams& p, const float* k1d_host, int k, cudaStrea
         p.magic_nq = static_cast<unsigned>((0x100000000ull + nq - 1) / nq);
         p.magic_nsplit = static_cast<unsigned>((0x100000000ull + nsplit - 1) / nsplit);
         p.magic_rs = static_cast<unsigned>((0x100000000ull + (p.R + 2 * P) - 1) / (p.R + 2 * P));
-        const size_t smem = hdr + (ipc > 1 ? 2 : 1) * tile_bytes(S);
+        const size_t smem = hdr + tile_bytes(S);
         int st = CLIPPPO_ERR_UNSUPPORTED;
         switch (K) {
             case 1: st = launch_disturb_fast<1>(p, smem, stream); break;
