@@ -120,8 +120,13 @@ def get_frozen_clip_features(
     x: torch.Tensor,
     clip_model: "clip.model.VisionTransformer | clip.model.CLIP",
 ) -> torch.Tensor:
-    """Frozen-encoder features (reference :185-217): no /255, no L2 normalise, fp32 out."""
-    return _engine_for(clip_model).encode(x, pre_scale=1.0, l2norm=False)
+    """Frozen-encoder features (reference :185-217): no /255, no L2 normalise, fp32 out.
+    This runs inside every policy forward in FROZEN_CLIP mode (E frames per call), where a tower pass is
+    bound by host launch latency: small batches replay a captured CUDA graph (same result, bitwise)."""
+    eng = _engine_for(clip_model)
+    if x.dim() == 4 and 0 < x.shape[0] <= eng.GRAPH_MAX_IMAGES and not torch.cuda.is_current_stream_capturing():
+        return eng.encode_graphed(x, pre_scale=1.0, l2norm=False)
+    return eng.encode(x, pre_scale=1.0, l2norm=False)
 
 
 @dataclass

@@ -254,6 +254,25 @@ def test_vit_l14_embeddings_vs_oracle(native):
     assert torch.equal(alone[0], emb[2])
 
 
+def test_small_batch_graph_replay_is_bitwise_eager(native):
+    """FROZEN_CLIP policy path: E frames per call through a captured CUDA graph (one per call shape)."""
+    eng = _engine(0)
+    gen = torch.Generator().manual_seed(21)
+    for n in (8, 64):
+        outs = []
+        for rep in range(3):
+            x = torch.rand(n, 3, 84, 84, generator=gen).cuda()
+            a = eng.encode(x, pre_scale=1.0, l2norm=False)
+            b = eng.encode_graphed(x, pre_scale=1.0, l2norm=False)           # first call captures, later calls replay
+            assert torch.equal(a, b)
+            outs.append(b)
+        assert not torch.equal(outs[0], outs[1])                             # fresh tensors, not views of the static output
+    big = eng.encode(torch.rand(700, 3, 84, 84, generator=gen).cuda())       # a bigger eager call reallocates the shared workspace
+    x = torch.rand(8, 3, 84, 84, generator=gen).cuda()
+    assert torch.equal(eng.encode(x, pre_scale=1.0, l2norm=False), eng.encode_graphed(x, pre_scale=1.0, l2norm=False))
+    assert len(eng._graphs) == 2 and torch.isfinite(big).all()
+
+
 def test_chunked_batch_and_uint8_input(native, monkeypatch):
     monkeypatch.setenv("CLIPPPO_VIT_CHUNK", "500")      # force several tower passes: chunk boundaries at 500 / 1000
     eng = _engine(0)
