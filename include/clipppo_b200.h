@@ -217,8 +217,9 @@ int clipppo_gemm_bf16_fused(const void* a_bf16, const void* w_bf16, int M, int N
                             const float* bias, const float* row_stats, const float* colsum,
                             void* out_bf16, int64_t ldo, clipppo_stream_t stream);
 /* Measurement probe (profiles/ only, never on the product path): the GEMM above with parts switched
- * off - dbg bit 0: the epilogue drains TMEM but does not compute or store; bit 1: no TMA operand
- * loads.  Output is garbage by construction; only the duration means anything. */
+ * off - dbg 1: the epilogue drains TMEM but does not compute or store; 2: no TMA operand loads;
+ * 3: both; 4: boxes staged but never sent (no output traffic); 8: epilogue arithmetic only.
+ * Output is garbage by construction; only the duration means anything. */
 int clipppo_gemm_bf16_probe(const void* a_bf16, const void* w_bf16, int M, int N, int K, int epilogue,
                             const float* bias, void* out, int64_t ldo, int dbg, clipppo_stream_t stream);
 int clipppo_attention_bf16(const void* qkv_bf16, int n_images, int tokens, int heads, int head_dim,

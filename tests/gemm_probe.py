@@ -57,7 +57,7 @@ for name, Nn, K, epi in SHAPES:
                                                          out.data_ptr(), Nn, d, st))
 
     cols = [("product", timeit(prod))]
-    for d, label in ((1, "no-epilogue"), (2, "no-TMA"), (3, "MMA-only")):
+    for d, label in ((1, "no-epilogue"), (2, "no-TMA"), (3, "MMA-only")) + (((4, "no-output"), (8, "math-only")) if epi >= 6 else ()):
         cols.append((label, timeit(probe(d))))
     cols.append(("cuBLAS", timeit(lambda: torch.matmul(a, w.t()))))
     print(f"{name:11s} N={Nn:4d} K={K:4d}  " + "  ".join(f"{lb} {us:7.1f} | {fl / us / 1e6:6.0f}" for lb, us in cols), flush=True)
