@@ -81,13 +81,6 @@ __device__ __forceinline__ float block_sum(float v, float* scratch) {
     return warp_sum(t);
 }
 
-// cp.async (LDGSTS): 16-byte global -> shared copies that bypass the register file
-__device__ __forceinline__ void cpa16(uint32_t dst_smem, const void* src) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cpa_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cpa_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
-
 // Programmatic dependent launch (PDL).  Every kernel of the tower calls pdl_launch_dependents() first
 // (the next kernel of the stream may begin its prologue - barrier init, TMEM alloc, descriptor
 // prefetch - as soon as all CTAs of this one are running) and pdl_wait() before its first access to

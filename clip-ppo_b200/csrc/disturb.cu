@@ -42,14 +42,11 @@ struct DisturbParams {
     int sh, sw, ph, pw;
     int S, R;       // stripes per image (= cluster size), rows per stripe
     int nsplit;     // row splits of a stripe in the blur phase (balances the 4-column tasks over the CTA)
-    int p1_mode;    // phase-1 variant: 0 = register-staged loads, 1 = cp.async for x (tuning knob)
     int fast;       // x / noise contiguous NCHW fp32, W % 4 == 0, 16-byte aligned
     int io_mode;    // 0: fp32 strided in, fp32 NCHW out.  1: u8 NHWC in / u8 NHWC out.
                     // 2: fp32 (0..255) NHWC in / u8 NHWC out.
     int nthreads;   // fast path: CTA size (covers the blur tasks in one round when it can)
     int log2S;      // fast path: S is a power of two
-    int ipc;        // fast path: images per cluster (> 1 => two tile buffers, the mean barrier hides behind the previous blur)
-    int fake_mean;  // EXPERIMENT ONLY (CLIPPPO_DISTURB_FAKE): skip the cluster-wide mean exchange (wrong results)
     unsigned magic_nq, magic_nsplit, magic_rs;   // fast path: ceil(2^32 / d), so that __umulhi(n, magic) == n / d for n < 2^16
     __device__ __forceinline__ float* out_f32() const { return static_cast<float*>(out); }
 };
@@ -151,8 +148,6 @@ __device__ __forceinline__ void blur_task(const float* __restrict__ base, float*
 //   * thread -> (row, quad) positions advance incrementally (no division in any loop);
 //   * the cutout is a warp-uniform row test plus a per-thread column mask.
 // =============================================================================================
-static int env_int(const char* name, int dflt);
-
 constexpr int kPad = 4;
 constexpr int kFastMaxThreads = 384;     // x 2 CTAs / SM => at most 85 registers per thread
 
@@ -191,33 +186,31 @@ __device__ __forceinline__ void hfilter4p(const float* __restrict__ rowq, const 
 // WT = compile-time image width (84 / 224: the reference's frame sizes; strides, quad counts and the
 // index divisions become immediates) or 0 for a run-time width.
 //
-// A cluster (the S stripe-CTAs of an image) walks `ipc` consecutive images.  With ipc > 1 the only
-// cluster-wide dependency - the per-image gray mean - is taken one image ahead by a streaming pre-pass
-// (see the pipeline at the end of the kernel), so nobody waits at the barrier.
+// One image = one cluster of S stripe-CTAs (S = 1: a plain CTA).  The only cluster-wide dependency is
+// the per-image gray mean of the contrast stage: one barrier, with the halo-row loads between its
+// ARRIVE and its WAIT.
 template <int K, int WT>
 __global__ void __launch_bounds__(kFastMaxThreads, 2)
 disturb_fast_kernel(const __grid_constant__ DisturbParams p) {
     constexpr int P = K / 2;
     extern __shared__ __align__(16) float smem[];
     float* red = smem;
-    float* partial = smem + 32;               // [2]: one slot per in-flight image
-    float* tiles = smem + kSmemHeaderFloats;
+    float* partial = smem + 32;
+    float* tile = smem + kSmemHeaderFloats;
 
     cg::cluster_group cluster = cg::this_cluster();
     const int S = p.S, R = p.R, C = p.C, H = p.H, W = WT ? WT : p.W;
-    const int grp = blockIdx.x >> p.log2S, s = blockIdx.x & (S - 1);
-    const int b_first = grp * p.ipc, n_img = min(p.ipc, p.B - b_first);
+    const int b = blockIdx.x >> p.log2S, s = blockIdx.x & (S - 1);
     const int r0 = min(s * R, H), r1 = min(r0 + R, H), rows = r1 - r0;
     const int WP = W + 2 * kPad;              // smem row pitch (floats)
     const int RS = R + 2 * P;                 // smem rows per channel: P halo rows above, R own rows, P below
     const int plane = RS * WP;                // smem floats per channel
-    const int tile_floats = C * plane;
     const int nq = W >> 2;
     auto div_nq = [&](int i) { return WT ? i / (WT >> 2 ? WT >> 2 : 1) : static_cast<int>(__umulhi(i, p.magic_nq)); };
     const int tid = threadIdx.x, nth = blockDim.x;
     const bool do_noise = (p.stages & CLIPPPO_STAGE_NOISE) != 0;
     const bool do_contrast = (p.stages & CLIPPPO_STAGE_CONTRAST) != 0;
-    const bool exchange = do_contrast && S > 1 && !p.fake_mean;     // the gray mean spans several CTAs
+    const bool exchange = do_contrast && S > 1;                     // the gray mean spans several CTAs
     const float sigma = p.sigma_n;
     const int n4 = rows * nq;
     const int HW = H * W;
@@ -236,8 +229,7 @@ disturb_fast_kernel(const __grid_constant__ DisturbParams p) {
     // The stripe of a channel is contiguous in global memory and is walked linearly, one quad per thread
     // and step; quad index -> (row, quad-in-row) is a multiply-high by a reciprocal (an immediate when the
     // width is a template constant); global offsets are 32-bit from one per-image base pointer.
-    auto load_own = [&](int b, float* tile, auto store_c) {
-        constexpr bool STORE = decltype(store_c)::value;     // false: the streaming pre-pass (gray sum only)
+    auto load_own = [&]() {
         const size_t img_off = static_cast<size_t>(b) * C * H * W;
         const float* __restrict__ xi = static_cast<const float*>(p.x) + img_off;
         const float* __restrict__ ni = do_noise ? p.noise + img_off : xi;
@@ -263,10 +255,8 @@ disturb_fast_kernel(const __grid_constant__ DisturbParams p) {
                 for (int u = 0; u < UNR; ++u) {
                     const float4 v = noisy4(xv[u], nv[u]);
                     csum += (v.x + v.y) + (v.z + v.w);
-                    if constexpr (STORE) {
-                        const int i = i0 + u * nth, row = div_nq(i), quad = i - row * nq;
-                        *reinterpret_cast<float4*>(tc + row * WP + 4 * quad) = v;
-                    }
+                    const int i = i0 + u * nth, row = div_nq(i), quad = i - row * nq;
+                    *reinterpret_cast<float4*>(tc + row * WP + 4 * quad) = v;
                 }
             }
             for (; i0 < n4; i0 += nth) {
@@ -275,10 +265,8 @@ disturb_fast_kernel(const __grid_constant__ DisturbParams p) {
                 if (do_noise) nv = ld_stream_f4(ns + 4 * i0);
                 const float4 v = noisy4(xv, nv);
                 csum += (v.x + v.y) + (v.z + v.w);
-                if constexpr (STORE) {
-                    const int row = div_nq(i0), quad = i0 - row * nq;
-                    *reinterpret_cast<float4*>(tc + row * WP + 4 * quad) = v;
-                }
+                const int row = div_nq(i0), quad = i0 - row * nq;
+                *reinterpret_cast<float4*>(tc + row * WP + 4 * quad) = v;
             }
             const float wc = (C == 3) ? (c_ == 0 ? 0.2989f : (c_ == 1 ? 0.587f : 0.114f)) : 1.0f;
             gsum = fmaf(wc, csum, gsum);
@@ -289,7 +277,7 @@ disturb_fast_kernel(const __grid_constant__ DisturbParams p) {
     // fetched and perturbed again by this CTA instead of being copied from the neighbour's shared
     // memory - 2P/R more (mostly L2-resident) reads, but no cluster barrier before the blur.  They are
     // not part of the gray sum, so they load between the ARRIVE and the WAIT of the mean barrier.
-    auto load_halo = [&](int b, float* tile) {
+    auto load_halo = [&]() {
         const size_t img_off = static_cast<size_t>(b) * C * H * W;
         const float* __restrict__ xi = static_cast<const float*>(p.x) + img_off;
         const float* __restrict__ ni = do_noise ? p.noise + img_off : xi;
@@ -312,7 +300,7 @@ disturb_fast_kernel(const __grid_constant__ DisturbParams p) {
     };
 
     // ---- contrast blend in place over own + halo rows: [tv] _blend: c*x + (1-c)*mean, clamp ----
-    auto contrast_image = [&](float* tile, float tot) {
+    auto contrast_image = [&](float tot) {
         const float m = tot / static_cast<float>(H * W);
         const float cm = __fmul_rn(p.omc, m);
         const float cf = p.c;
@@ -333,7 +321,7 @@ disturb_fast_kernel(const __grid_constant__ DisturbParams p) {
     };
 
     // ---- reflected pad columns of every smem row (own + halo) ----
-    auto pad_image = [&](float* tile) {
+    auto pad_image = [&]() {
         if constexpr (K > 1) {
             for (int i = tid; i < C * RS * 2; i += nth) {
                 const int side = i & 1, cr = i >> 1;
@@ -354,7 +342,7 @@ disturb_fast_kernel(const __grid_constant__ DisturbParams p) {
     const int ntasks = C * nsplit * nq;
     const bool do_cut = (p.stages & CLIPPPO_STAGE_CUTOUT) != 0;
     const int sw_end = p.sw + p.pw;
-    auto blur_image = [&](int b, const float* tile) {
+    auto blur_image = [&]() {
         for (int task = tid; task < ntasks; task += nth) {
             const int rest = div_nq(task), q = task - rest * nq;
             const int c_ = nsplit == 1 ? rest : __umulhi(rest, p.magic_nsplit), sp = rest - c_ * nsplit;
@@ -404,71 +392,33 @@ disturb_fast_kernel(const __grid_constant__ DisturbParams p) {
         }
     };
 
-    // ---- the pipeline over this cluster's images ----
-    using yes = std::true_type;
-    using no = std::false_type;
-    float* const tile = tiles;
-    if (exchange && p.ipc > 1) {
-        // Early-mean pipeline: the gray sum of image i+1 is taken by a streaming pre-pass (same loads,
-        // same summation order, nothing stored) BEFORE image i is filtered, and published with a barrier
-        // ARRIVE; the matching WAIT comes a whole blur + load later, when every stripe CTA has long
-        // arrived.  The image is read twice, the second time from L2 (it was fetched ~one image-time ago).
-        {
-            const float tot0 = block_sum(load_own(b_first, tile, no{}), red);
-            if (tid == 0) partial[0] = tot0;
+    // ---- the image ----
+    const float g = load_own();
+    float tot = 0.0f;
+    if (do_contrast) {
+        tot = block_sum(g, red);
+        if (exchange) {
+            if (tid == 0) *partial = tot;
             asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
         }
-        for (int it = 0; it < n_img; ++it) {
-            load_own(b_first + it, tile, yes{});
-            load_halo(b_first + it, tile);
-            asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-            float tot = 0.0f;
-            for (int q = 0; q < S; ++q) tot += *cluster.map_shared_rank(partial + (it & 1), q);
-            __syncthreads();
-            contrast_image(tile, tot);
-            __syncthreads();
-            pad_image(tile);
-            __syncthreads();
-            if (it + 1 < n_img) {
-                const float tn = block_sum(load_own(b_first + it + 1, tile, no{}), red);
-                if (tid == 0) partial[(it + 1) & 1] = tn;
-                asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-            }
-            blur_image(b_first + it, tile);
-            __syncthreads();                         // the tile is overwritten by the next image's load
-        }
-    } else {
-        for (int it = 0; it < n_img; ++it) {
-            const float g = load_own(b_first + it, tile, yes{});
-            float tot = 0.0f;
-            if (do_contrast) {
-                tot = block_sum(g, red);
-                if (exchange) {
-                    if (tid == 0) partial[0] = tot;
-                    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-                }
-            }
-            load_halo(b_first + it, tile);           // not part of the sum: rides between ARRIVE and WAIT
-            if (do_contrast) {
-                if (exchange) {
-                    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-                    tot = 0.0f;
-                    for (int q = 0; q < S; ++q) tot += *cluster.map_shared_rank(partial, q);
-                }
-                __syncthreads();
-                contrast_image(tile, tot);
-            }
-            __syncthreads();
-            pad_image(tile);
-            __syncthreads();
-            blur_image(b_first + it, tile);
-            if (it + 1 < n_img) {
-                if (exchange) cluster.sync();        // partial[0] is rewritten: every peer must have read it
-                else __syncthreads();
-            }
-        }
     }
-    if (exchange) cluster.sync();                    // nobody exits while a peer may still read its partial sums
+    load_halo();                                     // not part of the sum: rides between ARRIVE and WAIT
+    if (do_contrast) {
+        if (exchange) {
+            asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+            tot = 0.0f;
+            for (int q = 0; q < S; ++q) tot += *cluster.map_shared_rank(partial, q);
+            asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");     // my reads of the peers' sums are done
+        }
+        __syncthreads();
+        contrast_image(tot);
+    }
+    __syncthreads();
+    pad_image();
+    __syncthreads();
+    blur_image();
+    // nobody exits while a peer may still read its partial sum: the second barrier phase, waited for here
+    if (exchange) asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
 template <int K>
@@ -495,7 +445,7 @@ disturb_kernel(const __grid_constant__ DisturbParams p) {
 
     // ---- phase 1: stripe -> smem -----------------------------------------------------------
     float gsum = 0.0f;
-    if (p.fast && p.p1_mode == 0) {
+    if (p.fast) {
         const int n4 = (rows * W) >> 2;       // float4 per channel of this stripe (contiguous in global)
         constexpr int UNR = 4;
         for (int c_ = 0; c_ < C; ++c_) {
@@ -533,57 +483,6 @@ disturb_kernel(const __grid_constant__ DisturbParams p) {
             }
             gsum = fmaf(wc, csum, gsum);
         }
-    } else if (p.fast) {
-        // The whole stripe is requested up front: x goes straight into the tile with cp.async (no
-        // registers), the matching noise values wait in registers, NB float4 per thread at a time.
-        // One memory round trip per batch instead of one per (channel, unroll group).
-        const int n4 = (rows * W) >> 2;       // float4 per channel of this stripe (contiguous in global)
-        const int total4 = C * n4;
-        const size_t chan = static_cast<size_t>(H) * W;
-        const float* xb = static_cast<const float*>(p.x) + static_cast<size_t>(b) * C * chan + static_cast<size_t>(r0) * W;
-        const float* nb = do_noise ? p.noise + static_cast<size_t>(b) * C * chan + static_cast<size_t>(r0) * W : nullptr;
-        const uint32_t tile_s = ptx_smem(tile + P * W);
-        {
-            int c_ = 0, i = tid;
-            for (int idx = tid; idx < total4; idx += nth) {
-                while (i >= n4) { i -= n4; ++c_; }
-                cpa16(tile_s + (c_ * plane + 4 * i) * 4, xb + c_ * chan + 4 * i);
-                i += nth;
-            }
-            cpa_commit();
-        }
-        constexpr int NB = 8;
-        int c_ = 0, i = tid;
-        bool x_ready = false;
-        for (int idx0 = tid; idx0 < total4; idx0 += nth * NB) {
-            float4 nv[NB];
-            int cc[NB], ii[NB];
-#pragma unroll
-            for (int u = 0; u < NB; ++u) {
-                while (i >= n4 && c_ < C) { i -= n4; ++c_; }
-                cc[u] = c_; ii[u] = i;
-                if (idx0 + u * nth < total4 && do_noise) nv[u] = ld_stream_f4(nb + c_ * chan + 4 * i);
-                i += nth;
-            }
-            if (!x_ready) { cpa_wait_all(); x_ready = true; }    // my own copies have landed in the tile
-#pragma unroll
-            for (int u = 0; u < NB; ++u) {
-                if (idx0 + u * nth < total4) {
-                    float4* q = reinterpret_cast<float4*>(tile + cc[u] * plane + P * W) + ii[u];
-                    float4 v = *q;
-                    if (do_noise) {
-                        v.x = noisy(v.x, nv[u].x, sigma);
-                        v.y = noisy(v.y, nv[u].y, sigma);
-                        v.z = noisy(v.z, nv[u].z, sigma);
-                        v.w = noisy(v.w, nv[u].w, sigma);
-                        *q = v;
-                    }
-                    const float wc = (C == 3) ? (cc[u] == 0 ? 0.2989f : (cc[u] == 1 ? 0.587f : 0.114f)) : 1.0f;
-                    gsum = fmaf(wc, (v.x + v.y) + (v.z + v.w), gsum);
-                }
-            }
-        }
-        cpa_wait_all();
     } else {
         const int n = rows * W;
         const int total = C * n;
@@ -783,7 +682,7 @@ static int launch_disturb_fast_w(const DisturbParams& p, size_t smem, cudaStream
         configured = true;
     }
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(static_cast<unsigned>((p.B + p.ipc - 1) / p.ipc) * p.S);
+    cfg.gridDim = dim3(static_cast<unsigned>(p.B) * p.S);
     cfg.blockDim = dim3(p.nthreads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
@@ -794,8 +693,7 @@ static int launch_disturb_fast_w(const DisturbParams& p, size_t smem, cudaStream
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     // without the contrast stage the stripes of an image are independent: plain CTAs, no gang scheduling
-    static const int env_fake = env_int("CLIPPPO_DISTURB_FAKE", 0), env_forcecl = env_int("CLIPPPO_DISTURB_FORCECL", 0);
-    cfg.numAttrs = ((((p.stages & CLIPPPO_STAGE_CONTRAST) && p.S > 1) || env_forcecl) && !env_fake) ? 1 : 0;
+    cfg.numAttrs = ((p.stages & CLIPPPO_STAGE_CONTRAST) && p.S > 1) ? 1 : 0;
     CLIPPPO_CUDA_TRY(cudaLaunchKernelEx(&cfg, disturb_fast_kernel<K, WT>, p));
     prof_count_launch();
     return CLIPPPO_OK;
@@ -814,10 +712,9 @@ static int env_int(const char* name, int dflt) {
 }
 
 static int run_disturb(DisturbParams& p, const float* k1d_host, int k, cudaStream_t stream, int max_cluster = 0) {
-    static const int env_cl = env_int("CLIPPPO_DISTURB_MAXCL", 16), env_p1 = env_int("CLIPPPO_DISTURB_P1", 0);
+    static const int env_cl = env_int("CLIPPPO_DISTURB_MAXCL", 16);
     static const int env_budget = env_int("CLIPPPO_DISTURB_SMEM_KB", 56);
     if (max_cluster == 0) max_cluster = env_cl;
-    p.p1_mode = env_p1;
     if (p.B <= 0 || p.C <= 0 || p.H <= 0 || p.W <= 0) return CLIPPPO_ERR_BAD_SHAPE;
     if (!p.x || !p.out) return CLIPPPO_ERR_NULL;
     if ((p.stages & CLIPPPO_STAGE_NOISE) && !p.noise) return CLIPPPO_ERR_NULL;
@@ -838,32 +735,24 @@ static int run_disturb(DisturbParams& p, const float* k1d_host, int k, cudaStrea
     const int P = K / 2;
     if (p.fast && p.io_mode == 0 && K <= 7 && p.W >= 8) {
         // ---- fast path (disturb_fast_kernel): padded smem rows ----
-        static const int env_nsplit = env_int("CLIPPPO_DISTURB_NSPLIT", 0), env_ipc = env_int("CLIPPPO_DISTURB_IPC", 0);
+        static const int env_nsplit = env_int("CLIPPPO_DISTURB_NSPLIT", 0);
         auto tile_bytes = [&](int S) {
             const int R = (p.H + S - 1) / S;
             return (size_t)p.C * (R + 2 * P) * (p.W + 2 * kPad) * sizeof(float);
         };
         const size_t hdr = kSmemHeaderFloats * sizeof(float);
-        const bool contrast = (p.stages & CLIPPPO_STAGE_CONTRAST) != 0;
         // Stripes per image: the smallest cluster whose stripe (+ halo rows) fits the occupancy budget
         // (56 KB = 4 CTAs / SM, then 113 KB = 2, then a whole SM).
-        int S = 0, ipc = 1;
+        int S = 0;
         {
             const size_t budgets[3] = {static_cast<size_t>(env_budget) * 1024, 113 * 1024, 227 * 1024};
             for (int bi = 0; bi < 3 && !S; ++bi)
                 for (int cand = 1; cand <= max_cluster; cand *= 2)
                     if (tile_bytes(cand) + hdr <= budgets[bi]) { S = cand; break; }
         }
-        // CLIPPPO_DISTURB_IPC > 1 switches on the early-mean pipeline (a cluster walks `ipc` images and
-        // takes the gray sum of image i+1 in a streaming pre-pass before it filters image i, so the mean
-        // barrier never waits).  Measured on B200 (profiles/r01_disturb_experiments.txt): the barrier stall
-        // goes away, but the second (L2) read and the repeated noise arithmetic cost more than it saves on a
-        // kernel that is short of resident warps - 48 % of the HBM peak against 57 %.  Off by default.
-        if (S > 1 && contrast && env_ipc > 1) ipc = env_ipc;
         if (!S) return CLIPPPO_ERR_UNSUPPORTED;
         p.S = S;
         p.R = (p.H + S - 1) / S;
-        p.ipc = ipc;
         // Blur tasks = C x nsplit x (W/4) column quads, one per thread.  A split costs 2P extra
         // horizontally filtered rows per task; it buys warps (latency hiding) when a stripe has few quads.
         const int nq = p.W / 4;
@@ -880,7 +769,6 @@ static int run_disturb(DisturbParams& p, const float* k1d_host, int k, cudaStrea
         p.nthreads = nthreads;
         p.log2S = 0;
         while ((1 << p.log2S) < S) ++p.log2S;
-        p.fake_mean = env_int("CLIPPPO_DISTURB_FAKE", 0);
         p.magic_nq = static_cast<unsigned>((0x100000000ull + nq - 1) / nq);
         p.magic_nsplit = static_cast<unsigned>((0x100000000ull + nsplit - 1) / nsplit);
         p.magic_rs = static_cast<unsigned>((0x100000000ull + (p.R + 2 * P) - 1) / (p.R + 2 * P));
