@@ -231,45 +231,39 @@ disturb_fast_kernel(const __grid_constant__ DisturbParams p) {
     // width is a template constant); global offsets are 32-bit from one per-image base pointer.
     auto load_own = [&]() {
         const size_t img_off = static_cast<size_t>(b) * C * H * W;
-        const float* __restrict__ xi = static_cast<const float*>(p.x) + img_off;
-        const float* __restrict__ ni = do_noise ? p.noise + img_off : xi;
+        const float* xs = static_cast<const float*>(p.x) + img_off + r0 * W;
+        const float* ns = do_noise ? p.noise + img_off + r0 * W : xs;
+        asm volatile("" : "+l"(xs), "+l"(ns));           // keep the two bases in registers (no rematerialisation)
         float* const tile0 = tile + P * WP + kPad;      // first own row, first real column
+        // All channels form one index space of C * n4 quads, UNR of them per thread and trip: the whole
+        // stripe is fetched in ceil(quads per thread / UNR) memory round trips, with no serial tail.
+        constexpr int UNR = 6;                          // 12 independent 128-bit loads in flight per thread (4 and 8 measured slower)
+        const int total = C * n4;
         float gsum = 0.0f;
-        constexpr int UNR = 4;                          // 8 independent 128-bit loads in flight per thread
-        for (int c_ = 0; c_ < C; ++c_) {
-            const float* xs = xi + c_ * HW + r0 * W;
-            const float* ns = ni + c_ * HW + r0 * W;
-            int tco = c_ * plane;
-            asm volatile("" : "+l"(xs), "+l"(ns), "+r"(tco));    // keep the bases in registers (no rematerialisation)
-            float* tc = tile0 + tco;
-            float csum = 0.0f;
-            int i0 = tid;
-            for (; i0 + (UNR - 1) * nth < n4; i0 += nth * UNR) {   // full trips: no bounds tests
-                float4 xv[UNR], nv[UNR];
+        for (int i0 = tid; i0 < total; i0 += nth * UNR) {
+            float4 xv[UNR], nv[UNR];
+            int cc[UNR], jj[UNR];
 #pragma unroll
-                for (int u = 0; u < UNR; ++u) {
-                    xv[u] = ld_stream_f4(xs + 4 * (i0 + u * nth));
-                    if (do_noise) nv[u] = ld_stream_f4(ns + 4 * (i0 + u * nth));
+            for (int u = 0; u < UNR; ++u) {
+                const int i = i0 + u * nth;
+                cc[u] = (i >= n4) + (i >= 2 * n4);      // C <= 3
+                jj[u] = i - cc[u] * n4;
+                if (i < total) {
+                    const int off = cc[u] * HW + 4 * jj[u];
+                    xv[u] = ld_stream_f4(xs + off);
+                    if (do_noise) nv[u] = ld_stream_f4(ns + off);
                 }
+            }
 #pragma unroll
-                for (int u = 0; u < UNR; ++u) {
+            for (int u = 0; u < UNR; ++u) {
+                if (i0 + u * nth < total) {
                     const float4 v = noisy4(xv[u], nv[u]);
-                    csum += (v.x + v.y) + (v.z + v.w);
-                    const int i = i0 + u * nth, row = div_nq(i), quad = i - row * nq;
-                    *reinterpret_cast<float4*>(tc + row * WP + 4 * quad) = v;
+                    const float wc = (C == 3) ? (cc[u] == 0 ? 0.2989f : (cc[u] == 1 ? 0.587f : 0.114f)) : 1.0f;
+                    gsum = fmaf(wc, (v.x + v.y) + (v.z + v.w), gsum);
+                    const int row = div_nq(jj[u]), quad = jj[u] - row * nq;
+                    *reinterpret_cast<float4*>(tile0 + cc[u] * plane + row * WP + 4 * quad) = v;
                 }
             }
-            for (; i0 < n4; i0 += nth) {
-                const float4 xv = ld_stream_f4(xs + 4 * i0);
-                float4 nv = xv;
-                if (do_noise) nv = ld_stream_f4(ns + 4 * i0);
-                const float4 v = noisy4(xv, nv);
-                csum += (v.x + v.y) + (v.z + v.w);
-                const int row = div_nq(i0), quad = i0 - row * nq;
-                *reinterpret_cast<float4*>(tc + row * WP + 4 * quad) = v;
-            }
-            const float wc = (C == 3) ? (c_ == 0 ? 0.2989f : (c_ == 1 ? 0.587f : 0.114f)) : 1.0f;
-            gsum = fmaf(wc, csum, gsum);
         }
         return gsum;
     };
@@ -713,7 +707,7 @@ static int env_int(const char* name, int dflt) {
 
 static int run_disturb(DisturbParams& p, const float* k1d_host, int k, cudaStream_t stream, int max_cluster = 0) {
     static const int env_cl = env_int("CLIPPPO_DISTURB_MAXCL", 16);
-    static const int env_budget = env_int("CLIPPPO_DISTURB_SMEM_KB", 56);
+    static const int env_budget = env_int("CLIPPPO_DISTURB_SMEM_KB", 113);
     if (max_cluster == 0) max_cluster = env_cl;
     if (p.B <= 0 || p.C <= 0 || p.H <= 0 || p.W <= 0) return CLIPPPO_ERR_BAD_SHAPE;
     if (!p.x || !p.out) return CLIPPPO_ERR_NULL;
@@ -741,8 +735,10 @@ static int run_disturb(DisturbParams& p, const float* k1d_host, int k, cudaStrea
             return (size_t)p.C * (R + 2 * P) * (p.W + 2 * kPad) * sizeof(float);
         };
         const size_t hdr = kSmemHeaderFloats * sizeof(float);
-        // Stripes per image: the smallest cluster whose stripe (+ halo rows) fits the occupancy budget
-        // (56 KB = 4 CTAs / SM, then 113 KB = 2, then a whole SM).
+        // Stripes per image: the smallest cluster whose stripe (+ halo rows) fits half an SM (113 KB: two
+        // CTAs of up to 384 threads per SM), else a whole SM.  Measured (profiles/r01_disturb_experiments.txt):
+        // 2 x 352 threads beat 4 x 192 at 224x224x3 (63 % vs 58 % of the HBM peak), and an 84x84x3 frame
+        // that fits one CTA (no cluster, no barrier) reaches 74 % instead of 65 % as a 2-CTA cluster.
         int S = 0;
         {
             const size_t budgets[3] = {static_cast<size_t>(env_budget) * 1024, 113 * 1024, 227 * 1024};
@@ -759,7 +755,8 @@ static int run_disturb(DisturbParams& p, const float* k1d_host, int k, cudaStrea
         int nsplit = env_nsplit;
         if (nsplit <= 0) {
             nsplit = 1;
-            while (p.C * nq * nsplit < 160 && nsplit < p.R) ++nsplit;
+            while (p.C * nq * nsplit < 160 && nsplit < p.R) ++nsplit;                     // at least ~5 warps of tasks
+            while (p.C * nq * nsplit < 320 && p.R / (nsplit + 1) >= 12) ++nsplit;         // ~10 warps while a split keeps >= 12 rows
         }
         if (nsplit > p.R) nsplit = p.R;
         p.nsplit = nsplit;
