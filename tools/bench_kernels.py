@@ -1,5 +1,5 @@
 """Not a test: CUDA-event micro-benchmarks of the memory-bound kernels (disturb, preprocess, LN,
-attention) against the measured HBM peak.  python tests/bench_kernels.py [disturb|pre|ln|attn ...]"""
+attention) against the measured HBM peak.  python tools/bench_kernels.py [disturb|pre|ln|attn ...]"""
 import json
 import os
 import sys

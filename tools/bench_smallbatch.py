@@ -1,6 +1,6 @@
 """Not a test: latency of the FROZEN_CLIP policy path (get_frozen_clip_features inside every policy
 forward: E frames per call, reference clip_ppo_minigrid.py:249-254 / clip_ppo_atari.py:213-228) at small
-batches, eager launches vs one CUDA-graph replay.  python tests/bench_smallbatch.py"""
+batches, eager launches vs one CUDA-graph replay.  python tools/bench_smallbatch.py"""
 import os
 import sys
 import time

@@ -1,4 +1,4 @@
-"""Not a test: a diagnostic run for the GPU box.  python tests/gpu_probe.py"""
+"""Not a test: a diagnostic run for the GPU box.  python tools/gpu_probe.py"""
 import os
 import sys
 import time
