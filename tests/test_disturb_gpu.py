@@ -103,6 +103,60 @@ def test_random_shapes_against_oracle(native, shape, sev):
     assert (out.cpu() - ref).abs().max() <= TOL
 
 
+# Shapes that steer the dispatcher through every variant of the fast kernel (one CTA per frame / 8-CTA
+# clusters, template widths 84 and 224 / run-time widths, short last stripe, a single frame) and into the
+# general kernel (odd width, width not a multiple of 4, strided input).
+@pytest.mark.parametrize("shape,sev", [((3, 3, 224, 224), "MODERATE"), ((3, 3, 224, 224), "HARD"), ((4, 1, 224, 224), "MODERATE"),
+                                       ((1, 3, 224, 224), "SEVERE"), ((3, 3, 250, 224), "MODERATE"), ((2, 3, 300, 200), "HARD"),
+                                       ((6, 3, 96, 128), "MILD"), ((2, 3, 64, 512), "SEVERE"), ((2, 1, 90, 88), "HARD"),
+                                       ((3, 3, 84, 86), "MODERATE"), ((2, 3, 61, 61), "SEVERE"), ((1, 1, 8, 8), "MILD")])
+def test_dispatch_variants_against_oracle(native, shape, sev):
+    g = torch.Generator().manual_seed(sum(shape) * 7 + len(sev))
+    x = torch.rand(shape, generator=g)
+    noise = torch.randn(shape, generator=g)
+    cfg = od.SEVERITY_TABLE[sev]
+    H, W = shape[-2:]
+    ph, pw = od.cutout_patch(H, W, cfg["cutout"])
+    sh, sw = max(0, (H - ph) // 2), max(0, (W - pw) // 3 - 1)           # a patch taller than the frame is clipped, as in the reference
+    c = cfg["contrast"][1] - 0.02                          # > 1: the clamp of the blend is active for dark pixels
+    w = _wrapper(sev)
+    k = od.blur_kernel_size(cfg["blur_sigma"])
+    k1d = od.gaussian_kernel1d(k, float(torch.tensor(cfg["blur_sigma"], dtype=torch.float32)))
+    out = w.apply_disturbances(x.cuda(), noise=noise.cuda(), contrast_factor=c, cutout_start=(sh, sw))
+    ref = od.disturb(x, noise, cfg["noise_sigma"], c, k1d, sh, sw, ph, pw)
+    assert (out.cpu() - ref).abs().max() <= TOL
+    assert out[:, :, sh:sh + ph, sw:sw + pw].abs().max().item() == 0.0
+    # each stage on its own (stage mask): without the contrast stage a multi-stripe image runs as plain CTAs
+    xg = x.cuda()
+    assert torch.equal(w.apply_gaussian_noise(xg, noise=noise.cuda()).cpu(), od.add_noise(x, noise, cfg["noise_sigma"]))
+    assert (w.apply_contrast_jitter(xg, contrast_factor=c).cpu() - od.contrast(x, c)).abs().max() <= TOL
+    assert (w.apply_gaussian_blur(xg).cpu() - od.blur(x, k1d)).abs().max() <= TOL
+    assert torch.equal(w.apply_cutout(xg, cutout_start=(sh, sw)).cpu(), od.cutout(x, sh, sw, ph, pw))
+    # a strided view of the same data (general kernel) gives the same chain
+    xs = torch.empty(shape[0], H, W, shape[1]).cuda()
+    xs.copy_(x.permute(0, 2, 3, 1))
+    out_v = w.apply_disturbances(xs.permute(0, 3, 1, 2), noise=noise.cuda(), contrast_factor=c, cutout_start=(sh, sw))
+    assert (out_v.cpu() - ref).abs().max() <= TOL
+
+
+def test_wide_blur_kernels_use_the_general_kernel(native):
+    """Custom sigma: k = 9 .. 15 taps are outside the fast path's register ring."""
+    from shared.disturbances_gpu import DisturbanceWrapperGPU
+    g = torch.Generator().manual_seed(99)
+    x = torch.rand(3, 3, 84, 84, generator=g)
+    noise = torch.randn(3, 3, 84, 84, generator=g)
+    for sigma_b in (4.0, 5.5, 7.0):
+        w = DisturbanceWrapperGPU(device="cuda", severity=None, gaussian_noise_sigma=0.1, gaussian_blur_sigma=sigma_b,
+                                  contrast_range=(0.8, 1.2), cutout_ratio=0.2)
+        k = od.blur_kernel_size(sigma_b)
+        assert k >= 9
+        k1d = od.gaussian_kernel1d(k, float(torch.tensor(sigma_b, dtype=torch.float32)))
+        ph, pw = od.cutout_patch(84, 84, 0.2)
+        out = w.apply_disturbances(x.cuda(), noise=noise.cuda(), contrast_factor=0.9, cutout_start=(5, 7))
+        ref = od.disturb(x, noise, 0.1, 0.9, k1d, 5, 7, ph, pw)
+        assert (out.cpu() - ref).abs().max() <= TOL
+
+
 def test_full_size_batch_properties(native):
     """BASELINE config sizes (4096 x 3 x 224 x 224 is 2.4 GB): size-independent properties plus an
     oracle comparison on a slice of the batch."""
