@@ -174,11 +174,27 @@ __device__ __forceinline__ void hfilter4p(const float* __restrict__ rowq, const 
     const float4 m = *reinterpret_cast<const float4*>(rowq);
     const float4 z = *reinterpret_cast<const float4*>(rowq + 4);
     const float v[12] = {a.x, a.y, a.z, a.w, m.x, m.y, m.z, m.w, z.x, z.y, z.z, z.w};
+    // Output pair o reads the pairs (v[i], v[i+1]), i = 4 + 2o - P + u.  Those with even i sit in an aligned
+    // register pair of the 128-bit loads and go through FFMA2; the odd ones would cost two MOVs to re-pair,
+    // so they are two scalar FFMAs on the halves of the accumulator instead (same arithmetic, bit for bit).
 #pragma unroll
     for (int o = 0; o < 2; ++o) {
-        float2 acc = __fmul2_rn(t2[0], make_float2(v[4 + 2 * o - P], v[5 + 2 * o - P]));
+        float2 acc;
+        if constexpr ((P & 1) == 0) {
+            acc = __fmul2_rn(t2[0], make_float2(v[4 + 2 * o - P], v[5 + 2 * o - P]));
+        } else {
+            acc.x = t2[0].x * v[4 + 2 * o - P];
+            acc.y = t2[0].x * v[5 + 2 * o - P];
+        }
 #pragma unroll
-        for (int u = 1; u < K; ++u) acc = __ffma2_rn(t2[u], make_float2(v[4 + 2 * o + u - P], v[5 + 2 * o + u - P]), acc);
+        for (int u = 1; u < K; ++u) {
+            if (((u - P) & 1) == 0) {
+                acc = __ffma2_rn(t2[u], make_float2(v[4 + 2 * o + u - P], v[5 + 2 * o + u - P]), acc);
+            } else {
+                acc.x = fmaf(t2[u].x, v[4 + 2 * o + u - P], acc.x);
+                acc.y = fmaf(t2[u].x, v[5 + 2 * o + u - P], acc.y);
+            }
+        }
         h[o] = acc;
     }
 }
@@ -229,43 +245,54 @@ disturb_fast_kernel(const __grid_constant__ DisturbParams p) {
     // The stripe of a channel is contiguous in global memory and is walked linearly, one quad per thread
     // and step; quad index -> (row, quad-in-row) is a multiply-high by a reciprocal (an immediate when the
     // width is a template constant); global offsets are 32-bit from one per-image base pointer.
-    auto load_own = [&]() {
+    // One quad position j (row, quad-in-row) is shared by the channels: the index arithmetic is paid once per
+    // position, the channels differ by constants.  UJ positions x CT channels = 6 quads of x and 6 of noise
+    // per thread and trip (12 independent 128-bit loads in flight), no serial tail.
+    auto load_own_c = [&](auto ct_c, auto uj_c, int c_first) {
+        constexpr int CT = decltype(ct_c)::value, UJ = decltype(uj_c)::value;
         const size_t img_off = static_cast<size_t>(b) * C * H * W;
-        const float* xs = static_cast<const float*>(p.x) + img_off + r0 * W;
-        const float* ns = do_noise ? p.noise + img_off + r0 * W : xs;
+        const float* xs = static_cast<const float*>(p.x) + img_off + c_first * HW + r0 * W;
+        const float* ns = do_noise ? p.noise + img_off + c_first * HW + r0 * W : xs;
         asm volatile("" : "+l"(xs), "+l"(ns));           // keep the two bases in registers (no rematerialisation)
-        float* const tile0 = tile + P * WP + kPad;      // first own row, first real column
-        // All channels form one index space of C * n4 quads, UNR of them per thread and trip: the whole
-        // stripe is fetched in ceil(quads per thread / UNR) memory round trips, with no serial tail.
-        constexpr int UNR = 6;                          // 12 independent 128-bit loads in flight per thread (4 and 8 measured slower)
-        const int total = C * n4;
-        float gsum = 0.0f;
-        for (int i0 = tid; i0 < total; i0 += nth * UNR) {
-            float4 xv[UNR], nv[UNR];
-            int cc[UNR], jj[UNR];
+        float* const tile0 = tile + c_first * plane + P * WP + kPad;      // first own row, first real column
+        float gs[CT];
 #pragma unroll
-            for (int u = 0; u < UNR; ++u) {
-                const int i = i0 + u * nth;
-                cc[u] = (i >= n4) + (i >= 2 * n4);      // C <= 3
-                jj[u] = i - cc[u] * n4;
-                if (i < total) {
-                    const int off = cc[u] * HW + 4 * jj[u];
-                    xv[u] = ld_stream_f4(xs + off);
-                    if (do_noise) nv[u] = ld_stream_f4(ns + off);
+        for (int c_ = 0; c_ < CT; ++c_) gs[c_] = 0.0f;
+        for (int j0 = tid; j0 < n4; j0 += nth * UJ) {
+            float4 xv[UJ][CT], nv[UJ][CT];
+#pragma unroll
+            for (int u = 0; u < UJ; ++u) {
+                const int j = j0 + u * nth;
+                if (j < n4) {
+#pragma unroll
+                    for (int c_ = 0; c_ < CT; ++c_) {
+                        xv[u][c_] = ld_stream_f4(xs + c_ * HW + 4 * j);
+                        if (do_noise) nv[u][c_] = ld_stream_f4(ns + c_ * HW + 4 * j);
+                    }
                 }
             }
 #pragma unroll
-            for (int u = 0; u < UNR; ++u) {
-                if (i0 + u * nth < total) {
-                    const float4 v = noisy4(xv[u], nv[u]);
-                    const float wc = (C == 3) ? (cc[u] == 0 ? 0.2989f : (cc[u] == 1 ? 0.587f : 0.114f)) : 1.0f;
-                    gsum = fmaf(wc, (v.x + v.y) + (v.z + v.w), gsum);
-                    const int row = div_nq(jj[u]), quad = jj[u] - row * nq;
-                    *reinterpret_cast<float4*>(tile0 + cc[u] * plane + row * WP + 4 * quad) = v;
+            for (int u = 0; u < UJ; ++u) {
+                const int j = j0 + u * nth;
+                if (j < n4) {
+                    float* dst = tile0 + 4 * j + 2 * kPad * div_nq(j);    // row * WP + 4 * quad, with 4 j = row * W + 4 * quad
+#pragma unroll
+                    for (int c_ = 0; c_ < CT; ++c_) {
+                        const float4 v = noisy4(xv[u][c_], nv[u][c_]);
+                        gs[c_] += (v.x + v.y) + (v.z + v.w);
+                        *reinterpret_cast<float4*>(dst + c_ * plane) = v;
+                    }
                 }
             }
         }
-        return gsum;
+        if constexpr (CT == 3) return fmaf(0.114f, gs[2], fmaf(0.587f, gs[1], 0.2989f * gs[0]));
+        else return gs[0];
+    };
+    auto load_own = [&]() {
+        if (C == 3) return load_own_c(std::integral_constant<int, 3>{}, std::integral_constant<int, 2>{}, 0);
+        float g = 0.0f;                                   // C == 1 (or, without a contrast stage, any channel count)
+        for (int c_ = 0; c_ < C; ++c_) g += load_own_c(std::integral_constant<int, 1>{}, std::integral_constant<int, 6>{}, c_);
+        return g;
     };
     // Halo rows: the P image rows above and below the stripe (reflected at the image border) are
     // fetched and perturbed again by this CTA instead of being copied from the neighbour's shared
@@ -299,17 +326,19 @@ disturb_fast_kernel(const __grid_constant__ DisturbParams p) {
         const float cm = __fmul_rn(p.omc, m);
         const float cf = p.c;
         const int n43 = (rows > 0 ? rows + 2 * P : 0) * nq;
-        for (int c_ = 0; c_ < C; ++c_) {
-            float* tc = tile + kPad + c_ * plane;
-            for (int i = tid; i < n43; i += nth) {
-                const int row = div_nq(i), quad = i - row * nq;
-                float4* q4 = reinterpret_cast<float4*>(tc + row * WP + 4 * quad);
-                float4 v = *q4;
-                v.x = sat_add(__fmul_rn(cf, v.x), cm);
-                v.y = sat_add(__fmul_rn(cf, v.y), cm);
-                v.z = sat_add(__fmul_rn(cf, v.z), cm);
-                v.w = sat_add(__fmul_rn(cf, v.w), cm);
-                *q4 = v;
+        for (int j = tid; j < n43; j += nth) {
+            float* q = tile + kPad + 4 * j + 2 * kPad * div_nq(j);
+#pragma unroll
+            for (int c_ = 0; c_ < 3; ++c_) {
+                if (c_ < C) {
+                    float4* q4 = reinterpret_cast<float4*>(q + c_ * plane);
+                    float4 v = *q4;
+                    v.x = sat_add(__fmul_rn(cf, v.x), cm);
+                    v.y = sat_add(__fmul_rn(cf, v.y), cm);
+                    v.z = sat_add(__fmul_rn(cf, v.z), cm);
+                    v.w = sat_add(__fmul_rn(cf, v.w), cm);
+                    *q4 = v;
+                }
             }
         }
     };
