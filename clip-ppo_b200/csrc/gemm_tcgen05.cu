@@ -86,6 +86,16 @@ __device__ __forceinline__ float quick_gelu(float v) {
     return fmaf(hv, t, hv);
 }
 
+// the same on a pair: FMUL2 / FFMA2 around two MUFU.TANH
+__device__ __forceinline__ float2 quick_gelu2(float2 v) {
+    const float2 a = __fmul2_rn(make_float2(0.851f, 0.851f), v);
+    float2 t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t.x) : "f"(a.x));
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t.y) : "f"(a.y));
+    const float2 hv = __fmul2_rn(make_float2(0.5f, 0.5f), v);
+    return __ffma2_rn(hv, t, hv);
+}
+
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
     __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&h);
@@ -255,31 +265,33 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                             const uint32_t* vv = &v[j >> 2][(j & 3) * 8];
                             const float4 b0 = __ldg(reinterpret_cast<const float4*>(g.bias + col0 + 8 * j));      // warp-uniform
                             const float4 b1 = __ldg(reinterpret_cast<const float4*>(g.bias + col0 + 8 * j + 4));
-                            float o[8];
+                            // packed fp32 (FFMA2 / FADD2): the accumulator registers of tcgen05.ld are consecutive,
+                            // so (v[2i], v[2i+1]) is an aligned pair - half the instructions of the scalar form
+                            float2 o2[4];
+                            const float2 bb[4] = {make_float2(b0.x, b0.y), make_float2(b0.z, b0.w), make_float2(b1.x, b1.y), make_float2(b1.z, b1.w)};
                             if constexpr (EPI == CLIPPPO_EPI_RESID_BF16) {
-                                o[0] = __uint_as_float(vv[0]) + b0.x; o[1] = __uint_as_float(vv[1]) + b0.y;
-                                o[2] = __uint_as_float(vv[2]) + b0.z; o[3] = __uint_as_float(vv[3]) + b0.w;
-                                o[4] = __uint_as_float(vv[4]) + b1.x; o[5] = __uint_as_float(vv[5]) + b1.y;
-                                o[6] = __uint_as_float(vv[6]) + b1.z; o[7] = __uint_as_float(vv[7]) + b1.w;
+#pragma unroll
+                                for (int t = 0; t < 4; ++t)
+                                    o2[t] = __fadd2_rn(make_float2(__uint_as_float(vv[2 * t]), __uint_as_float(vv[2 * t + 1])), bb[t]);
                             } else {
                                 float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0;
                                 if (g.colsum != nullptr) {
                                     s0 = __ldg(reinterpret_cast<const float4*>(g.colsum + col0 + 8 * j));
                                     s1 = __ldg(reinterpret_cast<const float4*>(g.colsum + col0 + 8 * j + 4));
                                 }
-                                o[0] = fmaf(rstd, fmaf(nmean, s0.x, __uint_as_float(vv[0])), b0.x);
-                                o[1] = fmaf(rstd, fmaf(nmean, s0.y, __uint_as_float(vv[1])), b0.y);
-                                o[2] = fmaf(rstd, fmaf(nmean, s0.z, __uint_as_float(vv[2])), b0.z);
-                                o[3] = fmaf(rstd, fmaf(nmean, s0.w, __uint_as_float(vv[3])), b0.w);
-                                o[4] = fmaf(rstd, fmaf(nmean, s1.x, __uint_as_float(vv[4])), b1.x);
-                                o[5] = fmaf(rstd, fmaf(nmean, s1.y, __uint_as_float(vv[5])), b1.y);
-                                o[6] = fmaf(rstd, fmaf(nmean, s1.z, __uint_as_float(vv[6])), b1.z);
-                                o[7] = fmaf(rstd, fmaf(nmean, s1.w, __uint_as_float(vv[7])), b1.w);
+                                const float2 ss[4] = {make_float2(s0.x, s0.y), make_float2(s0.z, s0.w), make_float2(s1.x, s1.y), make_float2(s1.z, s1.w)};
+                                const float2 nm2 = make_float2(nmean, nmean), rs2 = make_float2(rstd, rstd);
+#pragma unroll
+                                for (int t = 0; t < 4; ++t) {
+                                    const float2 acc = make_float2(__uint_as_float(vv[2 * t]), __uint_as_float(vv[2 * t + 1]));
+                                    o2[t] = __ffma2_rn(rs2, __ffma2_rn(nm2, ss[t], acc), bb[t]);
+                                }
                                 if constexpr (EPI == CLIPPPO_EPI_ROWAFFINE_GELU_BF16) {
 #pragma unroll
-                                    for (int t = 0; t < 8; ++t) o[t] = quick_gelu(o[t]);
+                                    for (int t = 0; t < 4; ++t) o2[t] = quick_gelu2(o2[t]);
                                 }
                             }
+                            const float o[8] = {o2[0].x, o2[0].y, o2[1].x, o2[1].y, o2[2].x, o2[2].y, o2[3].x, o2[3].y};
                             // the XOR is the TMA 128-byte swizzle of a box with 128-byte rows; conflict-free STS.128
                             const uint4 pk = make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7]));
                             if constexpr ((DBG & 8) != 0) {          // probe: math only, nothing leaves the registers
