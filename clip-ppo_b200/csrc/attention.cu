@@ -53,41 +53,52 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-// Q, K, V slices of one (image, head): 3 x 64 rows x 8 chunks of 16 B = 12 chunks per thread
-__device__ __forceinline__ void prefetch_item(const __nv_bfloat16* __restrict__ qkv, int item, int heads, int T, int D,
-                                              uint32_t buf_addr, int tid) {
-    const int img = item / heads, head = item - img * heads;
-    const __nv_bfloat16* src = qkv + static_cast<size_t>(img) * T * (3 * D) + head * DH;
-    const int c8 = tid & 7, r0 = tid >> 3;                    // 16 rows per pass
+// Q, K, V slices of one (image, head): 3 x 64 rows x 8 chunks of 16 B = 12 chunks per thread.  With the
+// head count a template constant every one of the 12 addresses is the thread's item pointer plus an
+// immediate, and the row-validity predicates are computed once per thread, not per item (address
+// arithmetic was 36 % of the kernel's instructions before).
+template <int HEADS>
+__device__ __forceinline__ void prefetch_item(const __nv_bfloat16* __restrict__ item_ptr, const bool (&row_ok)[4],
+                                              const __nv_bfloat16* __restrict__ any_valid, uint32_t dst0) {
+    constexpr int D = HEADS * DH;
 #pragma unroll
     for (int m = 0; m < 3; ++m) {
 #pragma unroll
         for (int pass = 0; pass < 4; ++pass) {
-            const int r = r0 + pass * 16;
-            const bool ok = r < T;
-            const __nv_bfloat16* g = ok ? src + static_cast<size_t>(r) * (3 * D) + m * D + c8 * 8 : qkv;
-            cp_async16(buf_addr + (m * MAT_ELEMS + r * PITCH + c8 * 8) * 2, g, ok ? 16 : 0);
+            const __nv_bfloat16* g = row_ok[pass] ? item_ptr + (pass * 16 * 3 * D + m * D) : any_valid;
+            cp_async16(dst0 + (m * MAT_ELEMS + pass * 16 * PITCH) * 2, g, row_ok[pass] ? 16 : 0);
         }
     }
 }
 
+template <int HEADS>
 __global__ void __launch_bounds__(ATT_THREADS, ATT_CTAS_PER_SM)
-attention_kernel(const __nv_bfloat16* __restrict__ qkv, int n_items, int T, int heads, __nv_bfloat16* __restrict__ out) {
+attention_kernel(const __nv_bfloat16* __restrict__ qkv, int n_items, int T, __nv_bfloat16* __restrict__ out) {
     extern __shared__ __align__(16) __nv_bfloat16 att_smem[];
-    const int D = heads * DH;
+    constexpr int D = HEADS * DH;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t smem0 = ptx_smem(att_smem);
     const int row0 = warp * 16;
+    // per-thread constants of the prefetch: my 16-byte column piece, my first row, which of my 4 rows exist
+    const int c8 = tid & 7, pr0 = tid >> 3;
+    const bool row_ok[4] = {pr0 < T, pr0 + 16 < T, pr0 + 32 < T, pr0 + 48 < T};
+    const size_t thread_off = static_cast<size_t>(pr0) * (3 * D) + c8 * 8;
+    const uint32_t dst_off = (pr0 * PITCH + c8 * 8) * 2;
+    const size_t img_stride = static_cast<size_t>(T) * (3 * D);
+    auto item_ptr = [&](int item) {
+        const int img = item / HEADS, head = item - img * HEADS;      // compile-time divisor
+        return qkv + img * img_stride + head * DH + thread_off;
+    };
 
     pdl_launch_dependents();
     pdl_wait();
     int item = blockIdx.x;
-    if (item < n_items) prefetch_item(qkv, item, heads, T, D, smem0, tid);
+    if (item < n_items) prefetch_item<HEADS>(item_ptr(item), row_ok, qkv, smem0 + dst_off);
     cp_async_commit();
     int b = 0;
     for (; item < n_items; item += gridDim.x, b ^= 1) {
         const int next = item + gridDim.x;
-        if (next < n_items) prefetch_item(qkv, next, heads, T, D, smem0 + (b ^ 1) * BUF_ELEMS * 2, tid);
+        if (next < n_items) prefetch_item<HEADS>(item_ptr(next), row_ok, qkv, smem0 + (b ^ 1) * BUF_ELEMS * 2 + dst_off);
         cp_async_commit();
         cp_async_wait<1>();                                   // this item's slices have landed
         __syncthreads();
@@ -95,7 +106,7 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv, int n_items, int T, int 
         __nv_bfloat16* sQ = att_smem + b * BUF_ELEMS;
         const uint32_t q_base = smem0 + b * BUF_ELEMS * 2;
         const uint32_t k_base = q_base + MAT_ELEMS * 2, v_base = k_base + MAT_ELEMS * 2;
-        const int img = item / heads, head = item - img * heads;
+        const int img = item / HEADS, head = item - img * HEADS;
         if (row0 < T) {
             // ---- S = Q K^T (16 x 64 per warp) ----
             float s[8][4];
@@ -147,7 +158,7 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv, int n_items, int T, int 
             sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
             sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1);
             sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
-            const float inv0 = 1.0f / sum0, inv1 = 1.0f / sum1;
+            const float inv0 = __frcp_rn(sum0), inv1 = __frcp_rn(sum1);
 
             // ---- O = P V ----
             float o[8][4];
@@ -370,16 +381,28 @@ int attention_launch(const void* qkv_bf16, int n_images, int tokens, int heads, 
         prof_count_launch();
         return CLIPPPO_OK;
     }
-    static bool configured = false;
-    if (!configured) {
-        CLIPPPO_CUDA_TRY(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
-        configured = true;
-    }
     const long long items = static_cast<long long>(n_images) * heads;
+    if (items > 0x7fffffffLL) return CLIPPPO_ERR_BAD_SHAPE;
     const int grid = static_cast<int>(items < kNumSMs * ATT_CTAS_PER_SM ? items : kNumSMs * ATT_CTAS_PER_SM);
-    CLIPPPO_CUDA_TRY(launch_pdl(attention_kernel, grid, ATT_THREADS, ATT_SMEM_BYTES, stream, 1,
-                                static_cast<const __nv_bfloat16*>(qkv_bf16), static_cast<int>(items), tokens, heads,
-                                static_cast<__nv_bfloat16*>(out_bf16)));
+    const __nv_bfloat16* q = static_cast<const __nv_bfloat16*>(qkv_bf16);
+    __nv_bfloat16* o = static_cast<__nv_bfloat16*>(out_bf16);
+    if (heads == 12) {
+        static bool configured = false;
+        if (!configured) {
+            CLIPPPO_CUDA_TRY(cudaFuncSetAttribute(attention_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
+            configured = true;
+        }
+        CLIPPPO_CUDA_TRY(launch_pdl(attention_kernel<12>, grid, ATT_THREADS, ATT_SMEM_BYTES, stream, 1, q, static_cast<int>(items), tokens, o));
+    } else if (heads == 16) {
+        static bool configured = false;
+        if (!configured) {
+            CLIPPPO_CUDA_TRY(cudaFuncSetAttribute(attention_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
+            configured = true;
+        }
+        CLIPPPO_CUDA_TRY(launch_pdl(attention_kernel<16>, grid, ATT_THREADS, ATT_SMEM_BYTES, stream, 1, q, static_cast<int>(items), tokens, o));
+    } else {
+        return CLIPPPO_ERR_UNSUPPORTED;                      // head counts of the CLIP towers: 12 (B/32, B/16), 16 (L/14)
+    }
     prof_count_launch();
     return CLIPPPO_OK;
 }
