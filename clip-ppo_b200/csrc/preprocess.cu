@@ -27,7 +27,9 @@ struct PreParams {
 };
 
 __constant__ float kClipMean[3] = {0.48145466f, 0.4578275f, 0.40821073f};
-__constant__ float kClipStd[3] = {0.26862954f, 0.26130258f, 0.27577711f};
+// 1 / (0.26862954, 0.26130258, 0.27577711): the reference divides by std in fp32; a reciprocal multiply differs by
+// <= 1 ulp of fp32, far below the bf16 rounding of the patch matrix (8 fp32 divisions per thread were ~80 instructions)
+__constant__ float kClipInvStd[3] = {1.0f / 0.26862954f, 1.0f / 0.26130258f, 1.0f / 0.27577711f};
 
 __device__ __forceinline__ float load_px(const PreParams& p, long long off) {
     const float raw = (p.dtype == CLIPPPO_IMG_U8) ? static_cast<float>(static_cast<const uint8_t*>(p.img)[off])
@@ -90,11 +92,11 @@ __global__ void __launch_bounds__(256) preprocess_resize_kernel(const PreParams 
         const float4 a0 = *reinterpret_cast<const float4*>(r0p), a1 = *reinterpret_cast<const float4*>(r0p + 4);
         const float4 b0 = *reinterpret_cast<const float4*>(r1p), b1 = *reinterpret_cast<const float4*>(r1p + 4);
         const float h0 = 1.0f - ly;
-        const float mean = p.normalize ? kClipMean[c] : 0.0f, stdv = p.normalize ? kClipStd[c] : 1.0f;
+        const float mean = p.normalize ? kClipMean[c] : 0.0f, istd = p.normalize ? kClipInvStd[c] : 1.0f;
         float o[8] = {h0 * a0.x + ly * b0.x, h0 * a0.y + ly * b0.y, h0 * a0.z + ly * b0.z, h0 * a0.w + ly * b0.w,
                       h0 * a1.x + ly * b1.x, h0 * a1.y + ly * b1.y, h0 * a1.z + ly * b1.z, h0 * a1.w + ly * b1.w};
 #pragma unroll
-        for (int t = 0; t < 8; ++t) o[t] = (o[t] - mean) / stdv;
+        for (int t = 0; t < 8; ++t) o[t] = (o[t] - mean) * istd;
         const int ox0 = grp * 8, gx = ox0 / P, kx0 = ox0 - gx * P;
         __nv_bfloat16* dst = p.out + (static_cast<size_t>(b) * G * G + gy * G + gx) * p.kpad + (c * P + ky) * P + kx0;
         uint4 pk;
@@ -127,7 +129,7 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const PreParams p) {
             // h == w == image: the resize is the identity; 8 contiguous source pixels per thread
             const int cin = (p.C == 1) ? 0 : c;
             const long long off = img_off + cin * p.s[1] + static_cast<long long>(oy) * p.s[2] + (gx * P + kx0);
-            const float mean = p.normalize ? kClipMean[c] : 0.0f, stdv = p.normalize ? kClipStd[c] : 1.0f;
+            const float mean = p.normalize ? kClipMean[c] : 0.0f, istd = p.normalize ? kClipInvStd[c] : 1.0f;
             float o[8];
             if (p.dtype == CLIPPPO_IMG_U8) {
                 const uint2 raw = *reinterpret_cast<const uint2*>(static_cast<const uint8_t*>(p.img) + off);
@@ -142,7 +144,7 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const PreParams p) {
                 o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b4.x; o[5] = b4.y; o[6] = b4.z; o[7] = b4.w;
             }
 #pragma unroll
-            for (int t = 0; t < 8; ++t) o[t] = (o[t] * p.pre_scale - mean) / stdv;
+            for (int t = 0; t < 8; ++t) o[t] = (o[t] * p.pre_scale - mean) * istd;
             __nv_bfloat16* dst = p.out + (static_cast<size_t>(b) * G * G + gy * G + gx) * p.kpad + (c * P + ky) * P + kx0;
             uint4 pk;
             __nv_bfloat162 h0 = __floats2bfloat162_rn(o[0], o[1]), h1 = __floats2bfloat162_rn(o[2], o[3]);
@@ -157,7 +159,7 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const PreParams p) {
         const int cin = (p.C == 1) ? 0 : c;
         const long long base0 = img_off + cin * p.s[1] + static_cast<long long>(y0) * p.s[2];
         const long long base1 = img_off + cin * p.s[1] + static_cast<long long>(y1) * p.s[2];
-        const float mean = p.normalize ? kClipMean[c] : 0.0f, stdv = p.normalize ? kClipStd[c] : 1.0f;
+        const float mean = p.normalize ? kClipMean[c] : 0.0f, istd = p.normalize ? kClipInvStd[c] : 1.0f;
         float o[VEC];
 #pragma unroll
         for (int t = 0; t < VEC; ++t) {
@@ -167,7 +169,7 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const PreParams p) {
             const float p00 = load_px(p, base0 + x0 * p.s[3]), p01 = load_px(p, base0 + x1 * p.s[3]);
             const float p10 = load_px(p, base1 + x0 * p.s[3]), p11 = load_px(p, base1 + x1 * p.s[3]);
             const float v = (1.0f - ly) * ((1.0f - lx) * p00 + lx * p01) + ly * ((1.0f - lx) * p10 + lx * p11);
-            o[t] = (v - mean) / stdv;
+            o[t] = (v - mean) * istd;
         }
         __nv_bfloat16* dst = p.out + (static_cast<size_t>(b) * G * G + gy * G + gx) * p.kpad + (c * P + ky) * P + kx0;
         if constexpr (VEC == 8) {
