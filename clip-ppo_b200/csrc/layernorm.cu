@@ -37,27 +37,27 @@ rowstats_kernel(const __nv_bfloat16* __restrict__ x, int rows, long long row_str
     if (row >= rows) return;
     constexpr int width = NV * 256;
     const uint4* xr = reinterpret_cast<const uint4*>(x + static_cast<size_t>(row) * row_stride);
-    float v[NV][8];
-    float s = 0.f;
+    float2 v[NV][4];                                   // packed fp32 pairs: FADD2 / FFMA2 halve the arithmetic
+    float2 s2 = make_float2(0.f, 0.f);
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
         const uint4 u = xr[lane + 32 * i];
         const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
-            const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[t]));
-            v[i][2 * t] = f.x; v[i][2 * t + 1] = f.y;
+            v[i][t] = make_float2(__uint_as_float(w[t] << 16), __uint_as_float(w[t] & 0xffff0000u));     // bf16 -> fp32, exact
+            s2 = __fadd2_rn(s2, v[i][t]);
         }
-        s += ((v[i][0] + v[i][1]) + (v[i][2] + v[i][3])) + ((v[i][4] + v[i][5]) + (v[i][6] + v[i][7]));
     }
-    const float mean = warp_sum(s) * (1.0f / width);
-    float q = 0.f;
+    const float mean = warp_sum(s2.x + s2.y) * (1.0f / width);
+    const float2 nm = make_float2(-mean, -mean);
+    float2 q2 = make_float2(0.f, 0.f);
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
 #pragma unroll
-        for (int t = 0; t < 8; ++t) { const float d = v[i][t] - mean; q = fmaf(d, d, q); }
+        for (int t = 0; t < 4; ++t) { const float2 d = __fadd2_rn(v[i][t], nm); q2 = __ffma2_rn(d, d, q2); }
     }
-    const float rstd = rsqrtf(warp_sum(q) * (1.0f / width) + 1e-5f);
+    const float rstd = rsqrtf(warp_sum(q2.x + q2.y) * (1.0f / width) + 1e-5f);
     if (lane == 0) stats[row] = make_float2(mean, rstd);
 }
 
