@@ -156,7 +156,7 @@ def run_reference_arm(args):
     value = n * args.steps / dt
     cores = torch.get_num_threads()
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": args.gpus,
+        "impl": "reference", "metric": METRIC.replace("ViT-B/32", args.model), "value": value, "unit": "frames/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args, args.batch),
@@ -169,7 +169,8 @@ def run_reference_arm(args):
 
 
 def workload_config(args, per_gpu_batch):
-    return {"workload": f"BASELINE configs[2]: synthetic {args.hw}x{args.hw} RGB frames, disturb({args.severity}) -> "
+    which = "configs[2]" if args.model == "ViT-B/32" else "configs[4]'s ViT-L/14 variant, one GPU's share"
+    return {"workload": f"BASELINE {which}: synthetic {args.hw}x{args.hw} RGB frames, disturb({args.severity}) -> "
                         f"{args.model} embed -> cosine alignment loss",
             "per_gpu_batch": per_gpu_batch, "frame": [3, args.hw, args.hw], "severity": args.severity,
             "weights": f"seeded random {args.model} (openai key layout)",
@@ -351,7 +352,7 @@ def main():
         except Exception:
             ncu_traffic = None
     line = {
-        "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+        "metric": METRIC.replace("ViT-B/32", args.model), "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": workload_config(args, B),
         "clocks": clocks, "gpu_launches": int(launches.value),

@@ -204,80 +204,94 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv, int n_items, int T, __nv
 }
 
 // ---- any T (ViT-L/14: T = 257) ---------------------------------------------------------------
-// One CTA = one (image, head, block of 64 queries).  The keys / values are walked in blocks of 64
-// (cp.async double-buffered) with the usual online softmax: running row maximum and sum in
-// registers, the output accumulator rescaled when the maximum moves.  Same mma.sync fragments as
-// the single-block kernel above.
-constexpr int ATTG_SMEM_BYTES = (MAT_ELEMS + 2 * 2 * MAT_ELEMS) * 2;      // Q + 2 x (K, V): 46080 B
+// One CTA = one (image, head): K and V of all T tokens are loaded into shared memory ONCE (cp.async,
+// zero-filled up to a multiple of 16 rows), then the 6 warps walk the ceil(T/16) query tiles of 16 rows;
+// a warp stages its query tile through a private 16-row buffer, runs the keys in blocks of 64 with an
+// online softmax (running maximum / sum in registers, output accumulator rescaled when the maximum
+// moves) and writes its 16 x 64 output tile back through the same buffer.  A last key block of <= 8 keys
+// (T = 257: exactly the one key left after four blocks) costs one 8-key MMA tile instead of a padded block.
+constexpr int ATTG_WARPS = 6;
+constexpr int ATTG_THREADS = ATTG_WARPS * 32;
+constexpr int ATTG_QROWS = 16;
 
-__device__ __forceinline__ void prefetch_rows(const __nv_bfloat16* __restrict__ src, long long row_stride, int first_row, int T,
-                                              uint32_t dst, int tid) {
-    const int c8 = tid & 7, r0 = tid >> 3;                    // 16 rows per pass, 8 x 16 B per row
-#pragma unroll
-    for (int pass = 0; pass < 4; ++pass) {
-        const int r = r0 + pass * 16;
-        const bool ok = first_row + r < T;
-        const __nv_bfloat16* g = ok ? src + static_cast<size_t>(first_row + r) * row_stride + c8 * 8 : src;
-        cp_async16(dst + (r * PITCH + c8 * 8) * 2, g, ok ? 16 : 0);
-    }
+__host__ __device__ constexpr int attg_kv_rows(int T) { return (T + 15) / 16 * 16; }
+__host__ __device__ constexpr size_t attg_smem_bytes(int T) {
+    return (static_cast<size_t>(2) * attg_kv_rows(T) + ATTG_WARPS * ATTG_QROWS) * PITCH * 2;
 }
 
-__global__ void __launch_bounds__(ATT_THREADS, 4)
-attention_general_kernel(const __nv_bfloat16* __restrict__ qkv, int T, int heads, int qblocks, __nv_bfloat16* __restrict__ out) {
+template <int HEADS>
+__global__ void __launch_bounds__(ATTG_THREADS, 2)
+attention_general_kernel(const __nv_bfloat16* __restrict__ qkv, int T, __nv_bfloat16* __restrict__ out) {
     extern __shared__ __align__(16) __nv_bfloat16 att_smem[];
-    const int D = heads * DH;
+    constexpr int D = HEADS * DH;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const uint32_t q_base = ptx_smem(att_smem);
-    const uint32_t kv_base0 = q_base + MAT_ELEMS * 2;
-    const int row0 = warp * 16;
-    const int qb = blockIdx.x % qblocks, item = blockIdx.x / qblocks;
-    const int img = item / heads, head = item - img * heads;
-    const long long rs = 3LL * D;
-    const __nv_bfloat16* base = qkv + static_cast<size_t>(img) * T * rs + head * DH;
-    const int nkb = (T + TP - 1) / TP;
+    const int rows_kv = attg_kv_rows(T);
+    const uint32_t k_base = ptx_smem(att_smem);
+    const uint32_t v_base = k_base + rows_kv * PITCH * 2;
+    __nv_bfloat16* sQ = att_smem + 2 * rows_kv * PITCH + warp * ATTG_QROWS * PITCH;
+    const uint32_t q_base = ptx_smem(sQ);
+    const int item = blockIdx.x;
+    const int img = item / HEADS, head = item - img * HEADS;
+    const __nv_bfloat16* base = qkv + static_cast<size_t>(img) * T * (3 * D) + head * DH;
+    __nv_bfloat16* obase = out + static_cast<size_t>(img) * T * D + head * DH;
 
     pdl_launch_dependents();
     pdl_wait();
-    prefetch_rows(base, rs, qb * TP, T, q_base, tid);
-    prefetch_rows(base + D, rs, 0, T, kv_base0, tid);
-    prefetch_rows(base + 2 * D, rs, 0, T, kv_base0 + MAT_ELEMS * 2, tid);
+    // K, V -> smem: 8 x 16-byte pieces per row
+    for (int i = tid; i < rows_kv * 8; i += ATTG_THREADS) {
+        const int r = i >> 3, c8 = i & 7;
+        const bool ok = r < T;
+        const __nv_bfloat16* g = ok ? base + static_cast<size_t>(r) * (3 * D) + c8 * 8 : qkv;
+        cp_async16(k_base + (r * PITCH + c8 * 8) * 2, g + D, ok ? 16 : 0);
+        cp_async16(v_base + (r * PITCH + c8 * 8) * 2, g + 2 * D, ok ? 16 : 0);
+    }
     cp_async_commit();
 
     const float sl2 = 0.125f * 1.4426950408889634f;
-    float o[8][4];
+    const int n_qt = (T + ATTG_QROWS - 1) / ATTG_QROWS;
+    const int n_full = T / TP, k_tail = T - n_full * TP;          // key blocks of 64, keys left over
+    bool kv_ready = false;
+    for (int qt = warp; qt < n_qt; qt += ATTG_WARPS) {
+        // my query tile -> my staging rows (2 pieces per lane), zero-filled beyond T
+        {
+            const int r = lane >> 1, c0 = (lane & 1) * 4;
+            const bool ok = qt * ATTG_QROWS + r < T;
+            const __nv_bfloat16* g = ok ? base + static_cast<size_t>(qt * ATTG_QROWS + r) * (3 * D) + c0 * 8 : qkv;
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt) { o[nt][0] = o[nt][1] = o[nt][2] = o[nt][3] = 0.f; }
-    float mrun0 = -INFINITY, mrun1 = -INFINITY, lrun0 = 0.f, lrun1 = 0.f;      // rows lane/4 and lane/4 + 8
-    const bool active = qb * TP + row0 < T;
-    for (int kb = 0; kb < nkb; ++kb) {
-        const uint32_t k_base = kv_base0 + (kb & 1) * 2 * MAT_ELEMS * 2, v_base = k_base + MAT_ELEMS * 2;
-        if (kb + 1 < nkb) {
-            const uint32_t nk = kv_base0 + ((kb + 1) & 1) * 2 * MAT_ELEMS * 2;
-            prefetch_rows(base + D, rs, (kb + 1) * TP, T, nk, tid);
-            prefetch_rows(base + 2 * D, rs, (kb + 1) * TP, T, nk + MAT_ELEMS * 2, tid);
+            for (int c = 0; c < 4; ++c) cp_async16(q_base + (r * PITCH + (c0 + c) * 8) * 2, g + c * 8, ok ? 16 : 0);
+            cp_async_commit();
+            cp_async_wait<0>();
+            __syncwarp();
         }
-        cp_async_commit();
-        cp_async_wait<1>();                                   // Q and key block kb have landed
-        __syncthreads();
-        if (active) {
+        if (!kv_ready) { __syncthreads(); kv_ready = true; }     // everybody's K / V pieces have landed (first trip only)
+        uint32_t aq[DH / 16][4];
+        {
+            const uint32_t q_addr = q_base + ((lane & 15) * PITCH + (lane >> 4) * 8) * 2;
+#pragma unroll
+            for (int ks = 0; ks < DH / 16; ++ks) ldsm_x4(q_addr + ks * 32, aq[ks][0], aq[ks][1], aq[ks][2], aq[ks][3]);
+        }
+        float o[8][4];
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) { o[nt][0] = o[nt][1] = o[nt][2] = o[nt][3] = 0.f; }
+        float mrun0 = -INFINITY, mrun1 = -INFINITY, lrun0 = 0.f, lrun1 = 0.f;      // rows lane/4 and lane/4 + 8
+        const int nkb = n_full + (k_tail > 8 ? 1 : 0);            // blocks run at full width (a wide tail is masked)
+        for (int kb = 0; kb < nkb; ++kb) {
+            const uint32_t kb_k = k_base + kb * TP * PITCH * 2, kb_v = v_base + kb * TP * PITCH * 2;
             float s[8][4];
 #pragma unroll
             for (int nt = 0; nt < 8; ++nt) { s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f; }
-            const uint32_t q_addr = q_base + ((row0 + (lane & 15)) * PITCH + (lane >> 4) * 8) * 2;
-            const uint32_t k_addr = k_base + (((lane & 7) + (lane >> 4) * 8) * PITCH + ((lane >> 3) & 1) * 8) * 2;
+            const uint32_t k_addr = kb_k + (((lane & 7) + (lane >> 4) * 8) * PITCH + ((lane >> 3) & 1) * 8) * 2;
 #pragma unroll
             for (int ks = 0; ks < DH / 16; ++ks) {
-                uint32_t a[4];
-                ldsm_x4(q_addr + ks * 32, a[0], a[1], a[2], a[3]);
 #pragma unroll
                 for (int np = 0; np < 4; ++np) {
                     uint32_t b0, b1, b2, b3;
                     ldsm_x4(k_addr + (np * 16 * PITCH) * 2 + ks * 32, b0, b1, b2, b3);
-                    mma_bf16_16816(s[2 * np], a, b0, b1);
-                    mma_bf16_16816(s[2 * np + 1], a, b2, b3);
+                    mma_bf16_16816(s[2 * np], aq[ks], b0, b1);
+                    mma_bf16_16816(s[2 * np + 1], aq[ks], b2, b3);
                 }
             }
-            const int kleft = T - kb * TP;                    // valid keys in this block
+            const int kleft = T - kb * TP;                        // valid keys in this block (>= 64 unless it is the tail)
             float mx0 = mrun0, mx1 = mrun1;
 #pragma unroll
             for (int nt = 0; nt < 8; ++nt) {
@@ -293,7 +307,6 @@ attention_general_kernel(const __nv_bfloat16* __restrict__ qkv, int T, int heads
             mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
             mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
             mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
-            // every key block holds at least one valid key, so the new maxima are finite
             const float c0 = ex2((mrun0 - mx0) * sl2), c1 = ex2((mrun1 - mx1) * sl2);      // exp2(-inf) = 0 on the first block
             mrun0 = mx0; mrun1 = mx1;
             const float m0 = mx0 * sl2, m1 = mx1 * sl2;
@@ -315,47 +328,89 @@ attention_general_kernel(const __nv_bfloat16* __restrict__ qkv, int T, int heads
             lrun1 = lrun1 * c1 + sum1;
 #pragma unroll
             for (int nt = 0; nt < 8; ++nt) { o[nt][0] *= c0; o[nt][1] *= c0; o[nt][2] *= c1; o[nt][3] *= c1; }
-            const uint32_t v_addr = v_base + (((lane & 7) + ((lane >> 3) & 1) * 8) * PITCH + (lane >> 4) * 8) * 2;
-#pragma unroll
+            const uint32_t v_addr = kb_v + (((lane & 7) + ((lane >> 3) & 1) * 8) * PITCH + (lane >> 4) * 8) * 2;
+            const int ksteps = kleft >= TP ? TP / 16 : (kleft + 15) / 16;      // zero-filled rows beyond T contribute nothing
             for (int kk = 0; kk < TP / 16; ++kk) {
-                uint32_t a[4];
-                a[0] = pack2(s[2 * kk][0], s[2 * kk][1]);
-                a[1] = pack2(s[2 * kk][2], s[2 * kk][3]);
-                a[2] = pack2(s[2 * kk + 1][0], s[2 * kk + 1][1]);
-                a[3] = pack2(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+                if (kk < ksteps) {
+                    uint32_t a[4];
+                    a[0] = pack2(s[2 * kk][0], s[2 * kk][1]);
+                    a[1] = pack2(s[2 * kk][2], s[2 * kk][3]);
+                    a[2] = pack2(s[2 * kk + 1][0], s[2 * kk + 1][1]);
+                    a[3] = pack2(s[2 * kk + 1][2], s[2 * kk + 1][3]);
 #pragma unroll
-                for (int dp = 0; dp < 4; ++dp) {
-                    uint32_t b0, b1, b2, b3;
-                    ldsm_x4_trans(v_addr + (kk * 16 * PITCH + dp * 16) * 2, b0, b1, b2, b3);
-                    mma_bf16_16816(o[2 * dp], a, b0, b1);
-                    mma_bf16_16816(o[2 * dp + 1], a, b2, b3);
+                    for (int dp = 0; dp < 4; ++dp) {
+                        uint32_t b0, b1, b2, b3;
+                        ldsm_x4_trans(v_addr + (kk * 16 * PITCH + dp * 16) * 2, b0, b1, b2, b3);
+                        mma_bf16_16816(o[2 * dp], a, b0, b1);
+                        mma_bf16_16816(o[2 * dp + 1], a, b2, b3);
+                    }
                 }
             }
         }
-        __syncthreads();                                      // this K/V buffer is refilled two blocks later
-    }
-    cp_async_wait<0>();
-    if (active) {
-        const float inv0 = 1.0f / lrun0, inv1 = 1.0f / lrun1;
-        __nv_bfloat16* sQ = att_smem;                         // stage the 16 x 64 output in this warp's own Q rows
+        if (k_tail > 0 && k_tail <= 8) {
+            // narrow tail: one 8-key tile (keys n_full*64 .. +7, those beyond T masked), one 16-key PV step
+            const uint32_t kb_k = k_base + n_full * TP * PITCH * 2, kb_v = v_base + n_full * TP * PITCH * 2;
+            float s0[4] = {0.f, 0.f, 0.f, 0.f};
+            const uint32_t k_addr = kb_k + ((lane & 7) * PITCH + ((lane >> 3) & 1) * 8) * 2;     // lanes 16-31 repeat 0-15 (their matrices are unused)
+#pragma unroll
+            for (int ks = 0; ks < DH / 16; ++ks) {
+                uint32_t b0, b1, b2, b3;
+                ldsm_x4(k_addr + ks * 32, b0, b1, b2, b3);
+                mma_bf16_16816(s0, aq[ks], b0, b1);
+            }
+            const int n = 2 * (lane & 3);
+            if (n >= k_tail)     { s0[0] = -INFINITY; s0[2] = -INFINITY; }
+            if (n + 1 >= k_tail) { s0[1] = -INFINITY; s0[3] = -INFINITY; }
+            float mx0 = fmaxf(mrun0, fmaxf(s0[0], s0[1])), mx1 = fmaxf(mrun1, fmaxf(s0[2], s0[3]));
+            mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+            mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+            mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+            mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+            const float c0 = ex2((mrun0 - mx0) * sl2), c1 = ex2((mrun1 - mx1) * sl2);
+            const float m0 = mx0 * sl2, m1 = mx1 * sl2;
+            s0[0] = ex2(fmaf(s0[0], sl2, -m0)); s0[1] = ex2(fmaf(s0[1], sl2, -m0));
+            s0[2] = ex2(fmaf(s0[2], sl2, -m1)); s0[3] = ex2(fmaf(s0[3], sl2, -m1));
+            float sum0 = s0[0] + s0[1], sum1 = s0[2] + s0[3];
+            sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1);
+            sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
+            sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1);
+            sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
+            lrun0 = lrun0 * c0 + sum0;
+            lrun1 = lrun1 * c1 + sum1;
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) { o[nt][0] *= c0; o[nt][1] *= c0; o[nt][2] *= c1; o[nt][3] *= c1; }
+            uint32_t a[4] = {pack2(s0[0], s0[1]), pack2(s0[2], s0[3]), 0u, 0u};            // keys 8..15 of the step: zero weight
+            const uint32_t v_addr = kb_v + (((lane & 7) + ((lane >> 3) & 1) * 8) * PITCH + (lane >> 4) * 8) * 2;
+#pragma unroll
+            for (int dp = 0; dp < 4; ++dp) {
+                uint32_t b0, b1, b2, b3;
+                ldsm_x4_trans(v_addr + (dp * 16) * 2, b0, b1, b2, b3);
+                mma_bf16_16816(o[2 * dp], a, b0, b1);
+                mma_bf16_16816(o[2 * dp + 1], a, b2, b3);
+            }
+        }
+        // ---- normalise, stage the 16 x 64 tile in my query rows, 16-byte coalesced stores ----
+        const float inv0 = __frcp_rn(lrun0), inv1 = __frcp_rn(lrun1);
         __syncwarp();
 #pragma unroll
         for (int nt = 0; nt < 8; ++nt) {
             const int c = nt * 8 + 2 * (lane & 3);
-            *reinterpret_cast<uint32_t*>(sQ + (row0 + (lane >> 2)) * PITCH + c) = pack2(o[nt][0] * inv0, o[nt][1] * inv0);
-            *reinterpret_cast<uint32_t*>(sQ + (row0 + (lane >> 2) + 8) * PITCH + c) = pack2(o[nt][2] * inv1, o[nt][3] * inv1);
+            *reinterpret_cast<uint32_t*>(sQ + (lane >> 2) * PITCH + c) = pack2(o[nt][0] * inv0, o[nt][1] * inv0);
+            *reinterpret_cast<uint32_t*>(sQ + ((lane >> 2) + 8) * PITCH + c) = pack2(o[nt][2] * inv1, o[nt][3] * inv1);
         }
         __syncwarp();
-        __nv_bfloat16* dst = out + static_cast<size_t>(img) * T * D + head * DH;
 #pragma unroll
         for (int it = 0; it < 4; ++it) {
-            const int r = row0 + it * 4 + (lane >> 3), c8 = lane & 7;
-            const int t = qb * TP + r;
+            const int r = it * 4 + (lane >> 3), c8 = lane & 7;
+            const int t = qt * ATTG_QROWS + r;
             if (t < T)
-                *reinterpret_cast<uint4*>(dst + static_cast<size_t>(t) * D + c8 * 8) =
+                *reinterpret_cast<uint4*>(obase + static_cast<size_t>(t) * D + c8 * 8) =
                     *reinterpret_cast<const uint4*>(sQ + r * PITCH + c8 * 8);
         }
+        __syncwarp();                                             // my staging rows are refilled by the next query tile
     }
+    if (!kv_ready) __syncthreads();                               // a warp without a query tile still meets the barrier
+    cp_async_wait<0>();
 }
 
 }  // namespace
@@ -366,18 +421,30 @@ int attention_launch(const void* qkv_bf16, int n_images, int tokens, int heads, 
     if (n_images <= 0 || tokens <= 0 || heads <= 0) return CLIPPPO_ERR_BAD_SHAPE;
     if (head_dim != DH) return CLIPPPO_ERR_UNSUPPORTED;
     if ((reinterpret_cast<uintptr_t>(qkv_bf16) % 16) || (reinterpret_cast<uintptr_t>(out_bf16) % 16)) return CLIPPPO_ERR_ALIGN;
-    if (tokens > TP) {                               // ViT-L/14 (T = 257): key blocks + online softmax
-        static bool configured_g = false;
-        if (!configured_g) {
-            CLIPPPO_CUDA_TRY(cudaFuncSetAttribute(attention_general_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTG_SMEM_BYTES));
-            configured_g = true;
-        }
-        const int qblocks = (tokens + TP - 1) / TP;
-        const long long ctas = static_cast<long long>(n_images) * heads * qblocks;
+    if (tokens > TP) {                               // ViT-L/14 (T = 257): one CTA per (image, head), K / V resident
+        const size_t smem = attg_smem_bytes(tokens);
+        if (smem > 113 * 1024) return CLIPPPO_ERR_UNSUPPORTED;      // 2 CTAs / SM; T <= 352
+        const long long ctas = static_cast<long long>(n_images) * heads;
         if (ctas > 0x7fffffffLL) return CLIPPPO_ERR_BAD_SHAPE;
-        CLIPPPO_CUDA_TRY(launch_pdl(attention_general_kernel, static_cast<unsigned>(ctas), ATT_THREADS, ATTG_SMEM_BYTES, stream, 1,
-                                    static_cast<const __nv_bfloat16*>(qkv_bf16), tokens, heads, qblocks,
-                                    static_cast<__nv_bfloat16*>(out_bf16)));
+        const __nv_bfloat16* q = static_cast<const __nv_bfloat16*>(qkv_bf16);
+        __nv_bfloat16* o = static_cast<__nv_bfloat16*>(out_bf16);
+        if (heads == 16) {
+            static bool configured = false;
+            if (!configured) {
+                CLIPPPO_CUDA_TRY(cudaFuncSetAttribute(attention_general_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
+                configured = true;
+            }
+            CLIPPPO_CUDA_TRY(launch_pdl(attention_general_kernel<16>, static_cast<unsigned>(ctas), ATTG_THREADS, smem, stream, 1, q, tokens, o));
+        } else if (heads == 12) {
+            static bool configured = false;
+            if (!configured) {
+                CLIPPPO_CUDA_TRY(cudaFuncSetAttribute(attention_general_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
+                configured = true;
+            }
+            CLIPPPO_CUDA_TRY(launch_pdl(attention_general_kernel<12>, static_cast<unsigned>(ctas), ATTG_THREADS, smem, stream, 1, q, tokens, o));
+        } else {
+            return CLIPPPO_ERR_UNSUPPORTED;
+        }
         prof_count_launch();
         return CLIPPPO_OK;
     }
