@@ -74,6 +74,8 @@ struct GemmArgs {
     long long ldo;         // elements
     const float2* stats;   // ROWAFFINE: per-row (mean, rstd) of the un-normalised A rows, or null (=> 0, 1)
     const float* colsum;   // ROWAFFINE: s[n] = sum_k W[n,k] (LayerNorm gamma already folded into W)
+    int ksplit;            // RESID_BF16 only: a tile's K range is cut into ksplit work items that each reduce-add
+                           // their partial sum (the first one carries the bias); 1 everywhere else
 };
 
 // QuickGELU x * sigmoid(1.702 x) = 0.5 x (1 + tanh(0.851 x)): one MUFU op (tanh.approx, rel. error
@@ -128,7 +130,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     // work decomposition: unit = CTA (MODE 1) or CTA pair (MODE 2); a work item is CL stacked M-tiles
     const int rank = (CL == 2) ? static_cast<int>(cluster_ctarank()) : 0;
     const int unit = blockIdx.x / CL, num_units = gridDim.x / CL;
-    const int num_work = ((m_tiles + CL - 1) / CL) * n_tiles;
+    // split-K (small M, reduce-add epilogue): work item = (tile, K slice); the slices of a tile are neighbours
+    const int ksplit = (EPI == CLIPPPO_EPI_RESID_BF16) ? g.ksplit : 1;
+    const int num_work = ((m_tiles + CL - 1) / CL) * n_tiles * ksplit;
+    auto kb_begin = [&](int ks) { return ksplit == 1 ? 0 : ks * num_kb / ksplit; };
+    auto kb_end = [&](int ks) { return ksplit == 1 ? num_kb : (ks + 1) * num_kb / ksplit; };
 
     if (warp == W_TMA && lane == 0) {
         prefetch_tmap(&tmap_a);
@@ -157,8 +163,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
             for (int w = unit; w < num_work; w += num_units) {
-                const int mg = w / n_tiles, n_blk = w - mg * n_tiles, m_blk = mg * CL + rank;
-                for (int kb = 0; kb < num_kb; ++kb) {
+                const int t = w / ksplit, ks = w - t * ksplit;
+                const int mg = t / n_tiles, n_blk = t - mg * n_tiles, m_blk = mg * CL + rank;
+                for (int kb = kb_begin(ks), kbe = kb_end(ks); kb < kbe; ++kb) {
                     mbar_wait(empty_bar(stage), phase ^ 1);
                     const uint32_t sa = sbase + C::OFF_A + stage * C::A_STAGE_BYTES;
                     const uint32_t sb = sbase + C::OFF_B + stage * C::B_STAGE_BYTES;
@@ -189,7 +196,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 mbar_wait(tempty_bar(as), aphase ^ 1);          // epilogues have drained this accumulator
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + as * BN;
-                for (int kb = 0; kb < num_kb; ++kb) {
+                const int ks = w % ksplit, kb0 = kb_begin(ks);
+                for (int kb = kb0, kbe = kb_end(ks); kb < kbe; ++kb) {
                     mbar_wait(full_bar(stage), phase);          // TMA bytes (of both CTAs) have landed
                     tc_fence_after();
                     const uint64_t da = make_kmajor_sw128_desc(sbase + C::OFF_A + stage * C::A_STAGE_BYTES);
@@ -197,8 +205,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; ++k) {
                         // +32 bytes per 16-element k-step inside the 128-byte swizzle atom
-                        if constexpr (CL == 2) umma_bf16_2sm(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
-                        else umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                        if constexpr (CL == 2) umma_bf16_2sm(tmem_d, da + 2 * k, db + 2 * k, idesc, ((kb - kb0) | k) != 0);
+                        else umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, ((kb - kb0) | k) != 0);
                     }
                     // smem slot free (in both CTAs) once these MMAs retire
                     if constexpr (CL == 2) umma_commit_2sm(empty_bar(stage), 0x3); else umma_commit(empty_bar(stage));
@@ -218,7 +226,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         uint8_t* stg = stg0;
         int as = 0; uint32_t aphase = 0;
         for (int w = unit; w < num_work; w += num_units) {
-            const int mg = w / n_tiles, n_blk = w - mg * n_tiles, m_blk = mg * CL + rank;
+            const int t = w / ksplit, ks = w - t * ksplit;
+            const int mg = t / n_tiles, n_blk = t - mg * n_tiles, m_blk = mg * CL + rank;
             const int row_base = m_blk * BM + q * 32;
             if constexpr (is_bf16_tma(EPI)) {
                 // thread = accumulator row.  Two 64-column chunks per warp and tile; each becomes one
@@ -263,8 +272,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {                  // 16-byte piece j = columns 8j .. 8j+7
                             const uint32_t* vv = &v[j >> 2][(j & 3) * 8];
-                            const float4 b0 = __ldg(reinterpret_cast<const float4*>(g.bias + col0 + 8 * j));      // warp-uniform
-                            const float4 b1 = __ldg(reinterpret_cast<const float4*>(g.bias + col0 + 8 * j + 4));
+                            float4 b0 = __ldg(reinterpret_cast<const float4*>(g.bias + col0 + 8 * j));      // warp-uniform
+                            float4 b1 = __ldg(reinterpret_cast<const float4*>(g.bias + col0 + 8 * j + 4));
+                            if constexpr (EPI == CLIPPPO_EPI_RESID_BF16) {
+                                if (ks != 0) { b0 = make_float4(0.f, 0.f, 0.f, 0.f); b1 = b0; }           // the first K slice carries the bias
+                            }
                             // packed fp32 (FFMA2 / FADD2): the accumulator registers of tcgen05.ld are consecutive,
                             // so (v[2i], v[2i+1]) is an aligned pair - half the instructions of the scalar form
                             float2 o2[4];
@@ -505,7 +517,7 @@ int launch_gemm_mode(const CUtensorMap& ta, const CUtensorMap& tb, const CUtenso
         configured = true;
     }
     const int m_tiles = (g.M + BM - 1) / BM, n_tiles = (g.N + BN - 1) / BN;
-    const int work = ((m_tiles + C::CL - 1) / C::CL) * n_tiles;
+    const int work = ((m_tiles + C::CL - 1) / C::CL) * n_tiles * (EPI == CLIPPPO_EPI_RESID_BF16 ? g.ksplit : 1);
     const int grid = min(work, kNumSMs / C::CL) * C::CL;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
@@ -627,6 +639,24 @@ int gemm_probe_launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmAr
     return CLIPPPO_ERR_UNSUPPORTED;
 }
 
+// Small M with the reduce-add epilogue (opt-in, CLIPPPO_GEMM_KSPLIT=auto | n): when the tiles alone leave most
+// CTA pairs idle, cut each tile's K range into slices (>= 6 k-blocks each) until the pairs are covered; every
+// slice adds its bf16-rounded partial sum into the residual stream.  Off by default: the slices of a tile add
+// in whatever order they finish, so results are no longer bitwise reproducible run to run (8 frames per
+// call: 751 -> 586 us per tower pass; 64 frames: 955 -> 936 us).  Large M is never split.
+int pick_ksplit(int M, int N, int K) {
+    const char* e = getenv("CLIPPPO_GEMM_KSPLIT");
+    if (!e || !e[0]) return 1;
+    const int num_kb = K / BK;
+    if (e[0] != 'a') return max(1, min(atoi(e), num_kb));
+    const int cl = cluster_mode() == 2 ? 2 : 1;
+    const int m_tiles = (M + BM - 1) / BM, n_tiles = (N + BN - 1) / BN;
+    const int tiles = ((m_tiles + cl - 1) / cl) * n_tiles, units = kNumSMs / cl;
+    int ks = 1;
+    while ((ks + 1) * tiles <= units && num_kb / (ks + 1) >= 6) ++ks;
+    return ks;
+}
+
 int gemm_a_box_rows() { return BM; }
 int gemm_b_box_rows() { return BN / 2; }   // W is fetched as two 128-row halves (one per CTA of a pair)
 
@@ -635,7 +665,8 @@ int gemm_bf16_launch(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N,
                      const float* row_stats, const float* colsum) {
     if (M <= 0 || N <= 0 || K <= 0 || (K % BK) || (N % 32)) return CLIPPPO_ERR_BAD_SHAPE;
     if (!out) return CLIPPPO_ERR_NULL;
-    GemmArgs g{M, N, K, bias, pos, tokens, out, ldo, reinterpret_cast<const float2*>(row_stats), colsum};
+    GemmArgs g{M, N, K, bias, pos, tokens, out, ldo, reinterpret_cast<const float2*>(row_stats), colsum, 1};
+    if (epilogue == CLIPPPO_EPI_RESID_BF16) g.ksplit = pick_ksplit(M, N, K);
     const bool bf16_out = epilogue == CLIPPPO_EPI_BIAS_BF16 || epilogue == CLIPPPO_EPI_BIAS_GELU_BF16 || is_bf16_tma(epilogue);
     if ((reinterpret_cast<uintptr_t>(out) & 15) || ((ldo * (bf16_out ? 2 : 4)) & 15)) return CLIPPPO_ERR_ALIGN;
     if (is_bf16_tma(epilogue)) {
@@ -719,6 +750,6 @@ extern "C" int clipppo_gemm_bf16_probe(const void* a_bf16, const void* w_bf16, i
     if (st) return st;
     st = make_bf16_kmajor_tmap(&tb, w_bf16, N, K, K, gemm_b_box_rows());
     if (st) return st;
-    GemmArgs g{M, N, K, bias, nullptr, 0, out, ldo, nullptr, nullptr};
+    GemmArgs g{M, N, K, bias, nullptr, 0, out, ldo, nullptr, nullptr, 1};
     return gemm_probe_launch(ta, tb, g, epilogue, dbg, as_stream(stream));
 }
