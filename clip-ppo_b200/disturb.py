@@ -74,7 +74,7 @@ def fused_disturb(x: torch.Tensor, *, stages: int, noise: Optional[torch.Tensor]
     k = len(taps) if (stages & N.STAGE_BLUR) else 0
     taps_arr = (C.c_float * max(k, 1))(*(taps if k else (1.0,)))
     sh, sw, ph, pw = window
-    with torch.cuda.device(x.device):
+    with N.device_ctx(x.device):
         st = N.lib().clipppo_disturb_f32(
             x.data_ptr(), N.strides4(x), nptr, nstr, out.data_ptr(), B, Cc, H, W, stages,
             float(noise_sigma), float(contrast), taps_arr, k, int(sh), int(sw), int(ph), int(pw),
@@ -108,7 +108,7 @@ def fused_disturb_nhwc_u8(obs: torch.Tensor, *, stages: int, noise: Optional[tor
     k = len(taps) if (stages & N.STAGE_BLUR) else 0
     taps_arr = (C.c_float * max(k, 1))(*(taps if k else (1.0,)))
     sh, sw, ph, pw = window
-    with torch.cuda.device(obs.device):
+    with N.device_ctx(obs.device):
         st = N.lib().clipppo_disturb_nhwc_u8(
             obs.data_ptr(), int(obs.dtype == torch.float32), nptr, nstr, out.data_ptr(), B, H, W, Cc, stages,
             float(noise_sigma), float(contrast), taps_arr, k, int(sh), int(sw), int(ph), int(pw),

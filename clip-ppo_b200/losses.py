@@ -31,7 +31,7 @@ class _CosineLoss(torch.autograd.Function):
         rows, dim = zc.shape
         loss = torch.empty((), dtype=torch.float32, device=zc.device)
         stats = torch.empty((rows, 3), dtype=torch.float32, device=zc.device)
-        with torch.cuda.device(zc.device):
+        with N.device_ctx(zc.device):
             N.check(N.lib().clipppo_cosine_loss_fwd(zc.data_ptr(), cc.data_ptr(), rows, dim, loss.data_ptr(),
                                                     stats.data_ptr(), _stream(zc)), "clipppo_cosine_loss_fwd")
         ctx.save_for_backward(zc, cc, stats)
@@ -46,7 +46,7 @@ class _CosineLoss(torch.autograd.Function):
         gz = torch.empty_like(zc) if need_z else None
         gc = torch.empty_like(cc) if need_c else None
         g = grad_out.detach().to(torch.float32).contiguous()
-        with torch.cuda.device(zc.device):
+        with N.device_ctx(zc.device):
             N.check(N.lib().clipppo_cosine_loss_bwd(zc.data_ptr(), cc.data_ptr(), stats.data_ptr(), g.data_ptr(),
                                                     rows, dim, gz.data_ptr() if need_z else None,
                                                     gc.data_ptr() if need_c else None, _stream(zc)),
@@ -77,7 +77,7 @@ def gae(rewards: torch.Tensor, values: torch.Tensor, dones: torch.Tensor, next_v
     if nv.numel() != E or nd.numel() != E or v.shape != r.shape or d.shape != r.shape:
         raise ValueError("gae: shape mismatch")
     adv, ret = torch.empty_like(r), torch.empty_like(r)
-    with torch.cuda.device(r.device):
+    with N.device_ctx(r.device):
         N.check(N.lib().clipppo_gae_f32(r.data_ptr(), v.data_ptr(), d.data_ptr(), nv.data_ptr(), nd.data_ptr(), T, E,
                                         float(gamma), float(gae_lambda), adv.data_ptr(), ret.data_ptr(), _stream(r)),
                 "clipppo_gae_f32")
@@ -99,7 +99,7 @@ class _PpoLoss(torch.autograd.Function):
         need = any(ctx.needs_input_grad[:3]) or (clip_loss is not None and ctx.needs_input_grad[7])
         g = [torch.empty_like(nlp) for _ in range(3)] if need else [None] * 3
         cl = _f32c(clip_loss).reshape(()) if clip_loss is not None else None
-        with torch.cuda.device(nlp.device):
+        with N.device_ctx(nlp.device):
             N.check(N.lib().clipppo_ppo_loss_f32(
                 nlp.data_ptr(), ent.data_ptr(), nv.data_ptr(), olp.data_ptr(), adv.data_ptr(), ret.data_ptr(),
                 ov.data_ptr(), cl.data_ptr() if cl is not None else None, n, float(clip_coef), float(ent_coef),

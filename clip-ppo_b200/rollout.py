@@ -42,6 +42,41 @@ def disturb_atari_stack(disturber, next_obs: torch.Tensor) -> torch.Tensor:
     return torch.cat(frames, dim=1) * 255.0
 
 
+# ---- §8f-4: rollout observation storage (clip_ppo_minigrid.py:346, 467-483) --------------------------
+class ObsStoreU8:
+    """MiniGrid rollout observations kept as uint8 [T,E,H,W,C] instead of the script's fp32 0..255
+    (``obs = torch.zeros((num_steps, num_envs) + obs_shape)``, clip_ppo_minigrid.py:346): the values are
+    integral already (the env renders uint8; the disturbed frames go through ``.byte()``, :388), so the
+    store is lossless at a quarter of the HBM, and the tower's preprocess reads the bytes directly
+    (``CLIPPPO_IMG_U8``, any strides) - no fp32 copy of a minibatch is ever materialised.
+    Atari stacks are NOT integral after ``*255`` (clip_ppo_atari.py:584) and stay fp32."""
+
+    def __init__(self, num_steps: int, num_envs: int, obs_shape: Tuple[int, int, int], device="cuda"):
+        self.data = torch.zeros((num_steps, num_envs) + tuple(obs_shape), dtype=torch.uint8, device=device)
+
+    def __setitem__(self, step: int, next_obs: torch.Tensor) -> None:
+        """``obs[step] = next_obs``; fp32 input must hold integers in 0..255 (raises otherwise)."""
+        if next_obs.dtype != torch.uint8:
+            q = next_obs.to(torch.uint8)
+            if not torch.equal(q.to(next_obs.dtype), next_obs):
+                raise ValueError("ObsStoreU8 holds integral 0..255 observations only")
+            next_obs = q
+        self.data[step] = next_obs
+
+    def flat(self) -> torch.Tensor:
+        """``b_obs = obs.reshape((-1,) + obs_shape)`` (clip_ppo_minigrid.py:453), uint8 [T*E,H,W,C]."""
+        return self.data.reshape((-1,) + tuple(self.data.shape[2:]))
+
+    def clip_images(self, mb_inds: torch.Tensor) -> torch.Tensor:
+        """The ``images=`` argument of generate_clip_embeddings for a minibatch: uint8 [mb,C,H,W] as an
+        NHWC-strided view of the gathered rows (what ``b_obs[mb_inds].permute(0, 3, 1, 2)`` is in the script)."""
+        return self.flat()[mb_inds].permute(0, 3, 1, 2)
+
+    def policy_input(self, mb_inds: torch.Tensor) -> torch.Tensor:
+        """fp32 0..255 [mb,H,W,C] for the PPO encoder (it divides by 255 itself, :262)."""
+        return self.flat()[mb_inds].float()
+
+
 # ---- a17: Atari frame stack -> CLIP embeddings (clip_ppo_atari.py:249-299, 661) --------------------
 def convert_atari_frames_for_clip(obs_batch: torch.Tensor) -> torch.Tensor:
     """[B,4,84,84] gray -> [B,4,3,84,84] by channel repeat (reference :249-269).  Returned as an

@@ -139,6 +139,33 @@ def test_dispatch_variants_against_oracle(native, shape, sev):
     assert (out_v.cpu() - ref).abs().max() <= TOL
 
 
+@pytest.mark.parametrize("B,C", [(8, 3), (64, 3), (40, 1), (150, 3)])
+@pytest.mark.parametrize("sev", ["MODERATE", "SEVERE"])
+def test_env_step_batches_run_as_stripe_clusters(native, B, C, sev):
+    """Env-step call shapes (clip_ppo_minigrid.py:381-388: E x 84 x 84 x 3 NHWC; clip_ppo_atari.py:568-584:
+    [E,1,84,84]): below 148 frames a frame is cut into a cluster of stripes so the grid covers the SMs.  Same
+    chain as the oracle in both layouts; a frame alone agrees with the frame in its batch to the last bit or two
+    (the gray mean's summation order follows the stripe count)."""
+    g = torch.Generator().manual_seed(B * 3 + C)
+    frames = torch.rand(B, 84, 84, C, generator=g)
+    x = frames.permute(0, 3, 1, 2)                                  # NHWC-strided view, like the reference's call site
+    noise = torch.randn(B, 84, 84, C, generator=g).permute(0, 3, 1, 2)
+    cfg = od.SEVERITY_TABLE[sev]
+    ph, pw = od.cutout_patch(84, 84, cfg["cutout"])
+    k = od.blur_kernel_size(cfg["blur_sigma"])
+    k1d = od.gaussian_kernel1d(k, float(torch.tensor(cfg["blur_sigma"], dtype=torch.float32)))
+    idx = torch.linspace(0, B - 1, 5).long()
+    ref = od.disturb(x[idx].contiguous(), noise[idx].contiguous(), cfg["noise_sigma"], 1.21, k1d, 11, 30, ph, pw)
+    w = _wrapper(sev)
+    out_v = w.apply_disturbances(x.cuda(), noise=noise.cuda(), contrast_factor=1.21, cutout_start=(11, 30))
+    out_c = w.apply_disturbances(x.contiguous().cuda(), noise=noise.contiguous().cuda(), contrast_factor=1.21, cutout_start=(11, 30))
+    assert (out_v.cpu()[idx] - ref).abs().max() <= TOL
+    assert (out_c.cpu()[idx] - ref).abs().max() <= TOL
+    big = w.apply_disturbances(x.contiguous().repeat(4, 1, 1, 1).cuda(), noise=noise.contiguous().repeat(4, 1, 1, 1).cuda(),
+                               contrast_factor=1.21, cutout_start=(11, 30))
+    assert (big[:B] - out_c).abs().max().item() <= 1e-6
+
+
 def test_wide_blur_kernels_use_the_general_kernel(native):
     """Custom sigma: k = 9 .. 15 taps are outside the fast path's register ring."""
     from shared.disturbances_gpu import DisturbanceWrapperGPU

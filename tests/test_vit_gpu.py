@@ -323,3 +323,27 @@ def test_frozen_features_and_encode_image(native):
     assert cos.min().item() >= 0.999
     assert all(not p.requires_grad for p in model.parameters())
     assert "conv1.weight" in model.visual.state_dict()
+
+
+def test_uint8_obs_store_matches_fp32_rollout_storage(native):
+    """§8f-4: MiniGrid observations stored as uint8 give bitwise the embeddings of the script's fp32 0..255 store."""
+    import shared.clip_ppo_utils as U
+    from clip_ppo_b200 import rollout
+    model = U.load_clip_model("ViT-B/32", "cuda")
+    T, E = 4, 6
+    gen = torch.Generator().manual_seed(5)
+    frames = torch.randint(0, 256, (T, E, 84, 84, 3), generator=gen, dtype=torch.uint8).cuda()
+    obs_f32 = torch.zeros((T, E, 84, 84, 3), device="cuda")                      # clip_ppo_minigrid.py:346
+    store = rollout.ObsStoreU8(T, E, (84, 84, 3))
+    for t in range(T):
+        obs_f32[t] = frames[t].float()
+        store[t] = frames[t].float() if t % 2 else frames[t]                       # fp32-valued and uint8 writes
+    assert store.data.element_size() * 4 == obs_f32.element_size()
+    mb = torch.tensor([0, 5, 7, 13, 23], device="cuda")
+    ref = U.generate_clip_embeddings(U.AblationMode.NONE, model, "image", len(mb), "cuda",
+                                     images=obs_f32.reshape(-1, 84, 84, 3)[mb].permute(0, 3, 1, 2))
+    got = U.generate_clip_embeddings(U.AblationMode.NONE, model, "image", len(mb), "cuda", images=store.clip_images(mb))
+    assert torch.equal(ref, got)
+    assert torch.equal(store.policy_input(mb), obs_f32.reshape(-1, 84, 84, 3)[mb])
+    with pytest.raises(ValueError):
+        store[0] = torch.full((E, 84, 84, 3), 0.5, device="cuda")
