@@ -28,7 +28,9 @@ SYMBOLS = (
     "clipppo_disturb_f32", "clipppo_disturb_nhwc_u8",
     "clipppo_cosine_loss_fwd", "clipppo_cosine_loss_bwd", "clipppo_gae_f32", "clipppo_ppo_loss_f32",
     "clipppo_vit_create", "clipppo_vit_destroy", "clipppo_vit_workspace_bytes", "clipppo_vit_encode",
+    "clipppo_text_create", "clipppo_text_destroy", "clipppo_text_workspace_bytes", "clipppo_text_encode",
     "clipppo_preprocess_bf16", "clipppo_layernorm_bf16", "clipppo_gemm_bf16", "clipppo_gemm_bf16_fused", "clipppo_gemm_bf16_probe", "clipppo_rowstats_bf16", "clipppo_attention_bf16",
+    "clipppo_attention_causal_bf16",
 )
 
 
@@ -48,6 +50,15 @@ class VitLayer(C.Structure):          # fp32 device pointers, openai/CLIP state-
 class VitWeights(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("conv1", "class_embedding", "positional_embedding", "ln_pre_g", "ln_pre_b",
                                           "ln_post_g", "ln_post_b", "proj")] + [("layers_host", C.POINTER(VitLayer))]
+
+
+class TextConfig(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("width", "layers", "heads", "context", "vocab", "out_dim")]
+
+
+class TextWeights(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("token_embedding", "positional_embedding", "ln_final_g", "ln_final_b",
+                                          "text_projection")] + [("layers_host", C.POINTER(VitLayer))]
 
 
 _lib = None
@@ -88,6 +99,11 @@ def lib() -> C.CDLL:
     L.clipppo_rowstats_bf16.argtypes = [vp, i, i, C.c_int64, vp, vp]
     L.clipppo_gemm_bf16_probe.argtypes = [vp, vp, i, i, i, i, vp, vp, C.c_int64, i, vp]
     L.clipppo_attention_bf16.argtypes = [vp, i, i, i, i, vp, vp]
+    L.clipppo_attention_causal_bf16.argtypes = [vp, i, i, i, i, vp, vp]
+    L.clipppo_text_create.argtypes = [C.POINTER(vp), C.POINTER(TextConfig), C.POINTER(TextWeights)]
+    L.clipppo_text_destroy.argtypes = [vp]
+    L.clipppo_text_workspace_bytes.argtypes = [vp, i, C.POINTER(sz)]
+    L.clipppo_text_encode.argtypes = [vp, vp, i, i, vp, vp, sz, vp]
     for name in SYMBOLS:
         fn = getattr(L, name)
         if name not in ("clipppo_strerror",):

@@ -219,7 +219,10 @@ __host__ __device__ constexpr size_t attg_smem_bytes(int T) {
     return (static_cast<size_t>(2) * attg_kv_rows(T) + ATTG_WARPS * ATTG_QROWS) * PITCH * 2;
 }
 
-template <int HEADS>
+// CAUSAL (the text tower, [clip] build_attention_mask): query t sees keys 0 .. t.  Key blocks that start
+// beyond a query tile's last row are skipped; the block on the diagonal is masked element-wise (its first
+// key is <= every query row of the tile, so no row of a block is ever fully masked).
+template <int HEADS, bool CAUSAL>
 __global__ void __launch_bounds__(ATTG_THREADS, 2)
 attention_general_kernel(const __nv_bfloat16* __restrict__ qkv, int T, __nv_bfloat16* __restrict__ out) {
     extern __shared__ __align__(16) __nv_bfloat16 att_smem[];
@@ -274,7 +277,9 @@ attention_general_kernel(const __nv_bfloat16* __restrict__ qkv, int T, __nv_bflo
 #pragma unroll
         for (int nt = 0; nt < 8; ++nt) { o[nt][0] = o[nt][1] = o[nt][2] = o[nt][3] = 0.f; }
         float mrun0 = -INFINITY, mrun1 = -INFINITY, lrun0 = 0.f, lrun1 = 0.f;      // rows lane/4 and lane/4 + 8
-        const int nkb = n_full + (k_tail > 8 ? 1 : 0);            // blocks run at full width (a wide tail is masked)
+        int nkb = n_full + (k_tail > 8 ? 1 : 0);                  // blocks run at full width (a wide tail is masked)
+        const int q_last = qt * ATTG_QROWS + ATTG_QROWS - 1;      // last query row of my tile
+        if (CAUSAL && nkb > q_last / TP + 1) nkb = q_last / TP + 1;
         for (int kb = 0; kb < nkb; ++kb) {
             const uint32_t kb_k = k_base + kb * TP * PITCH * 2, kb_v = v_base + kb * TP * PITCH * 2;
             float s[8][4];
@@ -292,6 +297,9 @@ attention_general_kernel(const __nv_bfloat16* __restrict__ qkv, int T, __nv_bflo
                 }
             }
             const int kleft = T - kb * TP;                        // valid keys in this block (>= 64 unless it is the tail)
+            // causal: keys of this block visible to rows lane/4 and lane/4 + 8 of my tile (block-relative count)
+            const int vis0 = CAUSAL ? qt * ATTG_QROWS + (lane >> 2) - kb * TP + 1 : TP;
+            const bool diag = CAUSAL && kb * TP + TP - 1 > qt * ATTG_QROWS;
             float mx0 = mrun0, mx1 = mrun1;
 #pragma unroll
             for (int nt = 0; nt < 8; ++nt) {
@@ -299,6 +307,13 @@ attention_general_kernel(const __nv_bfloat16* __restrict__ qkv, int T, __nv_bflo
                     const int n = nt * 8 + 2 * (lane & 3);
                     if (n >= kleft)     { s[nt][0] = -INFINITY; s[nt][2] = -INFINITY; }
                     if (n + 1 >= kleft) { s[nt][1] = -INFINITY; s[nt][3] = -INFINITY; }
+                }
+                if (diag) {
+                    const int n = nt * 8 + 2 * (lane & 3);
+                    if (n >= vis0)         s[nt][0] = -INFINITY;
+                    if (n + 1 >= vis0)     s[nt][1] = -INFINITY;
+                    if (n >= vis0 + 8)     s[nt][2] = -INFINITY;
+                    if (n + 1 >= vis0 + 8) s[nt][3] = -INFINITY;
                 }
                 mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
                 mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
@@ -347,7 +362,7 @@ attention_general_kernel(const __nv_bfloat16* __restrict__ qkv, int T, __nv_bflo
                 }
             }
         }
-        if (k_tail > 0 && k_tail <= 8) {
+        if (k_tail > 0 && k_tail <= 8 && (!CAUSAL || n_full * TP <= qt * ATTG_QROWS)) {
             // narrow tail: one 8-key tile (keys n_full*64 .. +7, those beyond T masked), one 16-key PV step
             const uint32_t kb_k = k_base + n_full * TP * PITCH * 2, kb_v = v_base + n_full * TP * PITCH * 2;
             float s0[4] = {0.f, 0.f, 0.f, 0.f};
@@ -361,6 +376,13 @@ attention_general_kernel(const __nv_bfloat16* __restrict__ qkv, int T, __nv_bflo
             const int n = 2 * (lane & 3);
             if (n >= k_tail)     { s0[0] = -INFINITY; s0[2] = -INFINITY; }
             if (n + 1 >= k_tail) { s0[1] = -INFINITY; s0[3] = -INFINITY; }
+            if (CAUSAL) {
+                const int vis0 = qt * ATTG_QROWS + (lane >> 2) - n_full * TP + 1;
+                if (n >= vis0)         s0[0] = -INFINITY;
+                if (n + 1 >= vis0)     s0[1] = -INFINITY;
+                if (n >= vis0 + 8)     s0[2] = -INFINITY;
+                if (n + 1 >= vis0 + 8) s0[3] = -INFINITY;
+            }
             float mx0 = fmaxf(mrun0, fmaxf(s0[0], s0[1])), mx1 = fmaxf(mrun1, fmaxf(s0[2], s0[3]));
             mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
             mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
@@ -415,38 +437,42 @@ attention_general_kernel(const __nv_bfloat16* __restrict__ qkv, int T, __nv_bflo
 
 }  // namespace
 
+template <int HEADS, bool CAUSAL>
+static int launch_general(const __nv_bfloat16* q, int n_images, int tokens, __nv_bfloat16* o, size_t smem, cudaStream_t stream) {
+    static bool configured = false;
+    if (!configured) {
+        CLIPPPO_CUDA_TRY(cudaFuncSetAttribute(attention_general_kernel<HEADS, CAUSAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
+        configured = true;
+    }
+    CLIPPPO_CUDA_TRY(launch_pdl(attention_general_kernel<HEADS, CAUSAL>, static_cast<unsigned>(n_images) * HEADS, ATTG_THREADS, smem,
+                                stream, 1, q, tokens, o));
+    return CLIPPPO_OK;
+}
+
 int attention_launch(const void* qkv_bf16, int n_images, int tokens, int heads, int head_dim, void* out_bf16,
-                     cudaStream_t stream) {
+                     cudaStream_t stream, bool causal) {
     if (!qkv_bf16 || !out_bf16) return CLIPPPO_ERR_NULL;
     if (n_images <= 0 || tokens <= 0 || heads <= 0) return CLIPPPO_ERR_BAD_SHAPE;
     if (head_dim != DH) return CLIPPPO_ERR_UNSUPPORTED;
     if ((reinterpret_cast<uintptr_t>(qkv_bf16) % 16) || (reinterpret_cast<uintptr_t>(out_bf16) % 16)) return CLIPPPO_ERR_ALIGN;
-    if (tokens > TP) {                               // ViT-L/14 (T = 257): one CTA per (image, head), K / V resident
+    if (tokens > TP || causal) {                     // ViT-L/14 (T = 257), text tower (T = 77, causal): one CTA per (sequence, head), K / V resident
         const size_t smem = attg_smem_bytes(tokens);
         if (smem > 113 * 1024) return CLIPPPO_ERR_UNSUPPORTED;      // 2 CTAs / SM; T <= 352
-        const long long ctas = static_cast<long long>(n_images) * heads;
-        if (ctas > 0x7fffffffLL) return CLIPPPO_ERR_BAD_SHAPE;
+        if (static_cast<long long>(n_images) * heads > 0x7fffffffLL) return CLIPPPO_ERR_BAD_SHAPE;
         const __nv_bfloat16* q = static_cast<const __nv_bfloat16*>(qkv_bf16);
         __nv_bfloat16* o = static_cast<__nv_bfloat16*>(out_bf16);
-        if (heads == 16) {
-            static bool configured = false;
-            if (!configured) {
-                CLIPPPO_CUDA_TRY(cudaFuncSetAttribute(attention_general_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
-                configured = true;
-            }
-            CLIPPPO_CUDA_TRY(launch_pdl(attention_general_kernel<16>, static_cast<unsigned>(ctas), ATTG_THREADS, smem, stream, 1, q, tokens, o));
-        } else if (heads == 12) {
-            static bool configured = false;
-            if (!configured) {
-                CLIPPPO_CUDA_TRY(cudaFuncSetAttribute(attention_general_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
-                configured = true;
-            }
-            CLIPPPO_CUDA_TRY(launch_pdl(attention_general_kernel<12>, static_cast<unsigned>(ctas), ATTG_THREADS, smem, stream, 1, q, tokens, o));
+        int st = CLIPPPO_ERR_UNSUPPORTED;            // head counts of the CLIP towers: 8 (text), 12 (B/32, B/16), 16 (L/14)
+        if (causal) {
+            if (heads == 8) st = launch_general<8, true>(q, n_images, tokens, o, smem, stream);
+            else if (heads == 12) st = launch_general<12, true>(q, n_images, tokens, o, smem, stream);
+            else if (heads == 16) st = launch_general<16, true>(q, n_images, tokens, o, smem, stream);
         } else {
-            return CLIPPPO_ERR_UNSUPPORTED;
+            if (heads == 8) st = launch_general<8, false>(q, n_images, tokens, o, smem, stream);
+            else if (heads == 12) st = launch_general<12, false>(q, n_images, tokens, o, smem, stream);
+            else if (heads == 16) st = launch_general<16, false>(q, n_images, tokens, o, smem, stream);
         }
-        prof_count_launch();
-        return CLIPPPO_OK;
+        if (st == CLIPPPO_OK) prof_count_launch();
+        return st;
     }
     const long long items = static_cast<long long>(n_images) * heads;
     if (items > 0x7fffffffLL) return CLIPPPO_ERR_BAD_SHAPE;
@@ -478,5 +504,10 @@ int attention_launch(const void* qkv_bf16, int n_images, int tokens, int heads, 
 
 extern "C" int clipppo_attention_bf16(const void* qkv_bf16, int n_images, int tokens, int heads, int head_dim,
                                       void* out_bf16, clipppo_stream_t stream) {
-    return clipppo::attention_launch(qkv_bf16, n_images, tokens, heads, head_dim, out_bf16, clipppo::as_stream(stream));
+    return clipppo::attention_launch(qkv_bf16, n_images, tokens, heads, head_dim, out_bf16, clipppo::as_stream(stream), false);
+}
+
+extern "C" int clipppo_attention_causal_bf16(const void* qkv_bf16, int n_seqs, int tokens, int heads, int head_dim,
+                                             void* out_bf16, clipppo_stream_t stream) {
+    return clipppo::attention_launch(qkv_bf16, n_seqs, tokens, heads, head_dim, out_bf16, clipppo::as_stream(stream), true);
 }

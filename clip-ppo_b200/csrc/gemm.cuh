@@ -27,6 +27,6 @@ int layernorm_bf16in_launch(const void* x_bf16, const float* gamma, const float*
                             long long row_stride, void* y_bf16, cudaStream_t stream);
 int rowstats_launch(const void* x_bf16, int rows, int width, long long row_stride, float* stats, cudaStream_t stream);
 int attention_launch(const void* qkv_bf16, int n_images, int tokens, int heads, int head_dim, void* out_bf16,
-                     cudaStream_t stream);
+                     cudaStream_t stream, bool causal = false);
 
 }  // namespace clipppo

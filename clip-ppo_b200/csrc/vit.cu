@@ -13,6 +13,7 @@
 // Accumulation is fp32 everywhere; patch embedding + ln_pre run in fp32.  Images are processed in
 // chunks so the activation workspace stays bounded whatever N is; buffers that are never live
 // together (im2col patches / QKV / MLP hidden) share one allocation.
+#include <limits.h>
 #include <stdlib.h>
 
 #include <new>
@@ -21,20 +22,34 @@
 #include "common.cuh"
 #include "gemm.cuh"
 
+// one residual block's repacked weights ([clip] ResidualAttentionBlock; the same in both towers)
+struct clipppo_tower_layer {
+    const __nv_bfloat16 *w_qkv, *w_out, *w_fc, *w_proj;     // w_qkv / w_fc carry ln_1 / ln_2 gamma
+    const float *b_qkv, *s_qkv, *b_out, *b_fc, *s_fc, *b_proj;
+    CUtensorMap tm_qkv, tm_out, tm_fc, tm_proj;
+};
+
 struct clipppo_vit_s {
     clipppo_vit_config cfg;
     int tokens, grid, kpatch;
     // handle-owned device arena with the repacked frozen weights
     void* arena = nullptr;
-    struct Layer {
-        const __nv_bfloat16 *w_qkv, *w_out, *w_fc, *w_proj;     // w_qkv / w_fc carry ln_1 / ln_2 gamma
-        const float *b_qkv, *s_qkv, *b_out, *b_fc, *s_fc, *b_proj;
-        CUtensorMap tm_qkv, tm_out, tm_fc, tm_proj;
-    };
+    typedef clipppo_tower_layer Layer;
     std::vector<Layer> layers;
     const __nv_bfloat16 *w_patch, *w_head;
     const float *cls_pos0, *pos, *ln_pre_g, *ln_pre_b, *ln_post_g, *ln_post_b;
     CUtensorMap tm_patch, tm_head;
+};
+
+// Frozen CLIP text tower ([clip] CLIP.encode_text): token + positional embedding, the same residual blocks
+// with a causal attention mask, ln_final on the EOT row, text_projection.
+struct clipppo_text_s {
+    clipppo_text_config cfg;
+    void* arena = nullptr;
+    std::vector<clipppo_tower_layer> layers;
+    const float *tok_emb, *pos, *ln_final_g, *ln_final_b;
+    const __nv_bfloat16* w_head;
+    CUtensorMap tm_head;
 };
 
 namespace clipppo {
@@ -139,15 +154,116 @@ __global__ void l2norm_rows_kernel(float* __restrict__ out, int rows, int dim) {
 
 #define VIT_TRY(expr) do { int st__ = (expr); if (st__ != CLIPPPO_OK) return st__; } while (0)
 
+// L x [ x += out_proj(attn(ln_1(x)));  x += c_proj(QuickGELU(c_fc(ln_2(x)))) ] on the bf16 residual stream X [rows, D]
+int run_blocks(const std::vector<clipppo_tower_layer>& layers, int n, int T, int D, int heads, bool causal,
+               __nv_bfloat16* X, float* stats, __nv_bfloat16* Y, __nv_bfloat16* H, cudaStream_t stream) {
+    const int rows = n * T;
+    CUtensorMap tmX, tmY, tmH;
+    VIT_TRY(make_bf16_kmajor_tmap(&tmX, X, rows, D, D, gemm_a_box_rows()));
+    VIT_TRY(make_bf16_kmajor_tmap(&tmY, Y, rows, D, D, gemm_a_box_rows()));
+    VIT_TRY(make_bf16_kmajor_tmap(&tmH, H, rows, 4 * D, 4 * D, gemm_a_box_rows()));
+    for (const clipppo_tower_layer& w : layers) {
+        // ln_1 lives in the QKV GEMM's epilogue
+        VIT_TRY(rowstats_launch(X, rows, D, D, stats, stream));
+        VIT_TRY(gemm_bf16_launch(tmX, w.tm_qkv, rows, 3 * D, D, CLIPPPO_EPI_ROWAFFINE_BF16, w.b_qkv, nullptr, 0,
+                                 H, 3 * D, stream, stats, w.s_qkv));
+        VIT_TRY(attention_launch(H, n, T, heads, D / heads, Y, stream, causal));
+        VIT_TRY(gemm_bf16_launch(tmY, w.tm_out, rows, D, D, CLIPPPO_EPI_RESID_BF16, w.b_out, nullptr, 0, X, D, stream));
+        VIT_TRY(rowstats_launch(X, rows, D, D, stats, stream));
+        VIT_TRY(gemm_bf16_launch(tmX, w.tm_fc, rows, 4 * D, D, CLIPPPO_EPI_ROWAFFINE_GELU_BF16, w.b_fc, nullptr, 0,
+                                 H, 4 * D, stream, stats, w.s_fc));
+        VIT_TRY(gemm_bf16_launch(tmH, w.tm_proj, rows, D, 4 * D, CLIPPPO_EPI_RESID_BF16, w.b_proj, nullptr, 0, X, D, stream));
+    }
+    return CLIPPPO_OK;
+}
+
+// ---- text tower front / back end -------------------------------------------------------------
+// X[n*T + t, :] = bf16(token_embedding[tokens[n, t]] + positional_embedding[t]); one warp per row, ids clamped to the table
+__global__ void __launch_bounds__(256)
+text_embed_kernel(const int* __restrict__ tokens, const float* __restrict__ emb, const float* __restrict__ pos,
+                  __nv_bfloat16* __restrict__ X, int rows, int T, int D, int vocab) {
+    const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const int t = row % T;
+    int id = __ldg(tokens + row);
+    id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
+    const float4* e = reinterpret_cast<const float4*>(emb + static_cast<size_t>(id) * D);
+    const float4* p = reinterpret_cast<const float4*>(pos + static_cast<size_t>(t) * D);
+    uint2* x = reinterpret_cast<uint2*>(X + static_cast<size_t>(row) * D);
+    for (int i = lane; i < D / 4; i += 32) {
+        const float4 a = __ldg(e + i), b = __ldg(p + i);
+        __nv_bfloat162 lo = __floats2bfloat162_rn(a.x + b.x, a.y + b.y), hi = __floats2bfloat162_rn(a.z + b.z, a.w + b.w);
+        x[i] = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+    }
+}
+// Xe[n, :] = X[n*T + argmax_t tokens[n, t], :]  (first maximum, like torch.argmax; the EOT token has the largest id)
+__global__ void __launch_bounds__(256)
+text_gather_eot_kernel(const int* __restrict__ tokens, const __nv_bfloat16* __restrict__ X, __nv_bfloat16* __restrict__ Xe,
+                       int n, int T, int D) {
+    const int seq = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (seq >= n) return;
+    int best = INT_MIN, at = 0;
+    for (int t = lane; t < T; t += 32) {
+        const int v = __ldg(tokens + static_cast<size_t>(seq) * T + t);
+        if (v > best) { best = v; at = t; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const int ob = __shfl_xor_sync(0xffffffffu, best, o), oa = __shfl_xor_sync(0xffffffffu, at, o);
+        if (ob > best || (ob == best && oa < at)) { best = ob; at = oa; }
+    }
+    const uint4* src = reinterpret_cast<const uint4*>(X + (static_cast<size_t>(seq) * T + at) * D);
+    uint4* dst = reinterpret_cast<uint4*>(Xe + static_cast<size_t>(seq) * D);
+    for (int i = lane; i < D / 8; i += 32) dst[i] = src[i];
+}
+
+struct TextWorkspace {
+    __nv_bfloat16 *X, *Y, *H, *Xe, *Ycls;
+    float* stats;
+    size_t bytes;
+};
+
+TextWorkspace carve_text(const clipppo_text_s* h, int n, void* base) {
+    const size_t T = h->cfg.context, D = h->cfg.width, rows = static_cast<size_t>(n) * T;
+    TextWorkspace ws;
+    size_t off = 0;
+    uint8_t* b = static_cast<uint8_t*>(base);
+    ws.X = reinterpret_cast<__nv_bfloat16*>(b + off);    off += align_up(rows * D * 2, 1024);
+    ws.stats = reinterpret_cast<float*>(b + off);        off += align_up(rows * 2 * 4, 1024);
+    ws.Y = reinterpret_cast<__nv_bfloat16*>(b + off);    off += align_up(rows * D * 2, 1024);
+    ws.H = reinterpret_cast<__nv_bfloat16*>(b + off);    off += align_up(rows * 4 * D * 2, 1024);
+    ws.Xe = reinterpret_cast<__nv_bfloat16*>(b + off);   off += align_up(static_cast<size_t>(n) * D * 2, 1024);
+    ws.Ycls = reinterpret_cast<__nv_bfloat16*>(b + off); off += align_up(static_cast<size_t>(n) * D * 2, 1024);
+    ws.bytes = off;
+    return ws;
+}
+
+int encode_text_chunk(const clipppo_text_s* h, const int* tokens, int n, int flags, float* out, const TextWorkspace& ws,
+                      cudaStream_t stream) {
+    const int D = h->cfg.width, T = h->cfg.context, O = h->cfg.out_dim, rows = n * T;
+    text_embed_kernel<<<(rows + 7) / 8, 256, 0, stream>>>(tokens, h->tok_emb, h->pos, ws.X, rows, T, D, h->cfg.vocab);
+    CLIPPPO_CHECK_LAUNCH();
+    VIT_TRY(run_blocks(h->layers, n, T, D, h->cfg.heads, true, ws.X, ws.stats, ws.Y, ws.H, stream));
+    // ln_final is row-wise, so normalising only the EOT rows equals normalising everything and selecting them
+    text_gather_eot_kernel<<<(n + 7) / 8, 256, 0, stream>>>(tokens, ws.X, ws.Xe, n, T, D);
+    CLIPPPO_CHECK_LAUNCH();
+    VIT_TRY(layernorm_bf16in_launch(ws.Xe, h->ln_final_g, h->ln_final_b, n, D, D, ws.Ycls, stream));
+    CUtensorMap tmC;
+    VIT_TRY(make_bf16_kmajor_tmap(&tmC, ws.Ycls, n, D, D, gemm_a_box_rows()));
+    VIT_TRY(gemm_bf16_launch(tmC, h->tm_head, n, O, D, CLIPPPO_EPI_F32, nullptr, nullptr, 0, out, O, stream));
+    if (flags & CLIPPPO_VIT_L2NORM) {
+        l2norm_rows_kernel<<<(n + 7) / 8, 256, 0, stream>>>(out, n, O);
+        CLIPPPO_CHECK_LAUNCH();
+    }
+    return CLIPPPO_OK;
+}
+
 int encode_chunk(const clipppo_vit_s* h, const void* images, int img_dtype, const long long strides[4], int n, int C,
                  int ih, int iw, float pre_scale, int flags, float* out, const Workspace& ws, cudaStream_t stream) {
-    const int D = h->cfg.width, T = h->tokens, G = h->grid, O = h->cfg.out_dim, L = h->cfg.layers;
+    const int D = h->cfg.width, T = h->tokens, G = h->grid, O = h->cfg.out_dim;
     const int rows = n * T, prow = n * G * G;
-    CUtensorMap tmX, tmY, tmH, tmP, tmC;
+    CUtensorMap tmP, tmC;
     VIT_TRY(make_bf16_kmajor_tmap(&tmP, ws.H, prow, h->kpatch, h->kpatch, gemm_a_box_rows()));
-    VIT_TRY(make_bf16_kmajor_tmap(&tmX, ws.X, rows, D, D, gemm_a_box_rows()));
-    VIT_TRY(make_bf16_kmajor_tmap(&tmY, ws.Y, rows, D, D, gemm_a_box_rows()));
-    VIT_TRY(make_bf16_kmajor_tmap(&tmH, ws.H, rows, 4 * D, 4 * D, gemm_a_box_rows()));
     VIT_TRY(make_bf16_kmajor_tmap(&tmC, ws.Ycls, n, D, D, gemm_a_box_rows()));
 
     VIT_TRY(preprocess_launch(images, img_dtype, strides, n, C, ih, iw, pre_scale,
@@ -158,27 +274,68 @@ int encode_chunk(const clipppo_vit_s* h, const void* images, int img_dtype, cons
     VIT_TRY(gemm_bf16_launch(tmP, h->tm_patch, prow, D, h->kpatch, CLIPPPO_EPI_PATCH_F32, nullptr, h->pos, T,
                              ws.X0, D, stream));
     VIT_TRY(layernorm_launch(ws.X0, h->ln_pre_g, h->ln_pre_b, rows, D, D, ws.X, stream));          // ln_pre -> bf16 residual
-    for (int l = 0; l < L; ++l) {
-        const clipppo_vit_s::Layer& w = h->layers[l];
-        // x += out_proj(attn(ln_1(x)))   - ln_1 lives in the QKV GEMM's epilogue
-        VIT_TRY(rowstats_launch(ws.X, rows, D, D, ws.stats, stream));
-        VIT_TRY(gemm_bf16_launch(tmX, w.tm_qkv, rows, 3 * D, D, CLIPPPO_EPI_ROWAFFINE_BF16, w.b_qkv, nullptr, 0,
-                                 ws.H, 3 * D, stream, ws.stats, w.s_qkv));
-        VIT_TRY(attention_launch(ws.H, n, T, h->cfg.heads, D / h->cfg.heads, ws.Y, stream));
-        VIT_TRY(gemm_bf16_launch(tmY, w.tm_out, rows, D, D, CLIPPPO_EPI_RESID_BF16, w.b_out, nullptr, 0,
-                                 ws.X, D, stream));
-        // x += c_proj(QuickGELU(c_fc(ln_2(x))))
-        VIT_TRY(rowstats_launch(ws.X, rows, D, D, ws.stats, stream));
-        VIT_TRY(gemm_bf16_launch(tmX, w.tm_fc, rows, 4 * D, D, CLIPPPO_EPI_ROWAFFINE_GELU_BF16, w.b_fc, nullptr, 0,
-                                 ws.H, 4 * D, stream, ws.stats, w.s_fc));
-        VIT_TRY(gemm_bf16_launch(tmH, w.tm_proj, rows, D, 4 * D, CLIPPPO_EPI_RESID_BF16, w.b_proj, nullptr, 0,
-                                 ws.X, D, stream));
-    }
+    VIT_TRY(run_blocks(h->layers, n, T, D, h->cfg.heads, false, ws.X, ws.stats, ws.Y, ws.H, stream));
     VIT_TRY(layernorm_bf16in_launch(ws.X, h->ln_post_g, h->ln_post_b, n, D, static_cast<long long>(T) * D, ws.Ycls, stream));
     VIT_TRY(gemm_bf16_launch(tmC, h->tm_head, n, O, D, CLIPPPO_EPI_F32, nullptr, nullptr, 0, out, O, stream));
     if (flags & CLIPPPO_VIT_L2NORM) {
         l2norm_rows_kernel<<<(n + 7) / 8, 256, 0, stream>>>(out, n, O);
         CLIPPPO_CHECK_LAUNCH();
+    }
+    return CLIPPPO_OK;
+}
+
+// ---- residual-block weights: arena planning, repacking, TMA descriptors (both towers) --------
+struct LayerOff { size_t qkv, out, fc, proj, vec; };
+
+template <class Take>
+void plan_layers(std::vector<LayerOff>& lo, int D, Take&& take) {
+    const size_t vec_floats = 3 * D + 3 * D + D + 4 * D + 4 * D + D;      // b_qkv s_qkv b_out b_fc s_fc b_proj
+    for (LayerOff& o : lo) {
+        o.qkv = take(static_cast<size_t>(3) * D * D * 2);
+        o.out = take(static_cast<size_t>(D) * D * 2);
+        o.fc = take(static_cast<size_t>(4) * D * D * 2);
+        o.proj = take(static_cast<size_t>(4) * D * D * 2);
+        o.vec = take(vec_floats * 4);
+    }
+}
+
+bool layers_complete(const clipppo_vit_layer* src, int L) {
+    for (int l = 0; l < L; ++l) {
+        const clipppo_vit_layer& lw = src[l];
+        if (!lw.w_qkv || !lw.b_qkv || !lw.w_out || !lw.b_out || !lw.w_fc || !lw.b_fc || !lw.w_proj || !lw.b_proj ||
+            !lw.ln1_g || !lw.ln1_b || !lw.ln2_g || !lw.ln2_b)
+            return false;
+    }
+    return true;
+}
+
+void repack_layers(const clipppo_vit_layer* src, std::vector<clipppo_tower_layer>& dst, const std::vector<LayerOff>& lo,
+                   uint8_t* A, int D, cudaStream_t s0) {
+    auto bf = [&](size_t o) { return reinterpret_cast<__nv_bfloat16*>(A + o); };
+    auto blocks = [](size_t n) { return static_cast<unsigned>((n + 255) / 256); };
+    for (size_t l = 0; l < dst.size(); ++l) {
+        const clipppo_vit_layer& lw = src[l];
+        clipppo_tower_layer& hl = dst[l];
+        float* v = reinterpret_cast<float*>(A + lo[l].vec);
+        float *b_qkv = v, *s_qkv = v + 3 * D, *b_out = v + 6 * D, *b_fc = v + 7 * D, *s_fc = v + 11 * D, *b_proj = v + 15 * D;
+        fold_ln_kernel<<<3 * D, 128, 0, s0>>>(lw.w_qkv, lw.ln1_g, lw.ln1_b, lw.b_qkv, D, bf(lo[l].qkv), s_qkv, b_qkv);
+        fold_ln_kernel<<<4 * D, 128, 0, s0>>>(lw.w_fc, lw.ln2_g, lw.ln2_b, lw.b_fc, D, bf(lo[l].fc), s_fc, b_fc);
+        convert_pad_kernel<<<blocks(static_cast<size_t>(D) * D), 256, 0, s0>>>(lw.w_out, bf(lo[l].out), D, D, D);
+        convert_pad_kernel<<<blocks(static_cast<size_t>(4) * D * D), 256, 0, s0>>>(lw.w_proj, bf(lo[l].proj), D, 4 * D, 4 * D);
+        cudaMemcpyAsync(b_out, lw.b_out, static_cast<size_t>(D) * 4, cudaMemcpyDeviceToDevice, s0);
+        cudaMemcpyAsync(b_proj, lw.b_proj, static_cast<size_t>(D) * 4, cudaMemcpyDeviceToDevice, s0);
+        hl.w_qkv = bf(lo[l].qkv); hl.w_out = bf(lo[l].out); hl.w_fc = bf(lo[l].fc); hl.w_proj = bf(lo[l].proj);
+        hl.b_qkv = b_qkv; hl.s_qkv = s_qkv; hl.b_out = b_out; hl.b_fc = b_fc; hl.s_fc = s_fc; hl.b_proj = b_proj;
+    }
+}
+
+int map_layers(std::vector<clipppo_tower_layer>& layers, int D) {
+    const int nb = gemm_b_box_rows();
+    for (clipppo_tower_layer& hl : layers) {
+        VIT_TRY(make_bf16_kmajor_tmap(&hl.tm_qkv, hl.w_qkv, 3 * D, D, D, nb));
+        VIT_TRY(make_bf16_kmajor_tmap(&hl.tm_out, hl.w_out, D, D, D, nb));
+        VIT_TRY(make_bf16_kmajor_tmap(&hl.tm_fc, hl.w_fc, 4 * D, D, D, nb));
+        VIT_TRY(make_bf16_kmajor_tmap(&hl.tm_proj, hl.w_proj, D, 4 * D, 4 * D, nb));
     }
     return CLIPPPO_OK;
 }
@@ -201,12 +358,7 @@ extern "C" int clipppo_vit_create(clipppo_vit_t* handle, const clipppo_vit_confi
     if (!w.conv1 || !w.class_embedding || !w.positional_embedding || !w.ln_pre_g || !w.ln_pre_b || !w.ln_post_g ||
         !w.ln_post_b || !w.proj)
         return CLIPPPO_ERR_NULL;
-    for (int l = 0; l < L; ++l) {
-        const clipppo_vit_layer& lw = w.layers_host[l];
-        if (!lw.w_qkv || !lw.b_qkv || !lw.w_out || !lw.b_out || !lw.w_fc || !lw.b_fc || !lw.w_proj || !lw.b_proj ||
-            !lw.ln1_g || !lw.ln1_b || !lw.ln2_g || !lw.ln2_b)
-            return CLIPPPO_ERR_NULL;
-    }
+    if (!layers_complete(w.layers_host, L)) return CLIPPPO_ERR_NULL;
     clipppo_vit_s* h = new (std::nothrow) clipppo_vit_s();
     if (!h) return CLIPPPO_ERR_WORKSPACE;
     h->cfg = *cfg;
@@ -222,16 +374,8 @@ extern "C" int clipppo_vit_create(clipppo_vit_t* handle, const clipppo_vit_confi
     const size_t o_patch = take(static_cast<size_t>(D) * h->kpatch * 2), o_head = take(static_cast<size_t>(O) * D * 2);
     const size_t o_cls = take(D * 4), o_pos = take(static_cast<size_t>(T) * D * 4);
     const size_t o_lnv = take(4 * static_cast<size_t>(D) * 4);
-    struct LOff { size_t qkv, out, fc, proj, vec; };
-    std::vector<LOff> lo(L);
-    const size_t vec_floats = 3 * D + 3 * D + D + 4 * D + 4 * D + D;      // b_qkv s_qkv b_out b_fc s_fc b_proj
-    for (int l = 0; l < L; ++l) {
-        lo[l].qkv = take(static_cast<size_t>(3) * D * D * 2);
-        lo[l].out = take(static_cast<size_t>(D) * D * 2);
-        lo[l].fc = take(static_cast<size_t>(4) * D * D * 2);
-        lo[l].proj = take(static_cast<size_t>(4) * D * D * 2);
-        lo[l].vec = take(vec_floats * 4);
-    }
+    std::vector<LayerOff> lo(L);
+    plan_layers(lo, D, take);
     int st = record_cuda(cudaMalloc(&h->arena, off));
     if (st) { delete h; return st; }
     uint8_t* A = static_cast<uint8_t*>(h->arena);
@@ -250,33 +394,14 @@ extern "C" int clipppo_vit_create(clipppo_vit_t* handle, const clipppo_vit_confi
     h->w_patch = bf(o_patch); h->w_head = bf(o_head);
     h->cls_pos0 = fp(o_cls); h->pos = fp(o_pos);
     h->ln_pre_g = fp(o_lnv); h->ln_pre_b = fp(o_lnv) + D; h->ln_post_g = fp(o_lnv) + 2 * D; h->ln_post_b = fp(o_lnv) + 3 * D;
-    for (int l = 0; l < L; ++l) {
-        const clipppo_vit_layer& lw = w.layers_host[l];
-        clipppo_vit_s::Layer& hl = h->layers[l];
-        float* v = fp(lo[l].vec);
-        float *b_qkv = v, *s_qkv = v + 3 * D, *b_out = v + 6 * D, *b_fc = v + 7 * D, *s_fc = v + 11 * D, *b_proj = v + 15 * D;
-        fold_ln_kernel<<<3 * D, 128, 0, s0>>>(lw.w_qkv, lw.ln1_g, lw.ln1_b, lw.b_qkv, D, bf(lo[l].qkv), s_qkv, b_qkv);
-        fold_ln_kernel<<<4 * D, 128, 0, s0>>>(lw.w_fc, lw.ln2_g, lw.ln2_b, lw.b_fc, D, bf(lo[l].fc), s_fc, b_fc);
-        convert_pad_kernel<<<blocks(static_cast<size_t>(D) * D), 256, 0, s0>>>(lw.w_out, bf(lo[l].out), D, D, D);
-        convert_pad_kernel<<<blocks(static_cast<size_t>(4) * D * D), 256, 0, s0>>>(lw.w_proj, bf(lo[l].proj), D, 4 * D, 4 * D);
-        copyf(b_out, lw.b_out, D);
-        copyf(b_proj, lw.b_proj, D);
-        hl.w_qkv = bf(lo[l].qkv); hl.w_out = bf(lo[l].out); hl.w_fc = bf(lo[l].fc); hl.w_proj = bf(lo[l].proj);
-        hl.b_qkv = b_qkv; hl.s_qkv = s_qkv; hl.b_out = b_out; hl.b_fc = b_fc; hl.s_fc = s_fc; hl.b_proj = b_proj;
-    }
+    repack_layers(w.layers_host, h->layers, lo, A, D, s0);
     st = record_cuda(cudaGetLastError());
     if (!st) st = record_cuda(cudaStreamSynchronize(s0));      // the caller may free its fp32 weights on return
 
     const int nb = gemm_b_box_rows();
     if (!st) st = make_bf16_kmajor_tmap(&h->tm_patch, h->w_patch, D, h->kpatch, h->kpatch, nb);
     if (!st) st = make_bf16_kmajor_tmap(&h->tm_head, h->w_head, O, D, D, nb);
-    for (int l = 0; l < L && !st; ++l) {
-        clipppo_vit_s::Layer& hl = h->layers[l];
-        st = make_bf16_kmajor_tmap(&hl.tm_qkv, hl.w_qkv, 3 * D, D, D, nb);
-        if (!st) st = make_bf16_kmajor_tmap(&hl.tm_out, hl.w_out, D, D, D, nb);
-        if (!st) st = make_bf16_kmajor_tmap(&hl.tm_fc, hl.w_fc, 4 * D, D, D, nb);
-        if (!st) st = make_bf16_kmajor_tmap(&hl.tm_proj, hl.w_proj, D, 4 * D, 4 * D, nb);
-    }
+    if (!st) st = map_layers(h->layers, D);
     if (st) { cudaFree(h->arena); delete h; return st; }
     *handle = h;
     return CLIPPPO_OK;
@@ -349,6 +474,88 @@ extern "C" int clipppo_vit_encode(clipppo_vit_t handle, const void* images, int 
         const uint8_t* img = static_cast<const uint8_t*>(images) + static_cast<size_t>(n0) * s[0] * esz;
         int st = encode_chunk(handle, img, img_dtype, s, n, C, h, w, pre_scale, flags,
                               out + static_cast<size_t>(n0) * handle->cfg.out_dim, ws, as_stream(stream));
+        if (st) return st;
+    }
+    return CLIPPPO_OK;
+}
+
+// ---- text tower -------------------------------------------------------------------------------
+extern "C" int clipppo_text_create(clipppo_text_t* handle, const clipppo_text_config* cfg,
+                                   const clipppo_text_weights* weights_host) {
+    if (!handle || !cfg || !weights_host || !weights_host->layers_host) return CLIPPPO_ERR_NULL;
+    const int D = cfg->width, O = cfg->out_dim, L = cfg->layers, T = cfg->context, V = cfg->vocab;
+    if (D <= 0 || L <= 0 || cfg->heads <= 0 || T <= 0 || V <= 0 || O <= 0 || D % cfg->heads) return CLIPPPO_ERR_BAD_SHAPE;
+    if (D / cfg->heads != 64 || D % 256 || O % 32) return CLIPPPO_ERR_UNSUPPORTED;
+    const clipppo_text_weights& w = *weights_host;
+    if (!w.token_embedding || !w.positional_embedding || !w.ln_final_g || !w.ln_final_b || !w.text_projection) return CLIPPPO_ERR_NULL;
+    if (!layers_complete(w.layers_host, L)) return CLIPPPO_ERR_NULL;
+    clipppo_text_s* h = new (std::nothrow) clipppo_text_s();
+    if (!h) return CLIPPPO_ERR_WORKSPACE;
+    h->cfg = *cfg;
+    h->layers.resize(L);
+    size_t off = 0;
+    auto take = [&](size_t bytes) { const size_t o = off; off += align_up(bytes, 256); return o; };
+    const size_t o_emb = take(static_cast<size_t>(V) * D * 4), o_pos = take(static_cast<size_t>(T) * D * 4);
+    const size_t o_lnv = take(2 * static_cast<size_t>(D) * 4), o_head = take(static_cast<size_t>(O) * D * 2);
+    std::vector<LayerOff> lo(L);
+    plan_layers(lo, D, take);
+    int st = record_cuda(cudaMalloc(&h->arena, off));
+    if (st) { delete h; return st; }
+    uint8_t* A = static_cast<uint8_t*>(h->arena);
+    auto fp = [&](size_t o) { return reinterpret_cast<float*>(A + o); };
+    cudaStream_t s0 = nullptr;
+    cudaMemcpyAsync(fp(o_emb), w.token_embedding, static_cast<size_t>(V) * D * 4, cudaMemcpyDeviceToDevice, s0);
+    cudaMemcpyAsync(fp(o_pos), w.positional_embedding, static_cast<size_t>(T) * D * 4, cudaMemcpyDeviceToDevice, s0);
+    cudaMemcpyAsync(fp(o_lnv), w.ln_final_g, static_cast<size_t>(D) * 4, cudaMemcpyDeviceToDevice, s0);
+    cudaMemcpyAsync(fp(o_lnv) + D, w.ln_final_b, static_cast<size_t>(D) * 4, cudaMemcpyDeviceToDevice, s0);
+    transpose_convert_kernel<<<static_cast<unsigned>((static_cast<size_t>(D) * O + 255) / 256), 256, 0, s0>>>(
+        w.text_projection, reinterpret_cast<__nv_bfloat16*>(A + o_head), D, O);
+    h->tok_emb = fp(o_emb); h->pos = fp(o_pos); h->ln_final_g = fp(o_lnv); h->ln_final_b = fp(o_lnv) + D;
+    h->w_head = reinterpret_cast<const __nv_bfloat16*>(A + o_head);
+    repack_layers(w.layers_host, h->layers, lo, A, D, s0);
+    st = record_cuda(cudaGetLastError());
+    if (!st) st = record_cuda(cudaStreamSynchronize(s0));      // the caller may free its fp32 weights on return
+    if (!st) st = make_bf16_kmajor_tmap(&h->tm_head, h->w_head, O, D, D, gemm_b_box_rows());
+    if (!st) st = map_layers(h->layers, D);
+    if (st) { cudaFree(h->arena); delete h; return st; }
+    *handle = h;
+    return CLIPPPO_OK;
+}
+
+extern "C" int clipppo_text_destroy(clipppo_text_t handle) {
+    if (handle) {
+        if (handle->arena) cudaFree(handle->arena);
+        delete handle;
+    }
+    return CLIPPPO_OK;
+}
+
+static int text_chunk(int N) {
+    constexpr int kMaxChunkTexts = 4096;        // 315 k token rows: 2.3 GB of workspace at width 512
+    if (N <= kMaxChunkTexts) return N;
+    const int k = (N + kMaxChunkTexts - 1) / kMaxChunkTexts;
+    return (N + k - 1) / k;
+}
+
+extern "C" int clipppo_text_workspace_bytes(clipppo_text_t handle, int n_texts, size_t* bytes) {
+    if (!handle || !bytes) return CLIPPPO_ERR_NULL;
+    if (n_texts <= 0) return CLIPPPO_ERR_BAD_SHAPE;
+    *bytes = carve_text(handle, text_chunk(n_texts), nullptr).bytes;
+    return CLIPPPO_OK;
+}
+
+extern "C" int clipppo_text_encode(clipppo_text_t handle, const int32_t* tokens, int N, int flags, float* out,
+                                   void* workspace, size_t workspace_bytes, clipppo_stream_t stream) {
+    if (!handle || !tokens || !out || !workspace) return CLIPPPO_ERR_NULL;
+    if (N <= 0) return CLIPPPO_ERR_BAD_SHAPE;
+    if (reinterpret_cast<uintptr_t>(workspace) % 256) return CLIPPPO_ERR_ALIGN;
+    const int chunk = text_chunk(N);
+    const TextWorkspace ws = carve_text(handle, chunk, workspace);
+    if (ws.bytes > workspace_bytes) return CLIPPPO_ERR_WORKSPACE;
+    for (int n0 = 0; n0 < N; n0 += chunk) {
+        const int n = (N - n0 < chunk) ? (N - n0) : chunk;
+        int st = encode_text_chunk(handle, tokens + static_cast<size_t>(n0) * handle->cfg.context, n, flags,
+                                   out + static_cast<size_t>(n0) * handle->cfg.out_dim, ws, as_stream(stream));
         if (st) return st;
     }
     return CLIPPPO_OK;

@@ -186,6 +186,39 @@ int clipppo_vit_encode(clipppo_vit_t handle, const void* images, int img_dtype,
                        float pre_scale, int flags, float* out,
                        void* workspace, size_t workspace_bytes, clipppo_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * T*  frozen CLIP text tower (ViT-B/32's: width 512, 12 blocks, 8 heads, context 77, vocab 49408).
+ * Replaces clip_model.encode_text as called from generate_clip_embeddings(modality="text")
+ * (shared/clip_ppo_utils.py:132-139), the reference's DEFAULT MiniGrid modality: token + positional
+ * embedding, the same residual blocks as the image tower under a causal mask, ln_final on the EOT
+ * row (argmax of the token ids), text_projection, optional L2 normalise.  Token ids come from the
+ * caller (clip.tokenize on the host); weights are fp32 DEVICE pointers in openai/CLIP state-dict
+ * layout (token_embedding.weight, positional_embedding, transformer.resblocks.{i}.*, ln_final.*,
+ * text_projection) and are repacked once into handle-owned memory, as for the image tower.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct clipppo_text_config {
+    int width, layers, heads, context, vocab, out_dim;
+} clipppo_text_config;
+
+typedef struct clipppo_text_weights {
+    const float* token_embedding;           /* token_embedding.weight        [vocab, D]      */
+    const float* positional_embedding;      /* positional_embedding          [context, D]    */
+    const float *ln_final_g, *ln_final_b;   /* ln_final.weight / bias        [D]             */
+    const float* text_projection;           /* text_projection               [D, out_dim]    */
+    const clipppo_vit_layer* layers_host;   /* HOST array: transformer.resblocks.{i}.*       */
+} clipppo_text_weights;
+
+typedef struct clipppo_text_s* clipppo_text_t;
+
+int clipppo_text_create(clipppo_text_t* handle, const clipppo_text_config* cfg,
+                        const clipppo_text_weights* weights_host);
+int clipppo_text_destroy(clipppo_text_t handle);
+int clipppo_text_workspace_bytes(clipppo_text_t handle, int n_texts, size_t* bytes);
+/*   tokens : DEVICE int32 [N, context] (clip.tokenize output; ids are clamped to the table).
+ *   flags  : CLIPPPO_VIT_L2NORM or 0.      out : fp32 [N, out_dim].                         */
+int clipppo_text_encode(clipppo_text_t handle, const int32_t* tokens, int N, int flags, float* out,
+                        void* workspace, size_t workspace_bytes, clipppo_stream_t stream);
+
 /* Building blocks of the tower, exported for parity tests and micro-benchmarks. */
 int clipppo_preprocess_bf16(const void* images, int img_dtype, const int64_t img_strides_host[4],
                             int N, int C, int h, int w, float pre_scale, int normalize,
@@ -224,6 +257,9 @@ int clipppo_gemm_bf16_probe(const void* a_bf16, const void* w_bf16, int M, int N
                             const float* bias, void* out, int64_t ldo, int dbg, clipppo_stream_t stream);
 int clipppo_attention_bf16(const void* qkv_bf16, int n_images, int tokens, int heads, int head_dim,
                            void* out_bf16, clipppo_stream_t stream);
+/* the same under the text tower's causal mask ([clip] build_attention_mask): query t attends to keys 0 .. t */
+int clipppo_attention_causal_bf16(const void* qkv_bf16, int n_seqs, int tokens, int heads, int head_dim,
+                                  void* out_bf16, clipppo_stream_t stream);
 
 #ifdef __cplusplus
 }

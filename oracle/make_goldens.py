@@ -212,6 +212,84 @@ def make_vit_goldens():
     return ref_utils
 
 
+class _HFTextTower(torch.nn.Module):
+    """encode_text via transformers (CLIPTextModelWithProjection), weights copied from an openai-layout state dict."""
+
+    def __init__(self, sd):
+        super().__init__()
+        from transformers import CLIPTextConfig, CLIPTextModelWithProjection
+        from oracle import text as ot
+        cfg = ot.config_from_state_dict(sd)
+        hf_cfg = CLIPTextConfig(vocab_size=cfg.vocab, hidden_size=cfg.width, intermediate_size=4 * cfg.width,
+                                projection_dim=cfg.out_dim, num_hidden_layers=cfg.layers, num_attention_heads=cfg.heads,
+                                max_position_embeddings=cfg.context, hidden_act="quick_gelu", layer_norm_eps=1e-5,
+                                bos_token_id=cfg.vocab - 2, eos_token_id=cfg.vocab - 1, pad_token_id=0)
+        m = CLIPTextModelWithProjection(hf_cfg).eval()
+        D = cfg.width
+        t = {"text_model.embeddings.token_embedding.weight": sd["token_embedding.weight"],
+             "text_model.embeddings.position_embedding.weight": sd["positional_embedding"],
+             "text_model.final_layer_norm.weight": sd["ln_final.weight"],
+             "text_model.final_layer_norm.bias": sd["ln_final.bias"],
+             "text_projection.weight": sd["text_projection"].t().contiguous()}
+        for i in range(cfg.layers):
+            p = f"transformer.resblocks.{i}."
+            h = f"text_model.encoder.layers.{i}."
+            W, b = sd[p + "attn.in_proj_weight"], sd[p + "attn.in_proj_bias"]
+            for j, n in enumerate(("q_proj", "k_proj", "v_proj")):
+                t[h + f"self_attn.{n}.weight"] = W[j * D:(j + 1) * D]
+                t[h + f"self_attn.{n}.bias"] = b[j * D:(j + 1) * D]
+            t[h + "self_attn.out_proj.weight"] = sd[p + "attn.out_proj.weight"]
+            t[h + "self_attn.out_proj.bias"] = sd[p + "attn.out_proj.bias"]
+            t[h + "layer_norm1.weight"] = sd[p + "ln_1.weight"]
+            t[h + "layer_norm1.bias"] = sd[p + "ln_1.bias"]
+            t[h + "layer_norm2.weight"] = sd[p + "ln_2.weight"]
+            t[h + "layer_norm2.bias"] = sd[p + "ln_2.bias"]
+            t[h + "mlp.fc1.weight"] = sd[p + "mlp.c_fc.weight"]
+            t[h + "mlp.fc1.bias"] = sd[p + "mlp.c_fc.bias"]
+            t[h + "mlp.fc2.weight"] = sd[p + "mlp.c_proj.weight"]
+            t[h + "mlp.fc2.bias"] = sd[p + "mlp.c_proj.bias"]
+        missing, unexpected = m.load_state_dict(t, strict=False)
+        assert not unexpected, unexpected
+        assert all("position_ids" in k for k in missing), missing
+        self.m = m
+
+    @torch.no_grad()
+    def encode_text(self, tokens):
+        return self.m(input_ids=tokens).text_embeds
+
+
+def make_text_goldens():
+    """The reference's own text branch (shared/clip_ppo_utils.py:132-139: tokenize -> encode_text -> float ->
+    normalize) run on CPU over a stub ``clip`` whose ``encode_text`` is the HF text tower and whose ``tokenize``
+    returns seeded ids (the BPE merges file is not available offline)."""
+    from oracle import text as ot
+    sd = ot.random_state_dict(ot.TEXT_B32, seed=0)
+    tower = _HFTextTower(sd)
+    _install_stub_clip(tower)
+    clip = sys.modules["clip"]
+    tokens = ot.random_tokens(6, ot.TEXT_B32, seed=3)
+    tokens[0, 2:] = 0
+    tokens[0, 2] = ot.EOT                    # shortest caption: SOT, one word, EOT
+    tokens[1, :] = torch.randint(1, 40000, (77,), generator=torch.Generator().manual_seed(9))
+    tokens[1, 0], tokens[1, 76] = ot.SOT, ot.EOT            # longest: EOT in the last slot
+    clip.tokenize = lambda texts, *a, **k: tokens[:len(texts)].clone()
+    # by file path: this repository's own drop-in ``shared`` package would shadow the reference's namespace package
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("reference_clip_ppo_utils", os.path.join(REF, "shared", "clip_ppo_utils.py"))
+    ref_utils = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref_utils)
+    model = ref_utils.load_clip_model("ViT-B/32", device="cpu")
+    emb = ref_utils.generate_clip_embeddings(ref_utils.AblationMode.NONE, model, "text", 6, "cpu",
+                                             descriptions=[f"caption {i}" for i in range(6)])
+    mine = ot.text_embeddings(sd, tokens)
+    err, cos = (emb - mine).abs().max().item(), torch.sum(emb * mine, dim=-1).min().item()
+    print(f"text embeddings: oracle vs reference+HF text tower  max-abs {err:.2e}  min-cos {cos:.8f}")
+    assert err < 5e-5 and cos > 0.99999
+    np.savez_compressed(os.path.join(OUT, "text_b32_seed0.npz"), weights_seed=0, tokens=tokens.numpy().astype(np.int32),
+                        emb=emb.numpy())
+    print("wrote text_b32_seed0.npz")
+
+
 def _ref_lines(path, lo, hi):
     """Lines lo..hi (1-based, inclusive) of a reference source file, dedented for exec."""
     with open(os.path.join(REF, path)) as f:
@@ -277,6 +355,10 @@ def make_loss_goldens(ref_utils):
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
+    if sys.argv[1:] == ["text"]:             # the text-tower fixture alone (added after the others)
+        make_text_goldens()
+        sys.exit(0)
     make_disturb_goldens()
     ref_utils = make_vit_goldens()
     make_loss_goldens(ref_utils)
+    make_text_goldens()

@@ -28,6 +28,7 @@ except ImportError:                     # stand-in with the same surface (image 
     sys.modules.setdefault("clip.model", clip.model)
 
 from clip_ppo_b200 import losses as _L
+from clip_ppo_b200.text import TextEngine
 from clip_ppo_b200.vit import VitEngine
 
 
@@ -83,6 +84,19 @@ def _engine_for(clip_model) -> VitEngine:
     return eng
 
 
+def _text_engine_for(clip_model) -> TextEngine:
+    """The native text tower: our compat ``CLIP`` builds it lazily; a real openai module's top-level text weights
+    (``token_embedding.weight`` ... ``text_projection``) are repacked once and cached on the module."""
+    if hasattr(clip_model, "text_engine"):
+        return clip_model.text_engine()
+    eng = getattr(clip_model, "_clipppo_text_engine", None)
+    dev = next(clip_model.parameters()).device
+    if eng is None or eng.device != dev:
+        eng = TextEngine(clip_model.state_dict(), device=dev, prefix="")
+        object.__setattr__(clip_model, "_clipppo_text_engine", eng)
+    return eng
+
+
 def generate_clip_embeddings(
     ablation_mode: AblationMode,
     clip_model: torch.nn.Module,
@@ -99,10 +113,10 @@ def generate_clip_embeddings(
     if modality == "text":
         if descriptions is None:
             raise ValueError("descriptions required for text modality")
-        tokens = clip.tokenize(descriptions).to(device)
-        with torch.no_grad():
-            e = clip_model.encode_text(tokens).float()
-        return torch.nn.functional.normalize(e, dim=-1)
+        # additive: pre-tokenised [N, 77] ids are taken as they are (no tokenizer needed)
+        tokens = descriptions if isinstance(descriptions, torch.Tensor) else clip.tokenize(descriptions)
+        # encode_text -> float -> normalize, one call into the native text tower
+        return _text_engine_for(clip_model).encode(tokens.to(device), l2norm=True)
     if modality == "image":
         if images is None:
             raise ValueError("images required for image modality")

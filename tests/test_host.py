@@ -113,3 +113,23 @@ def test_compat_state_dict_matches_oracle_weights():
     assert a.keys() == b.keys()
     for k in ("visual.conv1.weight", "visual.transformer.resblocks.11.mlp.c_proj.weight", "visual.proj"):
         assert torch.equal(a[k], b[k])
+
+
+def test_compat_text_state_dict_matches_oracle_weights():
+    """clip_compat's seeded text-tower weights are the oracle's (same generator, same order), and they travel through
+    the compat CLIP module's state dict under upstream's top-level key names."""
+    from oracle import text as ot
+    from clip_ppo_b200 import clip_compat
+    a = clip_compat.random_text_state_dict("ViT-B/32", 0)
+    b = ot.random_state_dict(ot.TEXT_B32, 0)
+    assert set(a) == set(b) and all(torch.equal(a[k], b[k]) for k in a)
+    model, _ = clip_compat.load("ViT-B/32", device="cpu")
+    sd = model.state_dict()
+    assert torch.equal(sd["text_projection"], b["text_projection"]) and "visual.proj" in sd
+    assert torch.equal(sd["transformer.resblocks.11.mlp.c_proj.weight"], b["transformer.resblocks.11.mlp.c_proj.weight"])
+    other, _ = clip_compat.load("ViT-B/32", device="cpu", seed=1)
+    assert not torch.equal(other.state_dict()["ln_final.bias"], sd["ln_final.bias"])
+    other.load_state_dict(sd)
+    assert torch.equal(other.state_dict()["ln_final.bias"], sd["ln_final.bias"])
+    with pytest.raises(NotImplementedError):
+        clip_compat.tokenize(["a red door"])

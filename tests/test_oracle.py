@@ -98,6 +98,39 @@ def test_vit_oracle_matches_hf_small():
     assert (a - b).abs().max() < 2e-5
 
 
+def test_text_oracle_against_reference_goldens():
+    """tests/golden/text_b32_seed0.npz: the reference's own text branch (shared/clip_ppo_utils.py:132-139) over the
+    HF text tower with the seeded weights."""
+    from oracle import text as ot
+    g = np.load(os.path.join(GOLDEN, "text_b32_seed0.npz"))
+    sd = ot.random_state_dict(ot.TEXT_B32, seed=int(g["weights_seed"]))
+    tokens = torch.from_numpy(g["tokens"]).long()
+    assert tokens.shape == (6, 77) and int(tokens[0].argmax()) == 2 and int(tokens[1].argmax()) == 76
+    emb = ot.text_embeddings(sd, tokens)
+    ref = torch.from_numpy(g["emb"])
+    assert (emb - ref).abs().max() < 5e-5
+    assert torch.sum(emb * ref, dim=-1).min() > 0.99999
+
+
+def test_text_oracle_matches_hf_small():
+    """Independent implementation check on a small config (fast): restated text tower == HF CLIPTextModelWithProjection."""
+    pytest.importorskip("transformers")
+    from oracle import text as ot
+    from oracle.make_goldens import _HFTextTower
+    cfg = ot.TextConfig(width=128, layers=2, heads=2, context=77, vocab=1000, out_dim=64)
+    sd = ot.random_state_dict(cfg, seed=3)
+    tokens = ot.random_tokens(5, cfg, seed=1)
+    a = ot.text_tower(sd, tokens)
+    b = _HFTextTower(sd).encode_text(tokens)
+    assert (a - b).abs().max() < 2e-5
+    # causal: changing a token AFTER the EOT position must not change the embedding
+    t2 = tokens.clone()
+    eot = int(tokens[0].argmax())
+    if eot + 1 < 77:
+        t2[0, eot + 1:] = 5
+        assert torch.equal(ot.text_tower(sd, t2)[0], a[0])
+
+
 def test_loss_oracle_against_reference_goldens():
     g = np.load(os.path.join(GOLDEN, "losses.npz"))
     z = torch.from_numpy(g["cos_z"]).requires_grad_(True)
