@@ -7,6 +7,8 @@
 // cp.async (zero-filled beyond T) while item i is computed, so no warp ever waits on a global
 // load.  The two tiny matmuls run on the warp-level tensor-core path (mma.sync m16n8k16 bf16, fp32
 // accumulate); the softmax lives in the accumulator registers and P never leaves them.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "gemm.cuh"
 
@@ -210,23 +212,25 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv, int n_items, int T, __nv
 // online softmax (running maximum / sum in registers, output accumulator rescaled when the maximum
 // moves) and writes its 16 x 64 output tile back through the same buffer.  A last key block of <= 8 keys
 // (T = 257: exactly the one key left after four blocks) costs one 8-key MMA tile instead of a padded block.
-constexpr int ATTG_WARPS = 6;
-constexpr int ATTG_THREADS = ATTG_WARPS * 32;
+// Long sequences (T = 257): 6 warps, 2 CTAs / SM.  Short ones (the text tower, T = 77: five query tiles, 20 KB of
+// K / V): 3 warps and 4 CTAs / SM, so one CTA's load phase hides under its neighbours' arithmetic.
 constexpr int ATTG_QROWS = 16;
+constexpr int ATTG_SHORT_T = 128;
 
 __host__ __device__ constexpr int attg_kv_rows(int T) { return (T + 15) / 16 * 16; }
-__host__ __device__ constexpr size_t attg_smem_bytes(int T) {
-    return (static_cast<size_t>(2) * attg_kv_rows(T) + ATTG_WARPS * ATTG_QROWS) * PITCH * 2;
+__host__ __device__ constexpr size_t attg_smem_bytes(int T, int warps) {
+    return (static_cast<size_t>(2) * attg_kv_rows(T) + warps * ATTG_QROWS) * PITCH * 2;
 }
 
 // CAUSAL (the text tower, [clip] build_attention_mask): query t sees keys 0 .. t.  Key blocks that start
 // beyond a query tile's last row are skipped; the block on the diagonal is masked element-wise (its first
 // key is <= every query row of the tile, so no row of a block is ever fully masked).
-template <int HEADS, bool CAUSAL>
-__global__ void __launch_bounds__(ATTG_THREADS, 2)
+template <int HEADS, bool CAUSAL, int ATTG_WARPS>
+__global__ void __launch_bounds__(ATTG_WARPS * 32, ATTG_WARPS == 6 ? 2 : 4)
 attention_general_kernel(const __nv_bfloat16* __restrict__ qkv, int T, __nv_bfloat16* __restrict__ out) {
     extern __shared__ __align__(16) __nv_bfloat16 att_smem[];
     constexpr int D = HEADS * DH;
+    constexpr int ATTG_THREADS = ATTG_WARPS * 32;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int rows_kv = attg_kv_rows(T);
     const uint32_t k_base = ptx_smem(att_smem);
@@ -437,16 +441,25 @@ attention_general_kernel(const __nv_bfloat16* __restrict__ qkv, int T, __nv_bflo
 
 }  // namespace
 
-template <int HEADS, bool CAUSAL>
-static int launch_general(const __nv_bfloat16* q, int n_images, int tokens, __nv_bfloat16* o, size_t smem, cudaStream_t stream) {
+template <int HEADS, bool CAUSAL, int WARPS>
+static int launch_general_w(const __nv_bfloat16* q, int n_images, int tokens, __nv_bfloat16* o, cudaStream_t stream) {
+    const size_t smem = attg_smem_bytes(tokens, WARPS);
+    if (smem > 113 * 1024) return CLIPPPO_ERR_UNSUPPORTED;          // 2 CTAs / SM; T <= 352
     static bool configured = false;
     if (!configured) {
-        CLIPPPO_CUDA_TRY(cudaFuncSetAttribute(attention_general_kernel<HEADS, CAUSAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
+        CLIPPPO_CUDA_TRY(cudaFuncSetAttribute(attention_general_kernel<HEADS, CAUSAL, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
         configured = true;
     }
-    CLIPPPO_CUDA_TRY(launch_pdl(attention_general_kernel<HEADS, CAUSAL>, static_cast<unsigned>(n_images) * HEADS, ATTG_THREADS, smem,
+    CLIPPPO_CUDA_TRY(launch_pdl(attention_general_kernel<HEADS, CAUSAL, WARPS>, static_cast<unsigned>(n_images) * HEADS, WARPS * 32, smem,
                                 stream, 1, q, tokens, o));
     return CLIPPPO_OK;
+}
+
+template <int HEADS, bool CAUSAL>
+static int launch_general(const __nv_bfloat16* q, int n_images, int tokens, __nv_bfloat16* o, cudaStream_t stream) {
+    static const int short_warps = [] { const char* e = getenv("CLIPPPO_ATT_SHORT_WARPS"); return e ? atoi(e) : 3; }();
+    if (tokens <= ATTG_SHORT_T && short_warps == 3) return launch_general_w<HEADS, CAUSAL, 3>(q, n_images, tokens, o, stream);
+    return launch_general_w<HEADS, CAUSAL, 6>(q, n_images, tokens, o, stream);
 }
 
 int attention_launch(const void* qkv_bf16, int n_images, int tokens, int heads, int head_dim, void* out_bf16,
@@ -456,20 +469,18 @@ int attention_launch(const void* qkv_bf16, int n_images, int tokens, int heads, 
     if (head_dim != DH) return CLIPPPO_ERR_UNSUPPORTED;
     if ((reinterpret_cast<uintptr_t>(qkv_bf16) % 16) || (reinterpret_cast<uintptr_t>(out_bf16) % 16)) return CLIPPPO_ERR_ALIGN;
     if (tokens > TP || causal) {                     // ViT-L/14 (T = 257), text tower (T = 77, causal): one CTA per (sequence, head), K / V resident
-        const size_t smem = attg_smem_bytes(tokens);
-        if (smem > 113 * 1024) return CLIPPPO_ERR_UNSUPPORTED;      // 2 CTAs / SM; T <= 352
         if (static_cast<long long>(n_images) * heads > 0x7fffffffLL) return CLIPPPO_ERR_BAD_SHAPE;
         const __nv_bfloat16* q = static_cast<const __nv_bfloat16*>(qkv_bf16);
         __nv_bfloat16* o = static_cast<__nv_bfloat16*>(out_bf16);
         int st = CLIPPPO_ERR_UNSUPPORTED;            // head counts of the CLIP towers: 8 (text), 12 (B/32, B/16), 16 (L/14)
         if (causal) {
-            if (heads == 8) st = launch_general<8, true>(q, n_images, tokens, o, smem, stream);
-            else if (heads == 12) st = launch_general<12, true>(q, n_images, tokens, o, smem, stream);
-            else if (heads == 16) st = launch_general<16, true>(q, n_images, tokens, o, smem, stream);
+            if (heads == 8) st = launch_general<8, true>(q, n_images, tokens, o, stream);
+            else if (heads == 12) st = launch_general<12, true>(q, n_images, tokens, o, stream);
+            else if (heads == 16) st = launch_general<16, true>(q, n_images, tokens, o, stream);
         } else {
-            if (heads == 8) st = launch_general<8, false>(q, n_images, tokens, o, smem, stream);
-            else if (heads == 12) st = launch_general<12, false>(q, n_images, tokens, o, smem, stream);
-            else if (heads == 16) st = launch_general<16, false>(q, n_images, tokens, o, smem, stream);
+            if (heads == 8) st = launch_general<8, false>(q, n_images, tokens, o, stream);
+            else if (heads == 12) st = launch_general<12, false>(q, n_images, tokens, o, stream);
+            else if (heads == 16) st = launch_general<16, false>(q, n_images, tokens, o, stream);
         }
         if (st == CLIPPPO_OK) prof_count_launch();
         return st;
