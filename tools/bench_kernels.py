@@ -32,7 +32,9 @@ def timeit(fn, iters=20, warm=3):
 
 
 def bench_disturb():
-    from oracle.disturb import SEVERITY_TABLE
+    from shared.disturbance_types import DisturbanceSeverity, SEVERITY_CONFIGS
+    SEVERITY_TABLE = {s.name: {"noise_sigma": r["gaussian_noise_sigma"], "blur_sigma": r["gaussian_blur_sigma"],
+                               "cutout": r["cutout_ratio"]} for s, r in SEVERITY_CONFIGS.items()}
     for (B, C, H, W, sev) in [(4096, 3, 224, 224, "MODERATE"), (4096, 3, 224, 224, "SEVERE"), (501, 3, 224, 224, "MODERATE"),
                               (16384, 3, 84, 84, "MODERATE"), (16384, 1, 84, 84, "HARD"), (64, 3, 84, 84, "MODERATE"),
                               (256, 1, 84, 84, "HARD")]:

@@ -7,10 +7,11 @@ sys.path.insert(0, ROOT)
 import torch
 
 from clip_ppo_b200 import disturb as D
-from oracle.disturb import SEVERITY_TABLE
+from shared.disturbance_types import DisturbanceSeverity, SEVERITY_CONFIGS
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
-cfg = SEVERITY_TABLE["MODERATE"]
+_row = SEVERITY_CONFIGS[DisturbanceSeverity.MODERATE]
+cfg = {"blur_sigma": _row["gaussian_blur_sigma"], "noise_sigma": _row["gaussian_noise_sigma"], "cutout": _row["cutout_ratio"]}
 x = torch.rand(B, 3, 224, 224, device="cuda")
 n = torch.randn(B, 3, 224, 224, device="cuda")
 k = D.blur_kernel_size(cfg["blur_sigma"])
