@@ -99,6 +99,21 @@ def process_multiframe_clip_embeddings(rgb_frames: torch.Tensor, clip_model, abl
     return e.reshape(B, F * e.shape[-1])
 
 
+# ---- a20: latents for the alignment loss without the second encoder forward ---------------------------
+def action_value_and_latents(agent, obs: torch.Tensor, action: torch.Tensor):
+    """``agent.get_action_and_value(obs, action)`` plus the detached encoder output that
+    ``agent.get_latent_representation(obs)`` would recompute (clip_ppo_minigrid.py:262-271, 534): one forward
+    of the PPO encoder per minibatch instead of two, bitwise the same latents.  Returns
+    (action, logprob, entropy, value, latents); works with any agent exposing ``_pre`` / ``_get_features`` /
+    ``actor`` / ``critic`` like the reference's ``Agent``."""
+    from torch.distributions.categorical import Categorical
+    hidden = agent._get_features(agent._pre(obs))
+    probs = Categorical(logits=agent.actor(hidden))
+    if action is None:
+        action = probs.sample()
+    return action, probs.log_prob(action), probs.entropy(), agent.critic(hidden), hidden.detach()
+
+
 # ---- a21: GAE (clip_ppo_minigrid.py:437-450 = clip_ppo_atari.py:619-632) ---------------------------
 def compute_gae(rewards: torch.Tensor, values: torch.Tensor, dones: torch.Tensor, next_value: torch.Tensor,
                 next_done: torch.Tensor, gamma: float = 0.99, gae_lambda: float = 0.95) -> Tuple[torch.Tensor, torch.Tensor]:

@@ -133,3 +133,46 @@ def test_compat_text_state_dict_matches_oracle_weights():
     assert torch.equal(other.state_dict()["ln_final.bias"], sd["ln_final.bias"])
     with pytest.raises(NotImplementedError):
         clip_compat.tokenize(["a red door"])
+
+
+def test_single_forward_latents_equal_the_scripts_second_forward():
+    """a20: rollout.action_value_and_latents == get_action_and_value + get_latent_representation of the reference Agent
+    (clip_ppo_minigrid.py:213-271 restated), with one encoder forward."""
+    import torch.nn as nn
+    from torch.distributions.categorical import Categorical
+    from clip_ppo_b200 import rollout
+
+    class Agent(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.calls = 0
+            self.network = nn.Sequential(nn.Conv2d(3, 32, 8, stride=4), nn.ReLU(), nn.Conv2d(32, 64, 4, stride=2), nn.ReLU(),
+                                         nn.Conv2d(64, 64, 3, stride=1), nn.ReLU(), nn.Flatten(), nn.Linear(64 * 7 * 7, 512), nn.ReLU())
+            self.actor, self.critic = nn.Linear(512, 7), nn.Linear(512, 1)
+
+        def _pre(self, x):
+            return x.permute(0, 3, 1, 2).contiguous() / 255.0
+
+        def _get_features(self, x):
+            self.calls += 1
+            return self.network(x)
+
+        def get_action_and_value(self, x, action=None):
+            hidden = self._get_features(self._pre(x))
+            probs = Categorical(logits=self.actor(hidden))
+            return action, probs.log_prob(action), probs.entropy(), self.critic(hidden)
+
+        def get_latent_representation(self, x):
+            return self._get_features(self._pre(x)).detach()
+
+    torch.manual_seed(0)
+    agent = Agent()
+    obs = torch.randint(0, 256, (5, 84, 84, 3)).float()
+    act = torch.randint(0, 7, (5,))
+    _, lp, ent, val = agent.get_action_and_value(obs, act)
+    lat = agent.get_latent_representation(obs)
+    agent.calls = 0
+    a2, lp2, ent2, val2, lat2 = rollout.action_value_and_latents(agent, obs, act)
+    assert agent.calls == 1
+    assert torch.equal(lp, lp2) and torch.equal(ent, ent2) and torch.equal(val, val2) and torch.equal(lat, lat2)
+    assert not lat2.requires_grad and lp2.requires_grad
