@@ -800,7 +800,11 @@ static int run_disturb(DisturbParams& p, const float* k1d_host, int k, cudaStrea
         if (nsplit <= 0) {
             nsplit = 1;
             while (p.C * nq * nsplit < 160 && nsplit < p.R) ++nsplit;                     // at least ~5 warps of tasks
-            while (p.C * nq * nsplit < 320 && p.R / (nsplit + 1) >= 12) ++nsplit;         // ~10 warps while a split keeps >= 12 rows
+            // ~10 warps while a split keeps >= 12 rows (>= 6P beyond the first cut: every split pays 2P warm-up rows).
+            // Measured at 84x84x3 (tools/disturb_nsplit_84.py): 5 splits 84-87 % of the HBM peak at k = 3 / 5 where 6
+            // gave 81-84 %; k = 7: 4 splits 67 %, 6 splits 62-64 %.
+            auto min_rows = [&](int n) { return n >= 2 && 6 * P > 12 ? 6 * P : 12; };
+            while (p.C * nq * nsplit < 300 && p.R / (nsplit + 1) >= min_rows(nsplit)) ++nsplit;
         }
         if (nsplit > p.R) nsplit = p.R;
         p.nsplit = nsplit;
