@@ -173,7 +173,10 @@ class VitEngine:
     @torch.no_grad()
     def encode(self, images: torch.Tensor, pre_scale: float = 1.0 / 255.0, l2norm: bool = True,
                prenormalized: bool = False) -> torch.Tensor:
-        """images [N,C,h,w] (fp32 or uint8, any strides, C in {1,3}, h,w <= 224) -> fp32 [N,out_dim]."""
+        """images [N,C,h,w] (fp32 or uint8, any strides, C in {1,3}) -> fp32 [N,out_dim].  Frames up to the tower's
+        resolution take the fused resize (up-sampling: antialias is a no-op); larger ones - never produced by the
+        reference's environments - are first reduced by torch's antialiased bilinear resize, the op the reference
+        itself calls (shared/clip_ppo_utils.py:151-157), in chunks so the fp32 intermediate stays bounded."""
         if images.device != self.device:
             raise RuntimeError(f"images on {images.device}, tower on {self.device}")
         if images.dim() != 4:
@@ -181,6 +184,14 @@ class VitEngine:
         if images.dtype not in (torch.float32, torch.uint8):
             images = images.float()
         n, c, h, w = images.shape
+        R = self.cfg.image
+        if (h > R or w > R) and not prenormalized and n > 0:
+            outs = []
+            for i in range(0, n, 256):
+                x = torch.nn.functional.interpolate(images[i:i + 256].float() * pre_scale, size=(R, R), mode="bilinear",
+                                                    align_corners=False, antialias=True)
+                outs.append(self.encode(x, pre_scale=1.0, l2norm=l2norm))
+            return torch.cat(outs)
         out = torch.empty((n, self.cfg.out_dim), dtype=torch.float32, device=self.device)
         if n == 0:
             return out

@@ -347,3 +347,17 @@ def test_uint8_obs_store_matches_fp32_rollout_storage(native):
     assert torch.equal(store.policy_input(mb), obs_f32.reshape(-1, 84, 84, 3)[mb])
     with pytest.raises(ValueError):
         store[0] = torch.full((E, 84, 84, 3), 0.5, device="cuda")
+
+
+def test_frames_larger_than_the_tower_resolution(native):
+    """h, w > 224: antialiased down-sampling (torch's op, as in the reference) in front of the fused path."""
+    eng = _engine(0)
+    sd = ov.random_state_dict(ov.VIT_B32, 0)
+    gen = torch.Generator().manual_seed(9)
+    img = torch.randint(0, 256, (3, 3, 300, 260), generator=gen).float()
+    emb = eng.encode(img.cuda(), pre_scale=1 / 255.0, l2norm=True).cpu()
+    ref = ov.image_embeddings(sd, img)
+    assert torch.sum(emb * ref, dim=-1).min().item() >= 0.999
+    mixed = torch.randint(0, 256, (2, 3, 240, 100), generator=gen).float()          # one side down, one side up
+    emb = eng.encode(mixed.cuda(), pre_scale=1 / 255.0, l2norm=True).cpu()
+    assert torch.sum(emb * ov.image_embeddings(sd, mixed), dim=-1).min().item() >= 0.999
