@@ -11,7 +11,9 @@ from clip_ppo_b200 import _native as N
 L = N.lib()
 st = torch.cuda.current_stream().cuda_stream
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 2048
-T, H, dh = 50, 12, 64
+T = int(sys.argv[2]) if len(sys.argv) > 2 else 50            # 257 with H = 16: the ViT-L/14 kernel
+H = int(sys.argv[3]) if len(sys.argv) > 3 else 12
+dh = 64
 qkv = torch.randn(n * T, 3 * H * dh, device="cuda").bfloat16()
 out = torch.empty(n * T, H * dh, device="cuda", dtype=torch.bfloat16)
 for _ in range(3):
