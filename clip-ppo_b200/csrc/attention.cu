@@ -445,10 +445,9 @@ template <int HEADS, bool CAUSAL, int WARPS>
 static int launch_general_w(const __nv_bfloat16* q, int n_images, int tokens, __nv_bfloat16* o, cudaStream_t stream) {
     const size_t smem = attg_smem_bytes(tokens, WARPS);
     if (smem > 113 * 1024) return CLIPPPO_ERR_UNSUPPORTED;          // 2 CTAs / SM; T <= 352
-    static bool configured = false;
-    if (!configured) {
+    static DeviceOnce configured;
+    if (configured.first_use()) {
         CLIPPPO_CUDA_TRY(cudaFuncSetAttribute(attention_general_kernel<HEADS, CAUSAL, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
-        configured = true;
     }
     CLIPPPO_CUDA_TRY(launch_pdl(attention_general_kernel<HEADS, CAUSAL, WARPS>, static_cast<unsigned>(n_images) * HEADS, WARPS * 32, smem,
                                 stream, 1, q, tokens, o));
@@ -491,17 +490,15 @@ int attention_launch(const void* qkv_bf16, int n_images, int tokens, int heads, 
     const __nv_bfloat16* q = static_cast<const __nv_bfloat16*>(qkv_bf16);
     __nv_bfloat16* o = static_cast<__nv_bfloat16*>(out_bf16);
     if (heads == 12) {
-        static bool configured = false;
-        if (!configured) {
+        static DeviceOnce configured;
+        if (configured.first_use()) {
             CLIPPPO_CUDA_TRY(cudaFuncSetAttribute(attention_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
-            configured = true;
         }
         CLIPPPO_CUDA_TRY(launch_pdl(attention_kernel<12>, grid, ATT_THREADS, ATT_SMEM_BYTES, stream, 1, q, static_cast<int>(items), tokens, o));
     } else if (heads == 16) {
-        static bool configured = false;
-        if (!configured) {
+        static DeviceOnce configured;
+        if (configured.first_use()) {
             CLIPPPO_CUDA_TRY(cudaFuncSetAttribute(attention_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
-            configured = true;
         }
         CLIPPPO_CUDA_TRY(launch_pdl(attention_kernel<16>, grid, ATT_THREADS, ATT_SMEM_BYTES, stream, 1, q, static_cast<int>(items), tokens, o));
     } else {

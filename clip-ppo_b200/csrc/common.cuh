@@ -63,6 +63,20 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
 
 constexpr int kNumSMs = 148;   // B200: 2 dies x 74 SMs
 
+// cudaFuncSetAttribute is per DEVICE: a kernel instantiation opts in to large dynamic shared memory / non-portable
+// clusters once on every device it is launched on (one process may hold towers on several GPUs).
+struct DeviceOnce {
+    unsigned long long done = 0;
+    bool first_use() {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev > 63) return true;
+        const unsigned long long bit = 1ull << dev;
+        if (done & bit) return false;
+        done |= bit;
+        return true;
+    }
+};
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -673,11 +673,10 @@ disturb_kernel(const __grid_constant__ DisturbParams p) {
 
 template <int K>
 static int launch_disturb(const DisturbParams& p, size_t smem, cudaStream_t stream) {
-    static bool configured = false;     // opt in to > 48 KB dynamic smem once per instantiation
-    if (!configured) {
+    static DeviceOnce configured;     // opt in to > 48 KB dynamic smem once per instantiation
+    if (configured.first_use()) {
         CLIPPPO_CUDA_TRY(cudaFuncSetAttribute(disturb_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         CLIPPPO_CUDA_TRY(cudaFuncSetAttribute(disturb_kernel<K>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-        configured = true;
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(static_cast<unsigned>(p.B) * p.S);
@@ -698,11 +697,10 @@ static int launch_disturb(const DisturbParams& p, size_t smem, cudaStream_t stre
 
 template <int K, int WT>
 static int launch_disturb_fast_w(const DisturbParams& p, size_t smem, cudaStream_t stream) {
-    static bool configured = false;
-    if (!configured) {
+    static DeviceOnce configured;
+    if (configured.first_use()) {
         CLIPPPO_CUDA_TRY(cudaFuncSetAttribute(disturb_fast_kernel<K, WT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         CLIPPPO_CUDA_TRY(cudaFuncSetAttribute(disturb_fast_kernel<K, WT>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-        configured = true;
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(static_cast<unsigned>(p.B) * p.S);

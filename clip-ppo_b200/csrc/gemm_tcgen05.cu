@@ -511,10 +511,9 @@ template <int EPI, int MODE, int DBG = 0>
 int launch_gemm_mode(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tout, const GemmArgs& g,
                      cudaStream_t stream) {
     using C = Cfg<MODE, EPI>;
-    static bool configured = false;
-    if (!configured) {
+    static DeviceOnce configured;
+    if (configured.first_use()) {
         CLIPPPO_CUDA_TRY(cudaFuncSetAttribute(gemm_bf16_kernel<EPI, MODE, DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-        configured = true;
     }
     const int m_tiles = (g.M + BM - 1) / BM, n_tiles = (g.N + BN - 1) / BN;
     const int work = ((m_tiles + C::CL - 1) / C::CL) * n_tiles * (EPI == CLIPPPO_EPI_RESID_BF16 ? g.ksplit : 1);

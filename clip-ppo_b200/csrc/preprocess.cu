@@ -225,11 +225,9 @@ int preprocess_launch(const void* images, int img_dtype, const long long strides
     if (ident) {
         preprocess_kernel<8, true><<<grid, 256, 0, stream>>>(p);
     } else if (vec8 && image % 8 == 0 && rs_smem <= 200 * 1024) {
-        static size_t configured = 48 * 1024;
-        if (rs_smem > configured) {
+        static DeviceOnce configured;
+        if (rs_smem > 48 * 1024 && configured.first_use())
             CLIPPPO_CUDA_TRY(cudaFuncSetAttribute(preprocess_resize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-            configured = 200 * 1024;
-        }
         preprocess_resize_kernel<<<grid, 256, rs_smem, stream>>>(p, max_rows);
     } else if (vec8)
         preprocess_kernel<8, false><<<grid, 256, 0, stream>>>(p);

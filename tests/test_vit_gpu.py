@@ -361,3 +361,27 @@ def test_frames_larger_than_the_tower_resolution(native):
     mixed = torch.randint(0, 256, (2, 3, 240, 100), generator=gen).float()          # one side down, one side up
     emb = eng.encode(mixed.cuda(), pre_scale=1 / 255.0, l2norm=True).cpu()
     assert torch.sum(emb * ov.image_embeddings(sd, mixed), dim=-1).min().item() >= 0.999
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs in one process")
+def test_second_device_in_the_same_process(native):
+    """Kernel attributes (large dynamic smem, cluster sizes) are opted in per device: a process that used cuda:0 can
+    run the same path on cuda:1 and gets the same bits."""
+    from shared.disturbances_gpu import DisturbanceWrapperGPU
+    from shared.disturbance_types import DisturbanceSeverity
+    from clip_ppo_b200.vit import VitEngine
+    sd = ov.random_state_dict(ov.VIT_B32, 0)
+    gen = torch.Generator().manual_seed(3)
+    x = torch.rand(5, 3, 224, 224, generator=gen)
+    noise = torch.randn(5, 3, 224, 224, generator=gen)
+    small = torch.rand(9, 3, 84, 84, generator=gen)
+    outs = []
+    for dev in ("cuda:0", "cuda:1"):
+        w = DisturbanceWrapperGPU(device=dev, severity=DisturbanceSeverity.SEVERE)
+        d = w.apply_disturbances(x.to(dev), noise=noise.to(dev), contrast_factor=1.2, cutout_start=(5, 9))
+        eng = VitEngine(sd, device=dev)
+        e = eng.encode(d * 255.0, pre_scale=1 / 255.0, l2norm=True)
+        e2 = eng.encode(small.to(dev) * 255.0, pre_scale=1 / 255.0, l2norm=True)
+        outs.append((d.cpu(), e.cpu(), e2.cpu()))
+    for a, b in zip(outs[0], outs[1]):
+        assert torch.equal(a, b)
