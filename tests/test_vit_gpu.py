@@ -385,3 +385,30 @@ def test_second_device_in_the_same_process(native):
         outs.append((d.cpu(), e.cpu(), e2.cpu()))
     for a, b in zip(outs[0], outs[1]):
         assert torch.equal(a, b)
+
+
+def test_full_size_batches_of_the_baseline_configs(native):
+    """BASELINE configs at their full sizes, through size-independent properties: unit-norm rows, and an image's
+    embedding is bitwise the same alone, inside a small batch and inside the full batch (several tower chunks)."""
+    import shared.clip_ppo_utils as U
+    from clip_ppo_b200 import rollout
+    model = U.load_clip_model("ViT-B/32", "cuda")
+    gen = torch.Generator(device="cuda").manual_seed(1)
+    # configs[2]: 4096 frames of 224 x 224 x 3 (uint8-valued)
+    frames = torch.randint(0, 256, (4096, 3, 224, 224), device="cuda", generator=gen, dtype=torch.uint8)
+    emb = U.generate_clip_embeddings(U.AblationMode.NONE, model, "image", 4096, "cuda", images=frames)
+    assert emb.shape == (4096, 512) and torch.isfinite(emb).all()
+    assert (emb.norm(dim=-1) - 1).abs().max().item() <= 1e-5
+    idx = torch.tensor([0, 1337, 4095], device="cuda")
+    sub = U.generate_clip_embeddings(U.AblationMode.NONE, model, "image", 3, "cuda", images=frames[idx].float())
+    assert torch.equal(sub, emb[idx])
+    del frames, emb
+    # configs[3]: 256 envs x 128 steps of 4 stacked 84 x 84 gray frames = 131 072 CLIP frames -> [32768, 2048]
+    stacks = torch.randint(0, 256, (32768, 4, 84, 84), device="cuda", generator=gen, dtype=torch.uint8).float()
+    rgb = rollout.convert_atari_frames_for_clip(stacks) / 255.0               # the Atari call site's double /255 (clip_ppo_atari.py:661)
+    e = rollout.process_multiframe_clip_embeddings(rgb, model, U.AblationMode.NONE, "image", 32768, "cuda")
+    assert e.shape == (32768, 4 * 512) and torch.isfinite(e).all()
+    assert (e.reshape(-1, 512).norm(dim=-1) - 1).abs().max().item() <= 1e-5
+    pick = torch.tensor([0, 20000, 32767], device="cuda")
+    e_sub = rollout.process_multiframe_clip_embeddings(rgb[pick], model, U.AblationMode.NONE, "image", 3, "cuda")
+    assert torch.equal(e_sub, e[pick])
