@@ -7,6 +7,10 @@
 //     A[b*G*G + gy*G + gx, c*P*P + ky*P + kx] = pixel(b, c, gy*P+ky, gx*P+kx)
 // so the 224x224 fp32 intermediate (79 GB at the Atari config) is never materialised.
 // C == 1 inputs (Atari gray frames) are broadcast to the three channels in registers.
+#include <stdlib.h>
+
+#include <type_traits>
+
 #include "common.cuh"
 #include "gemm.cuh"
 
@@ -105,6 +109,63 @@ __global__ void __launch_bounds__(256) preprocess_resize_kernel(const PreParams 
         pk.x = *reinterpret_cast<uint32_t*>(&q0); pk.y = *reinterpret_cast<uint32_t*>(&q1);
         pk.z = *reinterpret_cast<uint32_t*>(&q2); pk.w = *reinterpret_cast<uint32_t*>(&q3);
         *reinterpret_cast<uint4*>(dst) = pk;
+    }
+}
+
+// 84 x 84 -> 224 x 224 with patch 32: the one up-sampling case of the reference (MiniGrid and Atari frames).
+// The ratio is 3 / 8, so source index and weight of an output pixel depend only on (pixel mod 8):
+//     x0 = 3g + {-1, 0, 0, 0, 1, 1, 1, 2}[j],  lambda = {11, 1, 7, 13, 3, 9, 15, 5}[j] / 16      (ox = 8g + j),
+// the same numbers ATen's area_pixel_compute_source_index gives in fp32 (3/8 and the sixteenths are exact), and the
+// same vertically.  Thread = (channel, 8-row group q of the patch row, 8-column group g): 5 source rows x 5 source
+// columns from global memory (L1 serves the overlap with the neighbours), 5 x 8 horizontal blends, 8 x 8 vertical
+// blends, normalise, eight 16-byte stores.  No shared memory, no barrier, ~7 instructions per output value
+// (the generic two-pass kernel: 35, bound by its load/store pipe).
+template <int DT>
+__global__ void __launch_bounds__(352) preprocess_up84_kernel(const PreParams p) {
+    constexpr int W = 84, P = 32, G = 7;
+    constexpr float kL[8] = {0.6875f, 0.0625f, 0.4375f, 0.8125f, 0.1875f, 0.5625f, 0.9375f, 0.3125f};
+    constexpr int kI[8] = {0, 1, 1, 1, 2, 2, 2, 3};          // first of the two source lines, relative to (3 * group - 1)
+    const int t = threadIdx.x;
+    if (t >= 3 * 4 * 28) return;
+    const int b = blockIdx.x / G, gy = blockIdx.x - b * G;
+    const int g = t % 28, cq = t / 28, q = cq & 3, c = cq >> 2;
+    using elem_t = typename std::conditional<DT == CLIPPPO_IMG_U8, uint8_t, float>::type;
+    const elem_t* img = static_cast<const elem_t*>(p.img) + static_cast<long long>(b) * p.s[0] + ((p.C == 1) ? 0 : c) * p.s[1];
+    const float ps = p.pre_scale;
+    // source columns 3g-1 .. 3g+3 and source rows 12gy+3q-1 .. +3, clamped to the frame
+    long long xo[5];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) xo[i] = static_cast<long long>(min(max(3 * g - 1 + i, 0), W - 1)) * p.s[3];
+    const int y_first = 12 * gy + 3 * q - 1;
+    float H[5][8];                                             // horizontally interpolated source rows
+#pragma unroll
+    for (int r = 0; r < 5; ++r) {
+        const elem_t* row = img + static_cast<long long>(min(max(y_first + r, 0), W - 1)) * p.s[2];
+        float v[5];
+#pragma unroll
+        for (int i = 0; i < 5; ++i) v[i] = static_cast<float>(__ldg(row + xo[i])) * ps;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float lx = (g == 0 && j == 0) ? 0.0f : kL[j];   // the left edge clamps the source coordinate to 0
+            H[r][j] = (1.0f - lx) * v[kI[j]] + lx * v[kI[j] + 1];
+        }
+    }
+    const float mean = p.normalize ? kClipMean[c] : 0.0f, istd = p.normalize ? kClipInvStd[c] : 1.0f;
+    const int gx = g >> 2, kx0 = (g & 3) * 8;
+    __nv_bfloat16* dst = p.out + (static_cast<size_t>(b) * G * G + gy * G + gx) * p.kpad + (c * P + 8 * q) * P + kx0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {                              // output row ky = 8q + j
+        const float ly = (gy == 0 && q == 0 && j == 0) ? 0.0f : kL[j];
+        const float h0 = 1.0f - ly;
+        uint32_t pk[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float o0 = (h0 * H[kI[j]][2 * e] + ly * H[kI[j] + 1][2 * e] - mean) * istd;
+            const float o1 = (h0 * H[kI[j]][2 * e + 1] + ly * H[kI[j] + 1][2 * e + 1] - mean) * istd;
+            __nv_bfloat162 h = __floats2bfloat162_rn(o0, o1);
+            pk[e] = *reinterpret_cast<uint32_t*>(&h);
+        }
+        *reinterpret_cast<uint4*>(dst + j * P) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
     }
 }
 
@@ -224,6 +285,9 @@ int preprocess_launch(const void* images, int img_dtype, const long long strides
     const size_t rs_smem = static_cast<size_t>(C) * max_rows * image * sizeof(float);
     if (ident) {
         preprocess_kernel<8, true><<<grid, 256, 0, stream>>>(p);
+    } else if (vec8 && h == 84 && w == 84 && image == 224 && patch == 32 && !getenv("CLIPPPO_PREPROCESS_GENERIC")) {
+        if (img_dtype == CLIPPPO_IMG_U8) preprocess_up84_kernel<CLIPPPO_IMG_U8><<<grid, 352, 0, stream>>>(p);
+        else preprocess_up84_kernel<CLIPPPO_IMG_F32><<<grid, 352, 0, stream>>>(p);
     } else if (vec8 && image % 8 == 0 && rs_smem <= 200 * 1024) {
         static DeviceOnce configured;
         if (rs_smem > 48 * 1024 && configured.first_use())
