@@ -104,7 +104,8 @@ class TextEngine:
         out = torch.empty((n, self.cfg.out_dim), dtype=torch.float32, device=self.device)
         if n == 0:
             return out
-        if int(tokens.min()) < 0 or int(tokens.max()) >= self.cfg.vocab:      # nn.Embedding's IndexError, raised on the host
+        lo, hi = (int(v) for v in torch.stack(torch.aminmax(tokens)).tolist())      # one read-back for both bounds
+        if lo < 0 or hi >= self.cfg.vocab:                                          # nn.Embedding's IndexError, raised on the host
             raise IndexError(f"token id out of range [0, {self.cfg.vocab})")
         tok = tokens.to(torch.int32).contiguous()
         ws = self._workspace_for(n)
