@@ -32,8 +32,13 @@ import torch
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 REF = "/root/reference"
-OUT = os.path.join(ROOT, "tests", "golden")
+OUT = os.environ.get("CLIPPPO_GOLDEN_OUT", os.path.join(ROOT, "tests", "golden"))
 sys.path.insert(0, ROOT)
+# `shared` must mean the REFERENCE's directory here, not this repository's drop-in package of the same name
+# (a regular package, which would win over the reference's namespace package): pin the name to /root/reference/shared.
+_ref_shared = types.ModuleType("shared")
+_ref_shared.__path__ = [os.path.join(REF, "shared")]
+sys.modules["shared"] = _ref_shared
 
 from oracle import disturb as od  # noqa: E402
 from oracle import vit as ov  # noqa: E402

@@ -176,3 +176,39 @@ def test_single_forward_latents_equal_the_scripts_second_forward():
     assert agent.calls == 1
     assert torch.equal(lp, lp2) and torch.equal(ent, ent2) and torch.equal(val, val2) and torch.equal(lat, lat2)
     assert not lat2.requires_grad and lp2.requires_grad
+
+
+def test_dropin_import_resolution_with_the_scripts_sys_path_hacks(tmp_path):
+    """PYTHONPATH=<this repo> against a reference-shaped tree: the scripts put their root and their `shared/`
+    directory at the FRONT of sys.path (clip_ppo_minigrid.py:22-29) and import `clip_ppo_utils` as a top-level
+    module.  This repository's modules must win for the three names it replaces, the reference's other `shared.*`
+    modules (the cv2 twin, checkpoint utils) must stay importable."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    ref = tmp_path / "ref"
+    (ref / "shared").mkdir(parents=True)                       # namespace package: no __init__.py, like the reference
+    (ref / "exp" / "clip").mkdir(parents=True)
+    (ref / "shared" / "clip_ppo_utils.py").write_text("WHO = 'reference'\n")
+    (ref / "shared" / "disturbances_gpu.py").write_text("WHO = 'reference'\n")
+    (ref / "shared" / "disturbances.py").write_text("from shared.disturbance_types import DisturbanceSeverity\nWHO = 'cv2 twin'\n")
+    (ref / "shared" / "checkpoint_utils.py").write_text("WHO = 'reference'\n")
+    (ref / "exp" / "clip" / "script.py").write_text(
+        "import os, sys\n"
+        "sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))\n"
+        "sys.path.insert(0, os.path.join(os.path.dirname(__file__), '..', '..', 'shared'))\n"
+        "import clip_ppo_utils\n"
+        "from shared.disturbances_gpu import DisturbanceWrapperGPU\n"
+        "from shared.disturbance_types import DisturbanceSeverity\n"
+        "from shared import disturbances\n"
+        "import shared.checkpoint_utils as ck\n"
+        "import shared.clip_ppo_utils as U2\n"
+        "print(clip_ppo_utils.__file__); print(sys.modules['shared.disturbances_gpu'].__file__)\n"
+        "print(disturbances.WHO, ck.WHO, clip_ppo_utils is U2, clip_ppo_utils.__name__, hasattr(clip_ppo_utils, 'generate_clip_embeddings'))\n")
+    env = dict(os.environ, PYTHONPATH=root)
+    out = subprocess.run([sys.executable, str(ref / "exp" / "clip" / "script.py")], capture_output=True, text=True, env=env, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = out.stdout.strip().splitlines()
+    assert lines[0] == os.path.join(root, "shared", "clip_ppo_utils.py")
+    assert lines[1] == os.path.join(root, "shared", "disturbances_gpu.py")
+    assert lines[2] == "cv2 twin reference True shared.clip_ppo_utils True"
