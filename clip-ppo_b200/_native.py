@@ -25,7 +25,7 @@ EPI_BIAS_BF16, EPI_BIAS_GELU_BF16, EPI_BIAS_RESID_F32, EPI_PATCH_F32, EPI_F32 = 
 # every symbol the header declares; tests/test_abi.py checks the .so exports all of them
 SYMBOLS = (
     "clipppo_abi_version", "clipppo_strerror", "clipppo_last_cuda_error", "clipppo_prof_begin", "clipppo_prof_end", "clipppo_prof_bucket",
-    "clipppo_disturb_f32", "clipppo_disturb_nhwc_u8",
+    "clipppo_disturb_f32", "clipppo_disturb_u8_f32", "clipppo_disturb_nhwc_u8",
     "clipppo_cosine_loss_fwd", "clipppo_cosine_loss_bwd", "clipppo_gae_f32", "clipppo_ppo_loss_f32",
     "clipppo_vit_create", "clipppo_vit_destroy", "clipppo_vit_workspace_bytes", "clipppo_vit_encode",
     "clipppo_text_create", "clipppo_text_destroy", "clipppo_text_workspace_bytes", "clipppo_text_encode",
@@ -83,6 +83,7 @@ def lib() -> C.CDLL:
     L.clipppo_prof_bucket.argtypes = [i, C.POINTER(C.c_longlong), C.POINTER(d), C.POINTER(d), C.POINTER(C.c_longlong)]
     L.clipppo_prof_end.argtypes = [C.POINTER(C.c_longlong), C.POINTER(d), C.POINTER(d), C.POINTER(C.c_longlong)]
     L.clipppo_disturb_f32.argtypes = [vp, i64p, vp, i64p, vp, i, i, i, i, i, f, f, fp, i, i, i, i, i, vp]
+    L.clipppo_disturb_u8_f32.argtypes = [vp, vp, vp, i, i, i, i, i, f, f, fp, i, i, i, i, i, vp]
     L.clipppo_disturb_nhwc_u8.argtypes = [vp, i, vp, i64p, vp, i, i, i, i, i, f, f, fp, i, i, i, i, i, vp]
     L.clipppo_cosine_loss_fwd.argtypes = [vp, vp, i, i, vp, vp, vp]
     L.clipppo_cosine_loss_bwd.argtypes = [vp, vp, vp, vp, i, i, vp, vp, vp]

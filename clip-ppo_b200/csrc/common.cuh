@@ -113,6 +113,23 @@ __device__ __forceinline__ float4 ld_stream_f4(const float* p) {
                  : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
     return r;
 }
+__device__ __forceinline__ unsigned ld_stream_u32(const void* p) {
+    unsigned r;
+    asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(r) : "l"(p));
+    return r;
+}
+// Four uint8 pixels -> what `obs.float() / 255` gives ON THE DEVICE: ATen divides a CUDA tensor by a host scalar
+// as a multiplication by fl(1 / 255) (BinaryDivTrueKernel.cu), which differs from the IEEE quotient in the last bit for
+// 126 of the 256 byte values.  No int->float conversion instruction: 0x4B0000vv is the float 2^23 + v.
+__device__ __forceinline__ float4 u8x4_over_255(unsigned w) {
+    const float r = 1.0f / 255.0f;
+    float4 o;
+    float* op = &o.x;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+        op[i] = __fmul_rn(__uint_as_float(__byte_perm(w, 0x4B000000u, 0x7540 | i)) - 8388608.0f, r);
+    return o;
+}
 __device__ __forceinline__ void st_stream_f4(float* p, float4 v) {
     asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};"
                  :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");

@@ -43,6 +43,7 @@ struct DisturbParams {
     int S, R;       // stripes per image (= cluster size), rows per stripe
     int nsplit;     // row splits of a stripe in the blur phase (balances the 4-column tasks over the CTA)
     int fast;       // x / noise contiguous NCHW fp32, W % 4 == 0, 16-byte aligned
+    int x_u8;       // fast path only: x holds uint8 pixels (contiguous NCHW), read as float(v) / 255
     int io_mode;    // 0: fp32 strided in, fp32 NCHW out.  1: u8 NHWC in / u8 NHWC out.
                     // 2: fp32 (0..255) NHWC in / u8 NHWC out.
     int nthreads;   // fast path: CTA size (covers the blur tasks in one round when it can)
@@ -205,7 +206,7 @@ __device__ __forceinline__ void hfilter4p(const float* __restrict__ rowq, const 
 // One image = one cluster of S stripe-CTAs (S = 1: a plain CTA).  The only cluster-wide dependency is
 // the per-image gray mean of the contrast stage: one barrier, with the halo-row loads between its
 // ARRIVE and its WAIT.
-template <int K, int WT>
+template <int K, int WT, bool XU8>
 __global__ void __launch_bounds__(kFastMaxThreads, 2)
 disturb_fast_kernel(const __grid_constant__ DisturbParams p) {
     constexpr int P = K / 2;
@@ -251,8 +252,10 @@ disturb_fast_kernel(const __grid_constant__ DisturbParams p) {
     auto load_own_c = [&](auto ct_c, auto uj_c, int c_first) {
         constexpr int CT = decltype(ct_c)::value, UJ = decltype(uj_c)::value;
         const size_t img_off = static_cast<size_t>(b) * C * H * W;
-        const float* xs = static_cast<const float*>(p.x) + img_off + c_first * HW + r0 * W;
-        const float* ns = do_noise ? p.noise + img_off + c_first * HW + r0 * W : xs;
+        constexpr bool xu8 = XU8;                        // uint8 frames (a template flag: as a run-time branch it cost the fp32 path 10 %): element offsets are byte offsets
+        const float* xs = xu8 ? reinterpret_cast<const float*>(static_cast<const uint8_t*>(p.x) + img_off + c_first * HW + r0 * W)
+                              : static_cast<const float*>(p.x) + img_off + c_first * HW + r0 * W;
+        const float* ns = do_noise ? p.noise + img_off + c_first * HW + r0 * W : static_cast<const float*>(p.x);
         asm volatile("" : "+l"(xs), "+l"(ns));           // keep the two bases in registers (no rematerialisation)
         float* const tile0 = tile + c_first * plane + P * WP + kPad;      // first own row, first real column
         float gs[CT];
@@ -266,7 +269,8 @@ disturb_fast_kernel(const __grid_constant__ DisturbParams p) {
                 if (j < n4) {
 #pragma unroll
                     for (int c_ = 0; c_ < CT; ++c_) {
-                        xv[u][c_] = ld_stream_f4(xs + c_ * HW + 4 * j);
+                        if constexpr (xu8) xv[u][c_].x = __uint_as_float(ld_stream_u32(reinterpret_cast<const uint8_t*>(xs) + c_ * HW + 4 * j));
+                        else xv[u][c_] = ld_stream_f4(xs + c_ * HW + 4 * j);
                         if (do_noise) nv[u][c_] = ld_stream_f4(ns + c_ * HW + 4 * j);
                     }
                 }
@@ -278,6 +282,7 @@ disturb_fast_kernel(const __grid_constant__ DisturbParams p) {
                     float* dst = tile0 + 4 * j + 2 * kPad * div_nq(j);    // row * WP + 4 * quad, with 4 j = row * W + 4 * quad
 #pragma unroll
                     for (int c_ = 0; c_ < CT; ++c_) {
+                        if constexpr (xu8) xv[u][c_] = u8x4_over_255(__float_as_uint(xv[u][c_].x));
                         const float4 v = noisy4(xv[u][c_], nv[u][c_]);
                         gs[c_] += (v.x + v.y) + (v.z + v.w);
                         *reinterpret_cast<float4*>(dst + c_ * plane) = v;
@@ -300,8 +305,10 @@ disturb_fast_kernel(const __grid_constant__ DisturbParams p) {
     // not part of the gray sum, so they load between the ARRIVE and the WAIT of the mean barrier.
     auto load_halo = [&]() {
         const size_t img_off = static_cast<size_t>(b) * C * H * W;
-        const float* __restrict__ xi = static_cast<const float*>(p.x) + img_off;
-        const float* __restrict__ ni = do_noise ? p.noise + img_off : xi;
+        constexpr bool xu8 = XU8;
+        const float* __restrict__ xi = static_cast<const float*>(p.x) + (xu8 ? 0 : img_off);
+        const uint8_t* __restrict__ xb = static_cast<const uint8_t*>(p.x) + img_off;
+        const float* __restrict__ ni = do_noise ? p.noise + img_off : static_cast<const float*>(p.x);
         if constexpr (K > 1) {
             const int nh4 = rows > 0 ? C * 2 * P * nq : 0;
             for (int i = tid; i < nh4; i += nth) {
@@ -312,7 +319,7 @@ disturb_fast_kernel(const __grid_constant__ DisturbParams p) {
                 if (ir < 0) ir = -ir;
                 if (ir >= H) ir = 2 * (H - 1) - ir;
                 const int goff = c_ * HW + ir * W + 4 * quad;
-                const float4 xv = ld_stream_f4(xi + goff);
+                const float4 xv = xu8 ? u8x4_over_255(ld_stream_u32(xb + goff)) : ld_stream_f4(xi + goff);
                 float4 nv = xv;
                 if (do_noise) nv = ld_stream_f4(ni + goff);
                 *reinterpret_cast<float4*>(tile + c_ * plane + lr * WP + kPad + 4 * quad) = noisy4(xv, nv);
@@ -695,12 +702,12 @@ static int launch_disturb(const DisturbParams& p, size_t smem, cudaStream_t stre
     return CLIPPPO_OK;
 }
 
-template <int K, int WT>
-static int launch_disturb_fast_w(const DisturbParams& p, size_t smem, cudaStream_t stream) {
+template <int K, int WT, bool XU8>
+static int launch_disturb_fast_x(const DisturbParams& p, size_t smem, cudaStream_t stream) {
     static DeviceOnce configured;
     if (configured.first_use()) {
-        CLIPPPO_CUDA_TRY(cudaFuncSetAttribute(disturb_fast_kernel<K, WT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        CLIPPPO_CUDA_TRY(cudaFuncSetAttribute(disturb_fast_kernel<K, WT>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        CLIPPPO_CUDA_TRY(cudaFuncSetAttribute(disturb_fast_kernel<K, WT, XU8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        CLIPPPO_CUDA_TRY(cudaFuncSetAttribute(disturb_fast_kernel<K, WT, XU8>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(static_cast<unsigned>(p.B) * p.S);
@@ -715,9 +722,14 @@ static int launch_disturb_fast_w(const DisturbParams& p, size_t smem, cudaStream
     cfg.attrs = attr;
     // without the contrast stage the stripes of an image are independent: plain CTAs, no gang scheduling
     cfg.numAttrs = ((p.stages & CLIPPPO_STAGE_CONTRAST) && p.S > 1) ? 1 : 0;
-    CLIPPPO_CUDA_TRY(cudaLaunchKernelEx(&cfg, disturb_fast_kernel<K, WT>, p));
+    CLIPPPO_CUDA_TRY(cudaLaunchKernelEx(&cfg, disturb_fast_kernel<K, WT, XU8>, p));
     prof_count_launch();
     return CLIPPPO_OK;
+}
+
+template <int K, int WT>
+static int launch_disturb_fast_w(const DisturbParams& p, size_t smem, cudaStream_t stream) {
+    return p.x_u8 ? launch_disturb_fast_x<K, WT, true>(p, smem, stream) : launch_disturb_fast_x<K, WT, false>(p, smem, stream);
 }
 
 template <int K>
@@ -768,6 +780,7 @@ static int run_disturb(DisturbParams& p, const float* k1d_host, int k, cudaStrea
         if (p.sh < 0 || p.sw < 0 || p.ph < 0 || p.pw < 0) return CLIPPPO_ERR_BAD_SHAPE;
     }
     const int P = K / 2;
+    if (p.x_u8 && !(p.fast && p.io_mode == 0 && K <= 7 && p.W >= 8)) return CLIPPPO_ERR_UNSUPPORTED;   // uint8 frames: fast kernel only
     if (p.fast && p.io_mode == 0 && K <= 7 && p.W >= 8) {
         // ---- fast path (disturb_fast_kernel): padded smem rows ----
         static const int env_nsplit = env_int("CLIPPPO_DISTURB_NSPLIT", 0);
@@ -908,6 +921,29 @@ extern "C" int clipppo_disturb_f32(const float* x, const int64_t x_strides_host[
     p.fast = is_contig_nchw(p.xs, C, H, W) && (!need_noise || is_contig_nchw(p.ns, C, H, W)) &&
              (W % 4 == 0) && (reinterpret_cast<uintptr_t>(x) % 16 == 0) &&
              (!need_noise || reinterpret_cast<uintptr_t>(noise) % 16 == 0);
+    return run_disturb(p, k1d_host, k, as_stream(stream));
+}
+
+extern "C" int clipppo_disturb_u8_f32(const uint8_t* x, const float* noise, float* out, int B, int C, int H, int W, int stages,
+                                      float noise_sigma, float contrast, const float* k1d_host, int k,
+                                      int sh, int sw, int ph, int pw, clipppo_stream_t stream) {
+    DisturbParams p = {};
+    p.x = x; p.noise = noise; p.out = out;
+    p.B = B; p.C = C; p.H = H; p.W = W;
+    if (B <= 0 || C <= 0 || H <= 0 || W <= 0) return CLIPPPO_ERR_BAD_SHAPE;
+    const long long dflt[4] = {(long long)C * H * W, (long long)H * W, W, 1};
+    for (int i = 0; i < 4; ++i) { p.xs[i] = dflt[i]; p.ns[i] = dflt[i]; }
+    p.stages = stages & CLIPPPO_STAGE_ALL;
+    p.sigma_n = noise_sigma;
+    p.c = contrast;
+    p.omc = static_cast<float>(1.0 - static_cast<double>(contrast));
+    p.sh = sh; p.sw = sw; p.ph = ph; p.pw = pw;
+    p.io_mode = 0;
+    p.x_u8 = 1;
+    const bool need_noise = (p.stages & CLIPPPO_STAGE_NOISE) != 0;
+    if ((W % 4) || (reinterpret_cast<uintptr_t>(x) % 4)) return CLIPPPO_ERR_UNSUPPORTED;
+    if (need_noise && noise && (reinterpret_cast<uintptr_t>(noise) % 16)) return CLIPPPO_ERR_ALIGN;
+    p.fast = 1;
     return run_disturb(p, k1d_host, k, as_stream(stream));
 }
 

@@ -54,10 +54,17 @@ def fused_disturb(x: torch.Tensor, *, stages: int, noise: Optional[torch.Tensor]
                   taps: Optional[Sequence[float]] = None,
                   window: Tuple[int, int, int, int] = (0, 0, 0, 0)) -> torch.Tensor:
     """out[B,C,H,W] fp32 (contiguous) = cutout(blur(contrast(noise(x)))) restricted to `stages`.
-    x may have arbitrary strides (e.g. the NHWC view of clip_ppo_minigrid.py:385)."""
+    x may have arbitrary strides (e.g. the NHWC view of clip_ppo_minigrid.py:385).  uint8 x (additive): pixels
+    0..255 are read as float(v) * fl(1/255), bit-identical to `x.float() / 255` evaluated by PyTorch on the device,
+    without materialising the fp32 batch."""
     _require_cuda(x, "fused_disturb")
     if x.dim() != 4:
         raise ValueError(f"expected [B,C,H,W], got shape {tuple(x.shape)}")
+    if x.dtype == torch.uint8:
+        out = _fused_disturb_u8(x, stages, noise, noise_sigma, contrast, taps, window)
+        if out is not None:
+            return out
+        x = x.float() / 255.0                       # shapes outside the fast kernel: convert, then the general path
     if x.dtype != torch.float32:
         x = x.float()
     B, Cc, H, W = x.shape
@@ -80,6 +87,35 @@ def fused_disturb(x: torch.Tensor, *, stages: int, noise: Optional[torch.Tensor]
             float(noise_sigma), float(contrast), taps_arr, k, int(sh), int(sw), int(ph), int(pw),
             _stream_ptr(x))
     N.check(st, "clipppo_disturb_f32")
+    return out
+
+
+def _fused_disturb_u8(x, stages, noise, noise_sigma, contrast, taps, window) -> Optional[torch.Tensor]:
+    """uint8 contiguous NCHW frames through clipppo_disturb_u8_f32; None when that entry point does not serve the shape."""
+    B, Cc, H, W = x.shape
+    if not x.is_contiguous() or W % 4:
+        return None
+    nptr = None
+    if stages & N.STAGE_NOISE:
+        if noise is None:
+            raise ValueError("noise stage needs a noise tensor")
+        if noise.shape != x.shape or noise.dtype != torch.float32 or noise.device != x.device:
+            raise ValueError("noise must match x in shape and device, dtype fp32")
+        if not noise.is_contiguous():
+            return None
+        nptr = noise.data_ptr()
+    out = torch.empty((B, Cc, H, W), dtype=torch.float32, device=x.device)
+    if B == 0:
+        return out
+    k = len(taps) if (stages & N.STAGE_BLUR) else 0
+    taps_arr = (C.c_float * max(k, 1))(*(taps if k else (1.0,)))
+    sh, sw, ph, pw = window
+    with N.device_ctx(x.device):
+        st = N.lib().clipppo_disturb_u8_f32(x.data_ptr(), nptr, out.data_ptr(), B, Cc, H, W, stages, float(noise_sigma),
+                                            float(contrast), taps_arr, k, int(sh), int(sw), int(ph), int(pw), _stream_ptr(x))
+    if st == N.ERR_UNSUPPORTED:
+        return None
+    N.check(st, "clipppo_disturb_u8_f32")
     return out
 
 

@@ -79,6 +79,15 @@ int clipppo_disturb_f32(const float* x, const int64_t x_strides_host[4],
                         int sh, int sw, int ph, int pw,
                         clipppo_stream_t stream);
 
+/* The same chain on uint8 frames [B,C,H,W] (contiguous): every pixel is read as float(v) * fl(1/255), which is what
+ * the reference's `.float() / 255` evaluates to on a CUDA tensor (benchmark_disturbances.py:59, the call sites'
+ * `/255`; ATen divides by a host scalar as a multiplication by its reciprocal), so the fp32 copy of the batch is
+ * never materialised.  noise is contiguous fp32 [B,C,H,W]; out is contiguous fp32.  Served by the fast
+ * kernel only (W % 4 == 0, k <= 7): anything else returns CLIPPPO_ERR_UNSUPPORTED and the caller converts first. */
+int clipppo_disturb_u8_f32(const uint8_t* x, const float* noise, float* out, int B, int C, int H, int W, int stages,
+                           float noise_sigma, float contrast, const float* k1d_host, int k,
+                           int sh, int sw, int ph, int pw, clipppo_stream_t stream);
+
 /* Same chain for the MiniGrid env-step call site (clip_ppo_minigrid.py:381-388) and the *_numpy
  * shims (shared/disturbances_gpu.py:75-95): NHWC frames in (uint8, or fp32 holding 0..255),
  * `/255`, disturb, `*255`, truncate to uint8 NHWC.  noise is fp32, logical [B,C,H,W] with the

@@ -114,9 +114,11 @@ class DisturbanceWrapperGPU:
     def apply_disturbances(self, obs: torch.Tensor, *, noise: Optional[torch.Tensor] = None,
                            contrast_factor: Optional[float] = None,
                            cutout_start: Optional[Tuple[int, int]] = None) -> torch.Tensor:
-        """noise -> contrast -> blur -> cutout (reference :66-73), one fused launch."""
+        """noise -> contrast -> blur -> cutout (reference :66-73), one fused launch.  Additive: uint8 `obs` holds
+        0..255 pixels and equals `apply_disturbances(obs.float() / 255)` bit for bit (same RNG consumption)."""
         if noise is None:
-            noise = torch.randn_like(obs)
+            noise = torch.randn_like(obs) if obs.dtype != torch.uint8 else \
+                torch.randn(obs.shape, dtype=torch.float32, device=obs.device)
         c = self._draw_contrast() if contrast_factor is None else float(contrast_factor)
         taps = self._draw_blur_taps()
         window = self._draw_cutout(obs.shape[-2], obs.shape[-1], cutout_start)

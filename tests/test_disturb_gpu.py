@@ -166,6 +166,34 @@ def test_env_step_batches_run_as_stripe_clusters(native, B, C, sev):
     assert (big[:B] - out_c).abs().max().item() <= 1e-6
 
 
+def test_uint8_frames_equal_the_float_path_bitwise(native):
+    """Additive: uint8 [B,C,H,W] input is converted inside the kernel - bit-identical to handing over
+    `obs.float() / 255` computed by PyTorch on the device (the reference benchmark's conversion; ATen multiplies by
+    fl(1/255) there), for every byte value and every dispatch variant."""
+    from clip_ppo_b200 import disturb as D, _native as Nn
+    # all 256 byte values through the load path alone (cutout stage with an empty window = copy)
+    ramp = torch.arange(256, dtype=torch.uint8, device="cuda").reshape(1, 1, 8, 32)
+    out = D.fused_disturb(ramp, stages=Nn.STAGE_CUTOUT, window=(0, 0, 0, 0))
+    assert torch.equal(out, ramp.float() / 255.0)
+    gen = torch.Generator(device="cuda").manual_seed(12)
+    for shape, sev in (((5, 3, 224, 224), "MODERATE"), ((2, 3, 224, 224), "SEVERE"), ((200, 3, 84, 84), "HARD"),
+                       ((8, 3, 84, 84), "MODERATE"), ((160, 1, 84, 84), "SEVERE"), ((3, 3, 84, 86), "MILD"), ((2, 3, 61, 61), "HARD")):
+        u8 = torch.randint(0, 256, shape, device="cuda", generator=gen, dtype=torch.uint8)
+        noise = torch.randn(shape, device="cuda", generator=gen)
+        w = _wrapper(sev)
+        a = w.apply_disturbances(u8, noise=noise, contrast_factor=1.17, cutout_start=(4, 9))
+        b = w.apply_disturbances(u8.float() / 255.0, noise=noise, contrast_factor=1.17, cutout_start=(4, 9))
+        assert a.dtype == torch.float32 and torch.equal(a, b), (shape, sev, (a - b).abs().max().item())
+    # default randomness: same seed, same draws as the float call
+    u8 = torch.randint(0, 256, (6, 3, 84, 84), device="cuda", generator=gen, dtype=torch.uint8)
+    w = _wrapper("MODERATE")
+    torch.manual_seed(5)
+    a = w.apply_disturbances(u8)
+    torch.manual_seed(5)
+    b = w.apply_disturbances(u8.float() / 255.0)
+    assert torch.equal(a, b)
+
+
 def test_wide_blur_kernels_use_the_general_kernel(native):
     """Custom sigma: k = 9 .. 15 taps are outside the fast path's register ring."""
     from shared.disturbances_gpu import DisturbanceWrapperGPU
