@@ -42,7 +42,9 @@ struct DisturbParams {
     int sh, sw, ph, pw;
     int S, R;       // stripes per image (= cluster size), rows per stripe
     int nsplit;     // row splits of a stripe in the blur phase (balances the 4-column tasks over the CTA)
-    int fast;       // x / noise contiguous NCHW fp32, W % 4 == 0, 16-byte aligned
+    int fast;       // x / noise: every image a contiguous [C,H,W] fp32 block (any batch stride that is a multiple of 4
+                    // elements, e.g. one frame of an Atari stack), W % 4 == 0, 16-byte aligned
+    int batch_contig;  // ... and the images back to back (what the general kernel's vector path assumes)
     int x_u8;       // fast path only: x holds uint8 pixels (contiguous NCHW), read as float(v) / 255
     int io_mode;    // 0: fp32 strided in, fp32 NCHW out.  1: u8 NHWC in / u8 NHWC out.
                     // 2: fp32 (0..255) NHWC in / u8 NHWC out.
@@ -251,11 +253,11 @@ disturb_fast_kernel(const __grid_constant__ DisturbParams p) {
     // per thread and trip (12 independent 128-bit loads in flight), no serial tail.
     auto load_own_c = [&](auto ct_c, auto uj_c, int c_first) {
         constexpr int CT = decltype(ct_c)::value, UJ = decltype(uj_c)::value;
-        const size_t img_off = static_cast<size_t>(b) * C * H * W;
+        const size_t x_off = static_cast<size_t>(b) * p.xs[0], n_off = static_cast<size_t>(b) * p.ns[0];   // batch strides (elements)
         constexpr bool xu8 = XU8;                        // uint8 frames (a template flag: as a run-time branch it cost the fp32 path 10 %): element offsets are byte offsets
-        const float* xs = xu8 ? reinterpret_cast<const float*>(static_cast<const uint8_t*>(p.x) + img_off + c_first * HW + r0 * W)
-                              : static_cast<const float*>(p.x) + img_off + c_first * HW + r0 * W;
-        const float* ns = do_noise ? p.noise + img_off + c_first * HW + r0 * W : static_cast<const float*>(p.x);
+        const float* xs = xu8 ? reinterpret_cast<const float*>(static_cast<const uint8_t*>(p.x) + x_off + c_first * HW + r0 * W)
+                              : static_cast<const float*>(p.x) + x_off + c_first * HW + r0 * W;
+        const float* ns = do_noise ? p.noise + n_off + c_first * HW + r0 * W : static_cast<const float*>(p.x);
         asm volatile("" : "+l"(xs), "+l"(ns));           // keep the two bases in registers (no rematerialisation)
         float* const tile0 = tile + c_first * plane + P * WP + kPad;      // first own row, first real column
         float gs[CT];
@@ -304,11 +306,11 @@ disturb_fast_kernel(const __grid_constant__ DisturbParams p) {
     // memory - 2P/R more (mostly L2-resident) reads, but no cluster barrier before the blur.  They are
     // not part of the gray sum, so they load between the ARRIVE and the WAIT of the mean barrier.
     auto load_halo = [&]() {
-        const size_t img_off = static_cast<size_t>(b) * C * H * W;
+        const size_t x_off = static_cast<size_t>(b) * p.xs[0], n_off = static_cast<size_t>(b) * p.ns[0];   // batch strides (elements)
         constexpr bool xu8 = XU8;
-        const float* __restrict__ xi = static_cast<const float*>(p.x) + (xu8 ? 0 : img_off);
-        const uint8_t* __restrict__ xb = static_cast<const uint8_t*>(p.x) + img_off;
-        const float* __restrict__ ni = do_noise ? p.noise + img_off : static_cast<const float*>(p.x);
+        const float* __restrict__ xi = static_cast<const float*>(p.x) + (xu8 ? 0 : x_off);
+        const uint8_t* __restrict__ xb = static_cast<const uint8_t*>(p.x) + x_off;
+        const float* __restrict__ ni = do_noise ? p.noise + n_off : static_cast<const float*>(p.x);
         if constexpr (K > 1) {
             const int nh4 = rows > 0 ? C * 2 * P * nq : 0;
             for (int i = tid; i < nh4; i += nth) {
@@ -475,7 +477,7 @@ disturb_kernel(const __grid_constant__ DisturbParams p) {
 
     // ---- phase 1: stripe -> smem -----------------------------------------------------------
     float gsum = 0.0f;
-    if (p.fast) {
+    if (p.fast && p.batch_contig) {
         const int n4 = (rows * W) >> 2;       // float4 per channel of this stripe (contiguous in global)
         constexpr int UNR = 4;
         for (int c_ = 0; c_ < C; ++c_) {
@@ -891,6 +893,11 @@ static int run_disturb(DisturbParams& p, const float* k1d_host, int k, cudaStrea
 static bool is_contig_nchw(const long long s[4], int C, int H, int W) {
     return s[3] == 1 && s[2] == W && s[1] == (long long)H * W && s[0] == (long long)C * H * W;
 }
+// every image one contiguous [C,H,W] block; the images may sit at any non-overlapping, 16-byte-aligned distance
+static bool is_image_contig(const long long s[4], int B, int C, int H, int W) {
+    return s[3] == 1 && s[2] == W && (C == 1 || s[1] == (long long)H * W) &&
+           (B == 1 || (s[0] >= (long long)C * H * W && s[0] % 4 == 0));
+}
 
 }  // namespace clipppo
 
@@ -918,7 +925,8 @@ extern "C" int clipppo_disturb_f32(const float* x, const int64_t x_strides_host[
     p.sh = sh; p.sw = sw; p.ph = ph; p.pw = pw;
     p.io_mode = 0;
     const bool need_noise = (p.stages & CLIPPPO_STAGE_NOISE) != 0;
-    p.fast = is_contig_nchw(p.xs, C, H, W) && (!need_noise || is_contig_nchw(p.ns, C, H, W)) &&
+    p.batch_contig = is_contig_nchw(p.xs, C, H, W) && (!need_noise || is_contig_nchw(p.ns, C, H, W));
+    p.fast = is_image_contig(p.xs, B, C, H, W) && (!need_noise || is_image_contig(p.ns, B, C, H, W)) &&
              (W % 4 == 0) && (reinterpret_cast<uintptr_t>(x) % 16 == 0) &&
              (!need_noise || reinterpret_cast<uintptr_t>(noise) % 16 == 0);
     return run_disturb(p, k1d_host, k, as_stream(stream));
@@ -944,6 +952,7 @@ extern "C" int clipppo_disturb_u8_f32(const uint8_t* x, const float* noise, floa
     if ((W % 4) || (reinterpret_cast<uintptr_t>(x) % 4)) return CLIPPPO_ERR_UNSUPPORTED;
     if (need_noise && noise && (reinterpret_cast<uintptr_t>(noise) % 16)) return CLIPPPO_ERR_ALIGN;
     p.fast = 1;
+    p.batch_contig = 1;
     return run_disturb(p, k1d_host, k, as_stream(stream));
 }
 

@@ -194,6 +194,34 @@ def test_uint8_frames_equal_the_float_path_bitwise(native):
     assert torch.equal(a, b)
 
 
+@pytest.mark.parametrize("E", [8, 256])
+def test_atari_stack_frames_take_the_fast_kernel(native, E):
+    """clip_ppo_atari.py:568-584 disturbs each of the 4 stacked frames as `x[:, f:f+1]`: [E,1,84,84] views whose images
+    are contiguous but 4 frames apart.  They run through the same kernel as a contiguous copy (bitwise the same result)."""
+    from clip_ppo_b200 import rollout
+    gen = torch.Generator(device="cuda").manual_seed(E)
+    stack = torch.rand(E, 4, 84, 84, device="cuda", generator=gen)
+    noise = torch.randn(E, 1, 84, 84, device="cuda", generator=gen)
+    w = _wrapper("HARD")
+    for f in (0, 3):
+        view = stack[:, f:f + 1]
+        assert not view.is_contiguous() or E == 1
+        a = w.apply_disturbances(view, noise=noise, contrast_factor=0.8, cutout_start=(20, 7))
+        b = w.apply_disturbances(view.contiguous(), noise=noise, contrast_factor=0.8, cutout_start=(20, 7))
+        assert torch.equal(a, b)
+    cfg = od.SEVERITY_TABLE["HARD"]
+    ph, pw = od.cutout_patch(84, 84, cfg["cutout"])
+    k1d = od.gaussian_kernel1d(od.blur_kernel_size(cfg["blur_sigma"]), float(torch.tensor(cfg["blur_sigma"], dtype=torch.float32)))
+    ref = od.disturb(stack[:4, 3:4].cpu().contiguous(), noise[:4].cpu(), cfg["noise_sigma"], 0.8, k1d, 20, 7, ph, pw)
+    assert (a[:4].cpu() - ref).abs().max() <= TOL
+    # the whole call site: same draws, frame by frame, as the reference loop
+    torch.manual_seed(9)
+    got = rollout.disturb_atari_stack(w, stack * 255.0)
+    torch.manual_seed(9)
+    want = torch.cat([w.apply_disturbances((stack * 255.0 / 255.0)[:, f:f + 1].contiguous()) for f in range(4)], dim=1) * 255.0
+    assert torch.equal(got, want)
+
+
 def test_wide_blur_kernels_use_the_general_kernel(native):
     """Custom sigma: k = 9 .. 15 taps are outside the fast path's register ring."""
     from shared.disturbances_gpu import DisturbanceWrapperGPU

@@ -52,3 +52,20 @@ for shape, nhwc in [((8, 3, 84, 84), True), ((64, 3, 84, 84), True), ((8, 3, 84,
         torch.cuda.synchronize()
         if it >= 10: tot += e0.elapsed_time(e1)
     print(f"  {shape} {'NHWC view' if nhwc else 'contiguous'}: {tot / 20 * 1e3:.1f} us")
+
+# Atari call site: one frame of a 4-frame stack, [E,1,84,84] with the images 4 frames apart
+for E in (64, 256):
+    stack = torch.rand(E, 4, 84, 84, device="cuda")
+    x = stack[:, 1:2]
+    noise = torch.randn(E, 1, 84, 84, device="cuda")
+    taps = w._draw_blur_taps(); win = w._draw_cutout(84, 84, None)
+    tot = 0.0
+    for it in range(30):
+        torch.cuda._sleep(2_000_000)
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        D.fused_disturb(x, stages=N.STAGE_ALL, noise=noise, noise_sigma=0.13, contrast=1.1, taps=taps, window=win)
+        e1.record()
+        torch.cuda.synchronize()
+        if it >= 10: tot += e0.elapsed_time(e1)
+    print(f"  ({E}, 1, 84, 84) frame of an Atari stack (batch stride 4 frames): {tot / 20 * 1e3:.1f} us")
