@@ -113,10 +113,19 @@ def generate_clip_embeddings(
     if modality == "text":
         if descriptions is None:
             raise ValueError("descriptions required for text modality")
-        # additive: pre-tokenised [N, 77] ids are taken as they are (no tokenizer needed)
-        tokens = descriptions if isinstance(descriptions, torch.Tensor) else clip.tokenize(descriptions)
-        # encode_text -> float -> normalize, one call into the native text tower
-        return _text_engine_for(clip_model).encode(tokens.to(device), l2norm=True)
+        eng = _text_engine_for(clip_model)
+        if isinstance(descriptions, torch.Tensor):          # additive: pre-tokenised [N, 77] ids, taken as they are
+            return eng.encode(descriptions.to(device), l2norm=True)
+        # A rollout batch repeats a handful of state descriptions thousands of times (clip_ppo_minigrid.py:459-462):
+        # tokenise and encode each distinct string once and gather.  The tower is batch-invariant bit for bit, so the
+        # result equals encoding every row (tokenize -> encode_text -> float -> normalize, :136-139).
+        index = {}
+        inverse = [index.setdefault(d, len(index)) for d in descriptions]
+        tokens = clip.tokenize(list(index))
+        e = eng.encode(tokens.to(device), l2norm=True)
+        if len(index) == len(inverse):
+            return e
+        return e[torch.tensor(inverse, device=e.device)]
     if modality == "image":
         if images is None:
             raise ValueError("images required for image modality")

@@ -102,3 +102,24 @@ def test_generate_clip_embeddings_text_modality(native):
         eng.encode(torch.full((1, 77), 50000, device="cuda"))
     with pytest.raises(TypeError):
         eng.encode(torch.zeros(1, 77, device="cuda"))
+
+
+def test_repeated_descriptions_are_encoded_once(native, monkeypatch):
+    """String descriptions: distinct strings are tokenised and encoded once, rows gathered - same values as
+    encoding every row.  (The tokenizer is stubbed: the BPE merges file is not available offline.)"""
+    import shared.clip_ppo_utils as U
+    model = U.load_clip_model("ViT-B/32", "cuda")
+    vocab = {"a red door": 0, "a key": 1, "an empty room": 2}
+    table = ot.random_tokens(3, ot.TEXT_B32, seed=8)
+    calls = []
+
+    def fake_tokenize(texts, *a, **k):
+        calls.append(list(texts))
+        return table[[vocab[t] for t in texts]].clone()
+
+    monkeypatch.setattr(U.clip, "tokenize", fake_tokenize, raising=False)
+    descriptions = ["a key", "a red door", "a key", "an empty room", "a key", "a red door"] * 50
+    e = U.generate_clip_embeddings(U.AblationMode.NONE, model, "text", len(descriptions), "cuda", descriptions=descriptions)
+    assert calls == [["a key", "a red door", "an empty room"]]
+    every_row = model.text_engine().encode(table[[vocab[t] for t in descriptions]].cuda(), l2norm=True)
+    assert e.shape == (300, 512) and torch.equal(e, every_row)
