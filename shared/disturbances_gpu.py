@@ -110,6 +110,14 @@ class DisturbanceWrapperGPU:
             sh, sw = start
         return int(sh), int(sw), ph, pw
 
+    @staticmethod
+    def _noise_like(obs: torch.Tensor) -> torch.Tensor:
+        """`torch.randn_like(obs)` (reference: [tv] gaussian_noise_image); for the additive uint8 input, the noise
+        `randn_like(obs.float() / 255)` would draw - same generator consumption, same values."""
+        if obs.dtype == torch.uint8:
+            return torch.randn(obs.shape, dtype=torch.float32, device=obs.device)
+        return torch.randn_like(obs)
+
     # ---- tensor API --------------------------------------------------------------------------
     def apply_disturbances(self, obs: torch.Tensor, *, noise: Optional[torch.Tensor] = None,
                            contrast_factor: Optional[float] = None,
@@ -117,8 +125,7 @@ class DisturbanceWrapperGPU:
         """noise -> contrast -> blur -> cutout (reference :66-73), one fused launch.  Additive: uint8 `obs` holds
         0..255 pixels and equals `apply_disturbances(obs.float() / 255)` bit for bit (same RNG consumption)."""
         if noise is None:
-            noise = torch.randn_like(obs) if obs.dtype != torch.uint8 else \
-                torch.randn(obs.shape, dtype=torch.float32, device=obs.device)
+            noise = self._noise_like(obs)
         c = self._draw_contrast() if contrast_factor is None else float(contrast_factor)
         taps = self._draw_blur_taps()
         window = self._draw_cutout(obs.shape[-2], obs.shape[-1], cutout_start)
@@ -127,7 +134,7 @@ class DisturbanceWrapperGPU:
 
     def apply_gaussian_noise(self, obs: torch.Tensor, *, noise: Optional[torch.Tensor] = None) -> torch.Tensor:
         if noise is None:
-            noise = torch.randn_like(obs)
+            noise = self._noise_like(obs)
         return _D.fused_disturb(obs, stages=_N.STAGE_NOISE, noise=noise, noise_sigma=self.gaussian_noise_sigma)
 
     def apply_contrast_jitter(self, obs: torch.Tensor, *, contrast_factor: Optional[float] = None) -> torch.Tensor:
