@@ -2,9 +2,10 @@
  * clipppo_b200.h - C ABI of the B200-native CLIP-PPO observation path.
  *
  * One shared library (libclipppo_b200.so, sm_100a only).  Plain pointers and sizes, no
- * torch types.  Every entry point is asynchronous on the caller's stream, never allocates
+ * torch types.  Every per-call entry point is asynchronous on the caller's stream, never allocates
  * or frees device memory (the caller owns all buffers including workspaces) and returns
- * 0 on success or a negative clipppo_status.  Pointers are DEVICE pointers unless the
+ * 0 on success or a negative clipppo_status; only clipppo_vit_create / clipppo_text_create (and
+ * their _destroy) allocate - the handle's repacked weights - and synchronise once.  Pointers are DEVICE pointers unless the
  * parameter name ends in _host.
  *
  * Each function cites the reference interface it replaces
