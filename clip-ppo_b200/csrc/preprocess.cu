@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(256) preprocess_resize_kernel(const PreParams 
 // blends, normalise, eight 16-byte stores.  No shared memory, no barrier, ~7 instructions per output value
 // (the generic two-pass kernel: 35, bound by its load/store pipe).
 template <int DT>
-__global__ void __launch_bounds__(352) preprocess_up84_kernel(const PreParams p) {
+__global__ void __launch_bounds__(352, 3) preprocess_up84_kernel(const PreParams p) {
     constexpr int W = 84, P = 32, G = 7;
     constexpr float kL[8] = {0.6875f, 0.0625f, 0.4375f, 0.8125f, 0.1875f, 0.5625f, 0.9375f, 0.3125f};
     constexpr int kI[8] = {0, 1, 1, 1, 2, 2, 2, 3};          // first of the two source lines, relative to (3 * group - 1)
