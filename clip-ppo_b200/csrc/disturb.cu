@@ -46,6 +46,8 @@ struct DisturbParams {
                     // elements, e.g. one frame of an Atari stack), W % 4 == 0, 16-byte aligned
     int batch_contig;  // ... and the images back to back (what the general kernel's vector path assumes)
     int x_u8;       // fast path only: x holds uint8 pixels (contiguous NCHW), read as float(v) / 255
+    int nhwc;       // fast path only: x and noise are fp32 NHWC-dense views of [B,3,H,W] (strides H*W*3, 1, W*3, 3: the
+                    // MiniGrid call site and the reference benchmark); de-interleaved in registers while loading
     int io_mode;    // 0: fp32 strided in, fp32 NCHW out.  1: u8 NHWC in / u8 NHWC out.
                     // 2: fp32 (0..255) NHWC in / u8 NHWC out.
     int nthreads;   // fast path: CTA size (covers the blur tasks in one round when it can)
@@ -208,7 +210,7 @@ __device__ __forceinline__ void hfilter4p(const float* __restrict__ rowq, const 
 // One image = one cluster of S stripe-CTAs (S = 1: a plain CTA).  The only cluster-wide dependency is
 // the per-image gray mean of the contrast stage: one barrier, with the halo-row loads between its
 // ARRIVE and its WAIT.
-template <int K, int WT, bool XU8>
+template <int K, int WT, bool XU8, bool NHWC>
 __global__ void __launch_bounds__(kFastMaxThreads, 2)
 disturb_fast_kernel(const __grid_constant__ DisturbParams p) {
     constexpr int P = K / 2;
@@ -295,7 +297,54 @@ disturb_fast_kernel(const __grid_constant__ DisturbParams p) {
         if constexpr (CT == 3) return fmaf(0.114f, gs[2], fmaf(0.587f, gs[1], 0.2989f * gs[0]));
         else return gs[0];
     };
+    // NHWC-dense input: the stripe is still one contiguous run of rows * W * 3 floats; position j (row, quad) owns the 12
+    // floats at 12 j - three 128-bit loads of x and three of noise - which are the quad's four pixels of all three channels.
+    auto deinterleave = [](const float4& a, const float4& b, const float4& c, float4 (&o)[3]) {
+        o[0] = make_float4(a.x, a.w, b.z, c.y);
+        o[1] = make_float4(a.y, b.x, b.w, c.z);
+        o[2] = make_float4(a.z, b.y, c.x, c.w);
+    };
+    auto load_own_nhwc = [&]() {
+        constexpr int UJ = 2;
+        const float* xs = static_cast<const float*>(p.x) + static_cast<size_t>(b) * p.xs[0] + 3 * r0 * W;
+        const float* ns = do_noise ? p.noise + static_cast<size_t>(b) * p.ns[0] + 3 * r0 * W : xs;
+        asm volatile("" : "+l"(xs), "+l"(ns));
+        float* const tile0 = tile + P * WP + kPad;
+        float gs[3] = {0.0f, 0.0f, 0.0f};
+        for (int j0 = tid; j0 < n4; j0 += nth * UJ) {
+            float4 xv[UJ][3], nv[UJ][3];
+#pragma unroll
+            for (int u = 0; u < UJ; ++u) {
+                const int j = j0 + u * nth;
+                if (j < n4) {
+#pragma unroll
+                    for (int t = 0; t < 3; ++t) {
+                        xv[u][t] = ld_stream_f4(xs + 12 * j + 4 * t);
+                        if (do_noise) nv[u][t] = ld_stream_f4(ns + 12 * j + 4 * t);
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < UJ; ++u) {
+                const int j = j0 + u * nth;
+                if (j < n4) {
+                    float* dst = tile0 + 4 * j + 2 * kPad * div_nq(j);
+                    float4 xc[3], nc[3];
+                    deinterleave(xv[u][0], xv[u][1], xv[u][2], xc);
+                    if (do_noise) deinterleave(nv[u][0], nv[u][1], nv[u][2], nc);
+#pragma unroll
+                    for (int c_ = 0; c_ < 3; ++c_) {
+                        const float4 v = noisy4(xc[c_], nc[c_]);
+                        gs[c_] += (v.x + v.y) + (v.z + v.w);
+                        *reinterpret_cast<float4*>(dst + c_ * plane) = v;
+                    }
+                }
+            }
+        }
+        return fmaf(0.114f, gs[2], fmaf(0.587f, gs[1], 0.2989f * gs[0]));
+    };
     auto load_own = [&]() {
+        if constexpr (NHWC) return load_own_nhwc();
         if (C == 3) return load_own_c(std::integral_constant<int, 3>{}, std::integral_constant<int, 2>{}, 0);
         float g = 0.0f;                                   // C == 1 (or, without a contrast stage, any channel count)
         for (int c_ = 0; c_ < C; ++c_) g += load_own_c(std::integral_constant<int, 1>{}, std::integral_constant<int, 6>{}, c_);
@@ -311,7 +360,28 @@ disturb_fast_kernel(const __grid_constant__ DisturbParams p) {
         const float* __restrict__ xi = static_cast<const float*>(p.x) + (xu8 ? 0 : x_off);
         const uint8_t* __restrict__ xb = static_cast<const uint8_t*>(p.x) + x_off;
         const float* __restrict__ ni = do_noise ? p.noise + n_off : static_cast<const float*>(p.x);
-        if constexpr (K > 1) {
+        if constexpr (K > 1 && NHWC) {
+            const int nh = rows > 0 ? 2 * P * nq : 0;               // (halo row, quad) positions; three channels each
+            for (int i = tid; i < nh; i += nth) {
+                const int hr = div_nq(i), quad = i - hr * nq;
+                const int lr = hr < P ? hr : rows + hr;
+                int ir = r0 - P + lr;
+                if (ir < 0) ir = -ir;
+                if (ir >= H) ir = 2 * (H - 1) - ir;
+                const int goff = 3 * (ir * W + 4 * quad);
+                float4 xv[3], nv[3], xc[3], nc[3];
+#pragma unroll
+                for (int t = 0; t < 3; ++t) {
+                    xv[t] = ld_stream_f4(xi + goff + 4 * t);
+                    if (do_noise) nv[t] = ld_stream_f4(ni + goff + 4 * t);
+                }
+                deinterleave(xv[0], xv[1], xv[2], xc);
+                if (do_noise) deinterleave(nv[0], nv[1], nv[2], nc);
+#pragma unroll
+                for (int c_ = 0; c_ < 3; ++c_)
+                    *reinterpret_cast<float4*>(tile + c_ * plane + lr * WP + kPad + 4 * quad) = noisy4(xc[c_], nc[c_]);
+            }
+        } else if constexpr (K > 1) {
             const int nh4 = rows > 0 ? C * 2 * P * nq : 0;
             for (int i = tid; i < nh4; i += nth) {
                 const int hr_c = div_nq(i), quad = i - hr_c * nq;
@@ -704,12 +774,12 @@ static int launch_disturb(const DisturbParams& p, size_t smem, cudaStream_t stre
     return CLIPPPO_OK;
 }
 
-template <int K, int WT, bool XU8>
+template <int K, int WT, bool XU8, bool NHWC>
 static int launch_disturb_fast_x(const DisturbParams& p, size_t smem, cudaStream_t stream) {
     static DeviceOnce configured;
     if (configured.first_use()) {
-        CLIPPPO_CUDA_TRY(cudaFuncSetAttribute(disturb_fast_kernel<K, WT, XU8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        CLIPPPO_CUDA_TRY(cudaFuncSetAttribute(disturb_fast_kernel<K, WT, XU8>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        CLIPPPO_CUDA_TRY(cudaFuncSetAttribute(disturb_fast_kernel<K, WT, XU8, NHWC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        CLIPPPO_CUDA_TRY(cudaFuncSetAttribute(disturb_fast_kernel<K, WT, XU8, NHWC>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(static_cast<unsigned>(p.B) * p.S);
@@ -724,14 +794,15 @@ static int launch_disturb_fast_x(const DisturbParams& p, size_t smem, cudaStream
     cfg.attrs = attr;
     // without the contrast stage the stripes of an image are independent: plain CTAs, no gang scheduling
     cfg.numAttrs = ((p.stages & CLIPPPO_STAGE_CONTRAST) && p.S > 1) ? 1 : 0;
-    CLIPPPO_CUDA_TRY(cudaLaunchKernelEx(&cfg, disturb_fast_kernel<K, WT, XU8>, p));
+    CLIPPPO_CUDA_TRY(cudaLaunchKernelEx(&cfg, disturb_fast_kernel<K, WT, XU8, NHWC>, p));
     prof_count_launch();
     return CLIPPPO_OK;
 }
 
 template <int K, int WT>
 static int launch_disturb_fast_w(const DisturbParams& p, size_t smem, cudaStream_t stream) {
-    return p.x_u8 ? launch_disturb_fast_x<K, WT, true>(p, smem, stream) : launch_disturb_fast_x<K, WT, false>(p, smem, stream);
+    if (p.nhwc) return launch_disturb_fast_x<K, WT, false, true>(p, smem, stream);
+    return p.x_u8 ? launch_disturb_fast_x<K, WT, true, false>(p, smem, stream) : launch_disturb_fast_x<K, WT, false, false>(p, smem, stream);
 }
 
 template <int K>
@@ -893,6 +964,10 @@ static int run_disturb(DisturbParams& p, const float* k1d_host, int k, cudaStrea
 static bool is_contig_nchw(const long long s[4], int C, int H, int W) {
     return s[3] == 1 && s[2] == W && s[1] == (long long)H * W && s[0] == (long long)C * H * W;
 }
+// the [B,3,H,W] view of NHWC memory (x.permute(0, 3, 1, 2) of a contiguous [B,H,W,3] tensor)
+static bool is_nhwc_dense(const long long s[4], int B, int H, int W) {
+    return s[1] == 1 && s[3] == 3 && s[2] == 3LL * W && (B == 1 || (s[0] >= 3LL * H * W && s[0] % 4 == 0));
+}
 // every image one contiguous [C,H,W] block; the images may sit at any non-overlapping, 16-byte-aligned distance
 static bool is_image_contig(const long long s[4], int B, int C, int H, int W) {
     return s[3] == 1 && s[2] == W && (C == 1 || s[1] == (long long)H * W) &&
@@ -926,9 +1001,13 @@ extern "C" int clipppo_disturb_f32(const float* x, const int64_t x_strides_host[
     p.io_mode = 0;
     const bool need_noise = (p.stages & CLIPPPO_STAGE_NOISE) != 0;
     p.batch_contig = is_contig_nchw(p.xs, C, H, W) && (!need_noise || is_contig_nchw(p.ns, C, H, W));
-    p.fast = is_image_contig(p.xs, B, C, H, W) && (!need_noise || is_image_contig(p.ns, B, C, H, W)) &&
-             (W % 4 == 0) && (reinterpret_cast<uintptr_t>(x) % 16 == 0) &&
-             (!need_noise || reinterpret_cast<uintptr_t>(noise) % 16 == 0);
+    const bool aligned = (W % 4 == 0) && (reinterpret_cast<uintptr_t>(x) % 16 == 0) &&
+                         (!need_noise || reinterpret_cast<uintptr_t>(noise) % 16 == 0);
+    p.fast = is_image_contig(p.xs, B, C, H, W) && (!need_noise || is_image_contig(p.ns, B, C, H, W)) && aligned;
+    if (!p.fast && C == 3 && aligned && is_nhwc_dense(p.xs, B, H, W) && (!need_noise || is_nhwc_dense(p.ns, B, H, W))) {
+        p.fast = 1;                 // the NHWC-strided view of the MiniGrid call site / the reference benchmark
+        p.nhwc = 1;
+    }
     return run_disturb(p, k1d_host, k, as_stream(stream));
 }
 
