@@ -467,7 +467,15 @@ int attention_launch(const void* qkv_bf16, int n_images, int tokens, int heads, 
     if (n_images <= 0 || tokens <= 0 || heads <= 0) return CLIPPPO_ERR_BAD_SHAPE;
     if (head_dim != DH) return CLIPPPO_ERR_UNSUPPORTED;
     if ((reinterpret_cast<uintptr_t>(qkv_bf16) % 16) || (reinterpret_cast<uintptr_t>(out_bf16) % 16)) return CLIPPPO_ERR_ALIGN;
-    if (tokens > TP || causal) {                     // ViT-L/14 (T = 257), text tower (T = 77, causal): one CTA per (sequence, head), K / V resident
+    // ViT-L/14 (T = 257) and every other unmasked 64 < T <= 257: the tcgen05 / TMEM / TMA kernel (attention_tc.cu);
+    // CLIPPPO_ATT_TC=0 keeps the mma.sync kernel below for A/B measurements
+    static const bool use_tc = [] { const char* e = getenv("CLIPPPO_ATT_TC"); return !(e && e[0] == '0'); }();
+    if (use_tc && attention_tc_supported(tokens, causal)) {
+        const int st = attention_tc_launch(qkv_bf16, n_images, tokens, heads, out_bf16, stream);
+        if (st == CLIPPPO_OK) prof_count_launch();
+        return st;
+    }
+    if (tokens > TP || causal) {                     // text tower (T = 77, causal), T > 257: one CTA per (sequence, head), K / V resident
         if (static_cast<long long>(n_images) * heads > 0x7fffffffLL) return CLIPPPO_ERR_BAD_SHAPE;
         const __nv_bfloat16* q = static_cast<const __nv_bfloat16*>(qkv_bf16);
         __nv_bfloat16* o = static_cast<__nv_bfloat16*>(out_bf16);

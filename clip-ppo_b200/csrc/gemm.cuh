@@ -29,4 +29,8 @@ int rowstats_launch(const void* x_bf16, int rows, int width, long long row_strid
 int attention_launch(const void* qkv_bf16, int n_images, int tokens, int heads, int head_dim, void* out_bf16,
                      cudaStream_t stream, bool causal = false);
 
+// tcgen05 / TMEM / TMA attention for 64 < T <= 257, no mask (attention_tc.cu)
+bool attention_tc_supported(int tokens, bool causal);
+int attention_tc_launch(const void* qkv_bf16, int n_images, int tokens, int heads, void* out_bf16, cudaStream_t stream);
+
 }  // namespace clipppo

@@ -34,17 +34,28 @@ ROOT = os.path.dirname(HERE)
 REF = "/root/reference"
 OUT = os.environ.get("CLIPPPO_GOLDEN_OUT", os.path.join(ROOT, "tests", "golden"))
 sys.path.insert(0, ROOT)
-# `shared` must mean the REFERENCE's directory here, not this repository's drop-in package of the same name
-# (a regular package, which would win over the reference's namespace package): pin the name to /root/reference/shared.
-_ref_shared = types.ModuleType("shared")
-_ref_shared.__path__ = [os.path.join(REF, "shared")]
-sys.modules["shared"] = _ref_shared
+
+
+def _pin_reference_shared():
+    """`shared` must mean the REFERENCE's directory while the goldens are generated, not this repository's drop-in
+    package of the same name (a regular package, which would win over the reference's namespace package).  Called
+    from the generators only - importing this module (tests/test_oracle.py borrows the HF towers) rebinds nothing."""
+    if getattr(sys.modules.get("shared"), "_clipppo_reference_pin", False):
+        return
+    for name in [m for m in sys.modules if m == "shared" or m.startswith("shared.")]:
+        del sys.modules[name]
+    ref_shared = types.ModuleType("shared")
+    ref_shared.__path__ = [os.path.join(REF, "shared")]
+    ref_shared._clipppo_reference_pin = True
+    sys.modules["shared"] = ref_shared
+
 
 from oracle import disturb as od  # noqa: E402
 from oracle import vit as ov  # noqa: E402
 
 
 def _import_reference():
+    _pin_reference_shared()
     sys.path.insert(0, REF)
     from shared.disturbances_gpu import DisturbanceWrapperGPU  # type: ignore
     from shared.disturbance_types import DisturbanceSeverity, SEVERITY_CONFIGS  # type: ignore
@@ -179,6 +190,7 @@ def make_vit_goldens():
     sd = ov.random_state_dict(ov.VIT_B32, seed=0)
     tower = _HFTower(sd)
     _install_stub_clip(tower)
+    _pin_reference_shared()
     sys.path.insert(0, REF)
     import shared.clip_ppo_utils as ref_utils  # type: ignore
 

@@ -8,6 +8,8 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 GOLDEN = os.path.join(ROOT, "tests", "golden")
+# no CLIP checkpoint exists offline: the towers under test are seeded random weights (an explicit opt-in, see clip_compat.load)
+os.environ.setdefault("CLIPPPO_ALLOW_RANDOM_WEIGHTS", "1")
 
 
 def pytest_configure(config):
