@@ -24,6 +24,7 @@
 // warps 10-11 - 0.4 % of the FLOPs.
 // Both key blocks of a tile accumulate into one TMEM accumulator under one running shift per row; the shift (and with
 // it the accumulator row) is only touched when a later 64-key half beats it by more than 2^8 - see the softmax role.
+#include <stdio.h>
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -48,8 +49,12 @@ constexpr int OFF_PART = 2 * STAGE_BYTES;               // 2 x 32 lanes x float4
 constexpr int OFF_BAR = OFF_PART + 2 * 32 * 16;
 enum { B_QK = 0, B_V = 2, B_FREE = 4, B_S = 6, B_P = 8, B_O = 10, B_OREAD = 12, NUM_BARS = 14 };   // two of each
 constexpr int ATC_SMEM_BYTES = OFF_BAR + NUM_BARS * 8 + 16 + 1024;   // + tmem slot + alignment slack
-constexpr uint32_t ATC_TMEM_COLS = 512;                 // S / P of tile w: 128 w;  O of tile w: 256 + 64 w (384 used; the allocation is a power of two)
+constexpr uint32_t ATC_TMEM_COLS = 512;                 // S / P of tile w: 128 w;  O of tile w: 256 + 64 w;  tail-key scores of tile w: 384 + 16 w
 constexpr int MAX_T = 2 * TILE + 1;
+
+#ifndef ATC_TIMING
+#define ATC_TIMING 0
+#endif
 
 struct AtcArgs {
     int n_items, T, heads;
@@ -57,6 +62,7 @@ struct AtcArgs {
     uint32_t v_lbo, v_sbo;   // MN-major descriptor fields of the V operand (16-byte units)
     uint32_t p_kstep_cols;   // TMEM columns per 16-key step of the P operand
     uint32_t wg1_delay_ns;
+    long long* dbg;          // ATC_TIMING builds: per-phase clock totals of CTA 0's first softmax warps
 };
 
 // mbarrier waits.  try_wait returns after a hardware-bounded nap (~50 ns on B200) whether or not the phase has
@@ -139,17 +145,17 @@ __device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t smem_addr, 
 
 // the row's dot product with a broadcast 64-element bf16 row
 __device__ __forceinline__ float dot64_bf16(const uint8_t* row, int sw, const uint8_t* bcast) {
-    float acc0 = 0.f, acc1 = 0.f;
+    float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
         const uint4 a = *reinterpret_cast<const uint4*>(row + ((c ^ sw) << 4));
         const uint4 b = *reinterpret_cast<const uint4*>(bcast + c * 16);
         acc0 = fmaf(bf16lo(a.x), bf16lo(b.x), acc0); acc1 = fmaf(bf16hi(a.x), bf16hi(b.x), acc1);
-        acc0 = fmaf(bf16lo(a.y), bf16lo(b.y), acc0); acc1 = fmaf(bf16hi(a.y), bf16hi(b.y), acc1);
+        acc2 = fmaf(bf16lo(a.y), bf16lo(b.y), acc2); acc3 = fmaf(bf16hi(a.y), bf16hi(b.y), acc3);
         acc0 = fmaf(bf16lo(a.z), bf16lo(b.z), acc0); acc1 = fmaf(bf16hi(a.z), bf16hi(b.z), acc1);
-        acc0 = fmaf(bf16lo(a.w), bf16lo(b.w), acc0); acc1 = fmaf(bf16hi(a.w), bf16hi(b.w), acc1);
+        acc2 = fmaf(bf16lo(a.w), bf16lo(b.w), acc2); acc3 = fmaf(bf16hi(a.w), bf16hi(b.w), acc3);
     }
-    return acc0 + acc1;
+    return (acc0 + acc1) + (acc2 + acc3);
 }
 
 // softmax(Q K^T / 8) V for sequences of 65 .. 257 tokens; see the header comment for the roles.
@@ -241,6 +247,18 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
                 mbar_wait_cold(bar(B_QK + st), use & 1);
                 tc_fence_after();
                 for (int w = 0; w < n_tiles; ++w) issue_s(w, 0);
+                if (tail) {
+                    // the tail key's score for all 256 query rows: Q_w x (k_tail box)^T, N = 16 (row 0 of the box is the key, rows 1-7
+                    // are zero-filled, the second 8-row group aliases the first), into 16 spare TMEM columns per tile.  Complete
+                    // before the softmax asks for it: every later commit on B_S covers these MMAs.
+                    const uint64_t dkt = make_kmajor_sw128_desc(base + OFF_TAIL + 1024) & ~(static_cast<uint64_t>(0x3FFF) << 32);   // SBO = 0
+                    const uint32_t idesc_t = make_idesc_bf16(TILE, 16);
+                    for (int w = 0; w < 2; ++w) {
+                        const uint64_t dq = make_kmajor_sw128_desc(base + OFF_Q + w * TILE_BYTES);
+#pragma unroll
+                        for (int k = 0; k < DH / 16; ++k) umma_bf16(tmem_base + 384 + 16 * w, dq + 2 * k, dkt + 2 * k, idesc_t, k != 0);
+                    }
+                }
                 mbar_wait_cold(bar(B_V + st), use & 1);
                 tc_fence_after();
                 for (int kb = 0; kb < n_tiles; ++kb) {
@@ -255,7 +273,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
                             umma_bf16_ts(tmem_base + 256 + 64 * w, tmem_base + 128 * w + g.p_kstep_cols * k,
                                          make_mnmajor_sw128_desc(v_addr + k * 2048, g.v_lbo, g.v_sbo), idesc_pv, (kb | k) != 0);
                         if (kb + 1 < n_tiles) issue_s(w, kb + 1);          // in order behind the MMAs that read P_w
-                        else umma_commit(bar(B_O + w));
+                        else {
+                            if (tail)      // + p_t v_tail: A = the (p_t, 0, ...) columns, B = the v_tail box (row 0; both 8-row groups alias it)
+                                umma_bf16_ts(tmem_base + 256 + 64 * w, tmem_base + 128 * w + 64,
+                                             make_mnmajor_sw128_desc(base + OFF_TAIL + 2048, g.v_lbo, 0), idesc_pv, 1);
+                            umma_commit(bar(B_O + w));
+                        }
                     }
                 }
             }
@@ -295,17 +318,21 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
                 float o0 = 0.f, o1 = 0.f;
                 const int cch = lane >> 2, cof = (lane & 3) * 4;
                 const uint8_t* vb = sm + OFF_V + half * TILE_BYTES + cof;
+                float o2 = 0.f, o3 = 0.f;
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-#pragma unroll 8
-                    for (int jj = 0; jj < 32; ++jj) {
-                        const int j = 32 * i + jj;
-                        const float pj = __shfl_sync(0xffffffffu, s[i], jj);
-                        const uint32_t w = *reinterpret_cast<const uint32_t*>(vb + j * 128 + ((cch ^ (j & 7)) << 4));
-                        o0 = fmaf(pj, bf16lo(w), o0);
-                        o1 = fmaf(pj, bf16hi(w), o1);
+#pragma unroll
+                    for (int jo = 0; jo < 4; ++jo) {
+#pragma unroll
+                        for (int ji = 0; ji < 8; ++ji) {          // row j = 32 i + 8 jo + ji: j & 7 = ji is a compile-time constant
+                            const float pj = __shfl_sync(0xffffffffu, s[i], 8 * jo + ji);
+                            const uint32_t w = *reinterpret_cast<const uint32_t*>(vb + (32 * i + 8 * jo + ji) * 128 + ((cch ^ ji) << 4));
+                            if (ji & 1) { o2 = fmaf(pj, bf16lo(w), o2); o3 = fmaf(pj, bf16hi(w), o3); }
+                            else { o0 = fmaf(pj, bf16lo(w), o0); o1 = fmaf(pj, bf16hi(w), o1); }
+                        }
                     }
                 }
+                o0 += o2; o1 += o3;
                 float4* part = reinterpret_cast<float4*>(smem + OFF_PART) + st * 32 + lane;
                 if (half == 1) {
                     const uint32_t w = *reinterpret_cast<const uint32_t*>(sm + OFF_TAIL + 2048 + (cch << 4) + cof);
@@ -340,23 +367,33 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
         constexpr float kLazy = 8.0f;
         uint32_t ph_s = 0;
         int it = 0;
+#if ATC_TIMING
+        long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        long long tprev = clock64();
+#define ATC_TICK(i) do { const long long tn = clock64(); tacc[i] += tn - tprev; tprev = tn; } while (0)
+#else
+#define ATC_TICK(i) do { } while (0)
+#endif
         for (int item = blockIdx.x; item < g.n_items; item += gridDim.x, ++it) {
             const int img = item / heads, head = item - img * heads;
             const int st = it & 1, use = it >> 1;
             uint8_t* sm = smem + st * STAGE_BYTES;
-            // the tail key's score for my row (overlaps the S MMAs)
-            float s_t = 0.f;
-            if (tail) {
-                mbar_wait_cold(bar(B_QK + st), use & 1);
-                s_t = sl2 * dot64_bf16(sm + OFF_Q + w * TILE_BYTES + r * 128, r & 7, sm + OFF_TAIL + 1024);
-            }
+            float s_t = 0.f;                                      // the tail key's score for my row
             float m = 0.f, l = 0.f;                               // running shift and row sum
             for (int kb = 0; kb < n_tiles; ++kb) {
                 const bool last = (kb == n_tiles - 1);
                 const int nvalid = last ? last_keys : TILE;
                 const bool ragged = nvalid != TILE;
+                ATC_TICK(0);
                 mbar_wait_hot(bar(B_S + w), ph_s); ph_s ^= 1;
                 tc_fence_after();
+                ATC_TICK(1);
+                if (tail && last) {                               // the tail key's score: column 0 of the 16-column MMA below S and O
+                    uint32_t t1;
+                    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(t1) : "r"(trow - 128 * w + 384 + 16 * w) : "memory");
+                    tmem_ld_wait();
+                    s_t = __uint_as_float(t1) * sl2;
+                }
                 // Four 32-key chunks, double-buffered: chunk c + 1 streams out of TMEM while chunk c is exponentiated
                 // against the running shift - no maximum has to be known first (lazy shift, see above).
                 uint32_t v[2][32], pk[64];
@@ -371,17 +408,33 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
                         tmem_ld_wait();
                         if (c + 1 < nch) tmem_ld_32x32(trow + (c + 1) * 32, v[(c + 1) & 1]);
                         uint32_t (&vc)[32] = v[c & 1];
-                        float mx = -INFINITY;
+                        if (ragged) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            if (ragged && c * 32 + j >= nvalid) vc[j] = 0xff800000u;          // -inf: keys beyond T
-                            mx = fmaxf(mx, __uint_as_float(vc[j]));
+                            for (int j = 0; j < 32; ++j)
+                                if (c * 32 + j >= nvalid) vc[j] = 0xff800000u;                // -inf: keys beyond T
                         }
-                        mx *= sl2;
+                        // the chunk's maximum: needed BEFORE the exponentials only for the very first chunk of the item; everywhere
+                        // else the exponentials run against the current shift at once (nothing to wait for) and the maximum is
+                        // checked afterwards - a chunk that beat the shift by more than 2^8 (rare) is redone
+                        float mxa[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) mxa[j & 3] = fmaxf(mxa[j & 3], __uint_as_float(vc[j]));
+                        float mx = fmaxf(fmaxf(mxa[0], mxa[1]), fmaxf(mxa[2], mxa[3])) * sl2;
                         if (tail && last && c == nch - 1) mx = fmaxf(mx, s_t);
                         if (kb == 0 && c == 0) m = mx;
-                        else if (__any_sync(0xffffffffu, mx > m + kLazy)) {
-                            // rare: move the shift; whatever this row already produced under the old one is scaled by f
+                        const float2 sum_before = sum2;
+                        {
+                            const float2 nm2 = make_float2(-m, -m);
+#pragma unroll
+                            for (int j = 0; j < 32; j += 2) {
+                                const float2 x = __ffma2_rn(make_float2(__uint_as_float(vc[j]), __uint_as_float(vc[j + 1])), sc2, nm2);
+                                const float2 e = make_float2(ex2f(x.x), ex2f(x.y));
+                                sum2 = __fadd2_rn(sum2, e);
+                                pk[16 * c + (j >> 1)] = pack_bf16x2(e.x, e.y);
+                            }
+                        }
+                        if (!(kb == 0 && c == 0) && __any_sync(0xffffffffu, mx > m + kLazy)) {
+                            // rare: move the shift; whatever this row already produced under the old one is scaled by f, this chunk redone
                             __nv_bfloat16 fb = __float2bfloat16_rn(1.0f);
                             if (mx > m + kLazy) fb = __float2bfloat16_rn(ex2f(m - mx));
                             const float ff = __bfloat162float(fb);
@@ -392,22 +445,26 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
                                 hv = __hmul2(hv, f2);
                                 pk[j] = *reinterpret_cast<uint32_t*>(&hv);
                             }
-                            sum2.x *= ff; sum2.y *= ff; l *= ff; fo *= ff;
-                            if (ff != 1.0f) m = (ff == 0.f) ? mx : m - __log2f(ff);
-                        }
-                        const float2 nm2 = make_float2(-m, -m);
+                            l *= ff; fo *= ff;
+                            if (ff != 1.0f) {
+                                m = (ff == 0.f) ? mx : m - __log2f(ff);
+                                sum2 = make_float2(sum_before.x * ff, sum_before.y * ff);
+                                const float2 nm2 = make_float2(-m, -m);
 #pragma unroll
-                        for (int j = 0; j < 32; j += 2) {
-                            const float2 x = __ffma2_rn(make_float2(__uint_as_float(vc[j]), __uint_as_float(vc[j + 1])), sc2, nm2);
-                            const float2 e = make_float2(ex2f(x.x), ex2f(x.y));
-                            sum2 = __fadd2_rn(sum2, e);
-                            pk[16 * c + (j >> 1)] = pack_bf16x2(e.x, e.y);
+                                for (int j = 0; j < 32; j += 2) {
+                                    const float2 x = __ffma2_rn(make_float2(__uint_as_float(vc[j]), __uint_as_float(vc[j + 1])), sc2, nm2);
+                                    const float2 e = make_float2(ex2f(x.x), ex2f(x.y));
+                                    sum2 = __fadd2_rn(sum2, e);
+                                    pk[16 * c + (j >> 1)] = pack_bf16x2(e.x, e.y);
+                                }
+                            }
                         }
                     } else {
 #pragma unroll
                         for (int j = 0; j < 16; ++j) pk[16 * c + j] = 0u;
                     }
                 }
+                ATC_TICK(2);
                 {
                     uint32_t (&lo)[32] = *reinterpret_cast<uint32_t (*)[32]>(&pk[0]);
                     uint32_t (&hi)[32] = *reinterpret_cast<uint32_t (*)[32]>(&pk[32]);
@@ -415,6 +472,16 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
                     if (nvalid > 64) tmem_st_32x32(trow + 32, hi);
                 }
                 l += sum2.x + sum2.y;
+                if (tail && last) {
+                    // the tail key: its probability goes into 8 spare columns of my S row as the bf16 pair (p_t, 0) followed by
+                    // zeros - a 16-key A operand whose only non-zero entry multiplies row 0 of the v_tail box (one extra MMA)
+                    const float p_t = ex2f(s_t - m);
+                    l += p_t;
+                    uint32_t pt[8] = {pack_bf16x2(p_t, 0.f), 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+                    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                                 ::"r"(trow + 64), "r"(pt[0]), "r"(pt[1]), "r"(pt[2]), "r"(pt[3]), "r"(pt[4]), "r"(pt[5]), "r"(pt[6]), "r"(pt[7])
+                                 : "memory");
+                }
                 // the accumulator row (holding the first key block) follows the shift; the whole warp moves together
                 if (kb > 0 && __any_sync(0xffffffffu, fo != 1.0f)) {
 #pragma unroll
@@ -431,15 +498,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar(B_P + w));
+                ATC_TICK(3);
             }
-            const float p_t = tail ? ex2f(s_t - m) : 0.f;
-            l += p_t;
-            // ---- epilogue of the tile: O = (O + p_t v_tail) / l ----
+            // ---- epilogue of the tile: O / l ----
             mbar_wait_hot(bar(B_O + w), it & 1);
             tc_fence_after();
+            ATC_TICK(4);
             const float inv = 1.0f / l;
-            const float wt = p_t * inv;
-            const float2 inv2 = make_float2(inv, inv), wt2 = make_float2(wt, wt);
+            const float2 inv2 = make_float2(inv, inv);
             uint8_t* stage = sm + OFF_Q + w * TILE_BYTES + r * 128;         // my row of the (dead) Q tile
             uint32_t oa[2][32];
             tmem_ld_32x32(orow, oa[0]);
@@ -448,6 +514,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar(B_OREAD + w));       // the accumulator is in registers
+            ATC_TICK(5);
 #pragma unroll
             for (int c = 0; c < 8; ++c) {                       // 16-byte pieces: columns 8 c .. 8 c + 7
                 float2 o2[4];
@@ -455,13 +522,6 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
                 for (int e = 0; e < 4; ++e)
                     o2[e] = __fmul2_rn(make_float2(__uint_as_float(oa[c >> 2][8 * (c & 3) + 2 * e]),
                                                    __uint_as_float(oa[c >> 2][8 * (c & 3) + 2 * e + 1])), inv2);
-                if (tail) {
-                    const uint4 t4 = *reinterpret_cast<const uint4*>(sm + OFF_TAIL + 2048 + c * 16);
-                    o2[0] = __ffma2_rn(wt2, make_float2(bf16lo(t4.x), bf16hi(t4.x)), o2[0]);
-                    o2[1] = __ffma2_rn(wt2, make_float2(bf16lo(t4.y), bf16hi(t4.y)), o2[1]);
-                    o2[2] = __ffma2_rn(wt2, make_float2(bf16lo(t4.z), bf16hi(t4.z)), o2[2]);
-                    o2[3] = __ffma2_rn(wt2, make_float2(bf16lo(t4.w), bf16hi(t4.w)), o2[3]);
-                }
                 const uint4 pk = make_uint4(pack_bf16x2(o2[0].x, o2[0].y), pack_bf16x2(o2[1].x, o2[1].y),
                                             pack_bf16x2(o2[2].x, o2[2].y), pack_bf16x2(o2[3].x, o2[3].y));
                 *reinterpret_cast<uint4*>(stage + ((c ^ (r & 7)) << 4)) = pk;
@@ -476,7 +536,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
                 mbar_arrive(bar(B_FREE + st));
             }
             __syncwarp();
+            ATC_TICK(6);
         }
+#if ATC_TIMING
+        if (g.dbg && blockIdx.x == 0 && lane == 0 && (warp & 3) == 0) {
+            for (int i = 0; i < 8; ++i) g.dbg[w * 8 + i] = tacc[i];
+        }
+#endif
         if (lane == 0) bulk_wait_group<0>();
     }
 
@@ -547,9 +613,22 @@ int attention_tc_launch(const void* qkv_bf16, int n_images, int tokens, int head
     // operand-layout knobs, only ever changed by tools/ probes
     static const uint32_t v_lbo = env_u32("CLIPPPO_ATC_V_LBO", 64), v_sbo = env_u32("CLIPPPO_ATC_V_SBO", 64),
                           p_cols = env_u32("CLIPPPO_ATC_P_COLS", 8), wg1_delay = env_u32("CLIPPPO_ATC_WG1_DELAY", 0);
-    AtcArgs g{static_cast<int>(items), tokens, heads, static_cast<__nv_bfloat16*>(out_bf16), v_lbo, v_sbo, p_cols, wg1_delay};
+    AtcArgs g{static_cast<int>(items), tokens, heads, static_cast<__nv_bfloat16*>(out_bf16), v_lbo, v_sbo, p_cols, wg1_delay, nullptr};
+#if ATC_TIMING
+    static long long* dbg = nullptr;
+    if (!dbg) { cudaMalloc(&dbg, 16 * 8); cudaMemset(dbg, 0, 16 * 8); }
+    g.dbg = dbg;
+#endif
     const int grid = static_cast<int>(items < kNumSMs ? items : kNumSMs);
     CLIPPPO_CUDA_TRY(launch_pdl(attention_tc_kernel, grid, ATC_THREADS, ATC_SMEM_BYTES, stream, 1, tq, tt, to, g));
+#if ATC_TIMING
+    {
+        long long h[16];
+        cudaMemcpy(h, g.dbg, sizeof(h), cudaMemcpyDeviceToHost);
+        const char* names[8] = {"loop top", "wait S", "chunks", "st+arrive", "wait O", "ld O", "epilogue", "-"};
+        for (int w = 0; w < 2; ++w) for (int i = 0; i < 7; ++i) printf("  wg%d %-10s %lld\n", w, names[i], h[w * 8 + i]);
+    }
+#endif
     return CLIPPPO_OK;
 }
 

@@ -44,6 +44,17 @@ def test_argument_validation_without_gpu(native):
     assert native.clipppo_gemm_bf16(None, None, 128, 256, 64, 0, None, None, 0, None, 256, None) == -4
 
 
+import pytest
+
+
+@pytest.mark.gpu
+def test_header_symbols_and_sass_on_the_gpu_box(native):
+    """The same header / export / SASS checks inside the `-m gpu` run, against the library the GPU tests actually load."""
+    test_header_symbols_are_exported(native)
+    test_binding_lists_every_header_symbol()
+    test_library_is_sm100a_native()
+
+
 def test_library_is_sm100a_native():
     """The shipped code object targets sm_100a and contains the tcgen05 / TMA instructions."""
     import shutil
@@ -57,3 +68,10 @@ def test_library_is_sm100a_native():
     assert "sm_100a" in sass
     for mnemonic in ("UTCHMMA", "UTMALDG", "LDTM"):
         assert mnemonic in sass, f"{mnemonic} missing from SASS"
+    # the long-sequence attention kernel is tcgen05 / TMEM / TMA as well: MMAs, TMEM loads AND stores (P goes back into
+    # TMEM as the A operand of P V), 3-D tensor-map loads and stores
+    att = sass[sass.index("attention_tc_kernel"):]
+    att = att[:att.index("Function :", 10)] if "Function :" in att[10:] else att
+    for mnemonic in ("UTCHMMA", "LDTM", "STTM", "UTMALDG.3D", "UTMASTG.3D"):
+        assert mnemonic in att, f"{mnemonic} missing from attention_tc_kernel"
+    assert "HMMA.16816" not in att

@@ -182,6 +182,30 @@ def test_attention_vs_torch(native, n, T, H):
     assert (out.float() - ref).abs().max().item() <= 3e-2
 
 
+@pytest.mark.parametrize("n,T,H,skew", [(2, 257, 16, 1), (2, 257, 16, 2), (3, 200, 12, 1), (2, 129, 8, 2), (150, 257, 16, 0)])
+def test_attention_tc_running_shift(native, n, T, H, skew):
+    """The tcgen05 kernel (64 < T <= 257) keeps ONE running softmax shift per row and only moves it when a later 32-key chunk
+    beats it by more than 2^8: keys whose scores grow (skew 1) or shrink (skew 2) by whole factors along the sequence drive
+    every path of that logic - shift moves inside a block, across blocks (accumulator row rescaled in TMEM), and on the
+    tail key.  n = 150 with skew 0 runs more items than there are CTAs (both shared-memory stages, barrier phase wrap)."""
+    from clip_ppo_b200 import _native as Nn
+    dh, D = 64, H * 64
+    gen = torch.Generator(device="cuda").manual_seed(7 * n + T + skew)
+    qkv = torch.randn(n * T, 3 * D, device="cuda", generator=gen)
+    if skew:
+        t = torch.arange(T, device="cuda").repeat(n)
+        f = (1.0 + 2.0 * (t // 64).float()) if skew == 1 else (1.0 + 2.0 * ((T - 1 - t) // 64).float())
+        qkv[:, D:2 * D] *= f[:, None]
+    qkv = qkv.bfloat16()
+    out = torch.full((n * T, D), float("nan"), device="cuda", dtype=torch.bfloat16)
+    Nn.check(native.clipppo_attention_bf16(qkv.data_ptr(), n, T, H, dh, out.data_ptr(), _stream()))
+    q, k, v = qkv.float().reshape(n, T, 3, H, dh).permute(2, 0, 3, 1, 4)
+    s = torch.softmax(q @ k.transpose(-1, -2) / math.sqrt(dh), dim=-1)
+    ref = (s @ v).permute(0, 2, 1, 3).reshape(n * T, D)
+    assert not out.float().isnan().any()
+    assert (out.float() - ref).abs().max().item() <= 3e-2
+
+
 @pytest.mark.parametrize("shape,dtype,scale", [((3, 3, 84, 84), torch.float32, 1 / 255.0), ((2, 3, 224, 224), torch.float32, 1 / 255.0),
                                                ((2, 1, 84, 84), torch.float32, 1 / 255.0 / 255.0), ((3, 3, 84, 84), torch.uint8, 1 / 255.0),
                                                ((2, 3, 60, 100), torch.float32, 1.0)])
