@@ -5,20 +5,27 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 Metric (BASELINE.json): CLIP-PPO frames/sec through  disturb -> ViT-B/32 embed -> alignment loss.
-Workload: BASELINE.json configs[2] - synthetic 224x224 RGB frames, 4096 per GPU per step (weak
-scaling), MODERATE disturbances, seeded random ViT-B/32 weights (no CLIP weights exist offline).
+Workload: BASELINE.json configs[2] - synthetic 224x224 RGB frames, 4096 per GPU per step (weak scaling), MODERATE
+disturbances, seeded random ViT-B/32 weights (no CLIP weights exist offline).
 
-One step, through the drop-in API of shared/:
-    d    = DisturbanceWrapperGPU.apply_disturbances(x, noise=...)       one fused launch  (D1)
-    emb  = frozen tower on d (resize/normalise/im2col + 12 blocks + proj + L2-norm)       (V0-V7)
-    loss = compute_cosine_embedding_loss(z, emb)                                           (L1)
-    N>1: NCCL all-reduce of a PPO-agent-sized fp32 gradient bucket (the path's only exchange)
+One step, every call the PUBLIC drop-in surface of shared/ (the calls the reference's training scripts make):
+    d    = DisturbanceWrapperGPU.apply_disturbances(x, noise=...)                  one fused launch          (D1)
+    obs  = d * 255                                                                 the call sites' own `* 255` (clip_ppo_minigrid.py:388)
+    emb  = generate_clip_embeddings(NONE, model, "image", B, dev, images=obs)      /255 + resize + normalise + tower + L2 norm (V0-V7)
+    loss = compute_cosine_embedding_loss(z, emb)                                   (L1)
+    N>1: GradBucket.all_reduce_mean() of the PPO agent's real gradients (the path's only exchange)
 
-`value` times the step with x / noise / z resident in HBM; `e2e` feeds uint8 frames from pinned
-host memory every step (H2D inside the timed region, prefetched one step ahead on a copy stream),
-draws the noise on the device like the public API does, and reads the loss back to the host.
-`--impl reference` times the CPU oracle port of the same path (the reference is Python and cannot
-travel to the GPU box; see oracle/__init__.py) on all host threads on a bounded sample.
+`value` times the step with x / noise / z resident in HBM; `e2e` feeds uint8 frames from pinned host memory every step (H2D
+inside the timed region, prefetched one step ahead on a copy stream), draws the noise on the device like the public API does,
+and reads the loss back to the host.  Extra keys of the JSON line:
+    roofline      the tcgen05 GEMM (dominant kernel), CUDA-event timed inside a second pass of the same steps
+    secondary     short CUDA-event measurements of the other BASELINE configs: disturbance HBM fractions (MODERATE / SEVERE
+                  224x224x3, HARD 84x84x1), the Atari 84 -> 224 path (configs[3], one GPU's share), ViT-L/14 (configs[4])
+    eager_gpu_baseline   the reference's OWN functions (oracle/_ref, staged by oracle/build_ref.py) on the same GPU with an
+                  fp16 eager tower (tools/eager_tower.py) - the library-dispatched path the reference runs on a GPU
+    cpu_baseline  the reference's own functions on the host cores (fp32 tower restated in oracle/vit.py), bounded sample
+    parity, strong   (N > 1) shard-vs-whole equality of embeddings / all-reduced gradients, and the fixed-total-work timing
+`--impl reference` times the reference's own CPU path (oracle/_ref; the oracle port if it was never staged) on all host threads.
 """
 from __future__ import annotations
 
@@ -35,13 +42,14 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
+# no CLIP checkpoint exists offline: the towers measured here are seeded random weights of the named architecture
+os.environ.setdefault("CLIPPPO_ALLOW_RANDOM_WEIGHTS", "1")
 
 import torch
 
 METRIC = "CLIP-PPO frames/sec (disturb+ViT-B/32 embed+align loss)"
-FLOPS_PER_IMAGE = 8.8176e9          # SURVEY.md §8d, ViT-B/32, all 50 tokens through 12 layers
-FLOPS_PER_IMAGE_BY_MODEL = {"ViT-B/32": 8.8176e9, "ViT-L/14": 162.03e9}
-AGENT_GRAD_ELEMS = 1_686_180        # MiniGrid NatureCNN agent fp32 grads, 7 actions
+FLOPS_PER_IMAGE_BY_MODEL = {"ViT-B/32": 8.8176e9, "ViT-L/14": 162.03e9}      # SURVEY.md §8d
+CHUNK = 256                          # frames per seeded generation chunk (inputs are a function of the GLOBAL frame index)
 
 
 def parse():
@@ -59,6 +67,7 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=192, help="frames of the cpu_baseline sample")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the secondary / eager_gpu_baseline legs")
     return ap.parse_args()
 
 
@@ -115,72 +124,163 @@ class ClockSampler:
                 "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
-# ------------------------------------------------------------------------------------------------
-# CPU oracle arm (cpu_baseline and --impl reference)
-# ------------------------------------------------------------------------------------------------
-def cpu_path_step(sd, frames01, noise, z, sev):
-    from oracle import disturb as od, losses as ol, vit as ov
-    cfg = od.SEVERITY_TABLE[sev]
-    H, W = frames01.shape[-2:]
-    ph, pw = od.cutout_patch(H, W, cfg["cutout"])
-    k1d = od.gaussian_kernel1d(od.blur_kernel_size(cfg["blur_sigma"]), cfg["blur_sigma"])
-    d = od.disturb(frames01, noise, cfg["noise_sigma"], 1.1, k1d, H // 5, W // 4, ph, pw)
-    emb = ov.image_embeddings(sd, d * 255.0)
-    return ol.cosine_embedding_loss(z, emb)
+def event_ms(fn, iters: int, warm: int = 2) -> float:
+    """Mean device time of fn() over `iters` calls after `warm` untimed ones (CUDA events on the current stream)."""
+    for _ in range(warm):
+        fn()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    a.record()
+    for _ in range(iters):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / iters
 
 
-def cpu_inputs(n, hw, seed=0):
+# ------------------------------------------------------------------------------------------------
+# the reference's own functions (oracle/_ref) - CPU arm, cpu_baseline, eager GPU baseline
+# ------------------------------------------------------------------------------------------------
+class _OracleTower(torch.nn.Module):
+    """What `clip.load(name, "cpu")` would return as far as shared/clip_ppo_utils.py can tell: `encode_image` on a
+    normalised fp32 batch.  The arithmetic is the fp32 restatement of [clip] VisionTransformer in oracle/vit.py."""
+
+    def __init__(self, sd):
+        super().__init__()
+        self.sd = sd
+        self.anchor = torch.nn.Parameter(torch.zeros(1))
+
+    @torch.no_grad()
+    def encode_image(self, x):
+        from oracle import vit as ov
+        return ov.vision_tower(self.sd, x.float())
+
+
+def reference_step_fn(device: str, model_name: str, severity: str, seed: int = 0):
+    """(step(frames01, z) -> loss, kind): the reference's stock code path - DisturbanceWrapperGPU.apply_disturbances ->
+    `* 255` -> generate_clip_embeddings -> compute_cosine_embedding_loss - out of oracle/_ref when it is staged
+    (kind "reference"), else the oracle port (kind "port")."""
+    from oracle import build_ref, vit as ov
+    cfg = ov.VIT_B32 if model_name == "ViT-B/32" else ov.VIT_L14
+    sd = ov.random_state_dict(cfg, 0)
+    if build_ref.available():
+        if device == "cpu":
+            tower = _OracleTower(sd)
+        else:
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            from eager_tower import EagerCLIP
+            tower = EagerCLIP(sd, device)
+        ref = build_ref.load(tower)
+        U, DG, DT = ref.clip_ppo_utils, ref.disturbances_gpu, ref.disturbance_types
+        model = U.load_clip_model(model_name, device)
+        w = DG.DisturbanceWrapperGPU(device=device, seed=seed, severity=DT.DisturbanceSeverity[severity])
+
+        def step(frames01, z):
+            d = w.apply_disturbances(frames01)
+            emb = U.generate_clip_embeddings(U.AblationMode.NONE, model, "image", frames01.shape[0], device, images=d * 255.0)
+            return U.compute_cosine_embedding_loss(z, emb)
+        return step, "reference"
+    if device != "cpu":
+        return None, "unavailable"
+    from oracle import disturb as od, losses as ol
+    c = od.SEVERITY_TABLE[severity]
+
+    def step(frames01, z):
+        H, W = frames01.shape[-2:]
+        ph, pw = od.cutout_patch(H, W, c["cutout"])
+        k1d = od.gaussian_kernel1d(od.blur_kernel_size(c["blur_sigma"]), c["blur_sigma"])
+        d = od.disturb(frames01, torch.randn_like(frames01), c["noise_sigma"], 1.1, k1d, H // 5, W // 4, ph, pw)
+        return ol.cosine_embedding_loss(z, ov.image_embeddings(sd, d * 255.0))
+    return step, "port"
+
+
+def cpu_inputs(n, hw, out_dim=512, seed=0):
     g = torch.Generator().manual_seed(seed)
     frames = torch.randint(0, 256, (n, 3, hw, hw), generator=g).float() / 255.0
-    noise = torch.randn(n, 3, hw, hw, generator=g)
-    z = torch.relu(torch.randn(n, 512, generator=g))
-    return frames, noise, z
+    z = torch.relu(torch.randn(n, out_dim, generator=g))
+    return frames, z
 
 
 def run_reference_arm(args):
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
+    if int(os.environ.get("RANK", "0")) != 0:
         return
-    from oracle import vit as ov
     torch.set_num_threads(os.cpu_count() or 1)
-    sd = ov.random_state_dict(ov.VIT_B32, 0)
+    step, kind = reference_step_fn("cpu", args.model, args.severity)
     n = args.ref_batch
-    frames, noise, z = cpu_inputs(n, args.hw)
+    frames, z = cpu_inputs(n, args.hw, 512 if args.model == "ViT-B/32" else 768)
     with torch.no_grad():
         for _ in range(args.warmup):
-            cpu_path_step(sd, frames, noise, z, args.severity)
+            step(frames, z)
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            loss = cpu_path_step(sd, frames, noise, z, args.severity)
+            loss = step(frames, z)
         dt = time.perf_counter() - t0
     value = n * args.steps / dt
     cores = torch.get_num_threads()
+    what = ("the reference's own shared/disturbances_gpu.py + shared/clip_ppo_utils.py (oracle/_ref, unmodified) over the fp32 "
+            "tower of oracle/vit.py" if kind == "reference" else "fp32 CPU oracle port (oracle/: torch CPU ops)")
     line = {
         "impl": "reference", "metric": METRIC.replace("ViT-B/32", args.model), "value": value, "unit": "frames/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, args.batch),
-        "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cores, "kind": "port",
-                         "sample": f"{n} frames/step x {args.steps} steps of the same workload, fp32 CPU oracle port "
-                                   f"(oracle/: torch CPU ops, {cores} threads); loss {float(loss):.6f}"},
+        "config": workload_config(args, n, note=f"CPU arm: a bounded {n}-frame step of the same workload (the GPU arm runs {args.batch})"),
+        "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cores, "kind": kind,
+                         "sample": f"{n} frames/step x {args.steps} steps of the same workload, {what}, {cores} threads; loss {float(loss):.6f}"},
         "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
 
 
-def workload_config(args, per_gpu_batch):
+def workload_config(args, per_gpu_batch, note=None):
     which = "configs[2]" if args.model == "ViT-B/32" else "configs[4]'s ViT-L/14 variant, one GPU's share"
-    return {"workload": f"BASELINE {which}: synthetic {args.hw}x{args.hw} RGB frames, disturb({args.severity}) -> "
-                        f"{args.model} embed -> cosine alignment loss",
-            "per_gpu_batch": per_gpu_batch, "frame": [3, args.hw, args.hw], "severity": args.severity,
-            "weights": f"seeded random {args.model} (openai key layout)",
-            "l2_policy": "inputs larger than L2 (x + noise = 4.9 GB per step at 4096 frames); no flush needed",
-            "parallelism": f"dp{args.gpus} by observation, frozen tower replicated, grad-bucket all-reduce only"}
+    cfg = {"workload": f"BASELINE {which}: synthetic {args.hw}x{args.hw} RGB frames, disturb({args.severity}) -> "
+                       f"{args.model} embed -> cosine alignment loss",
+           "per_gpu_batch": per_gpu_batch, "frame": [3, args.hw, args.hw], "severity": args.severity,
+           "weights": f"seeded random {args.model} (openai key layout)",
+           "api": "apply_disturbances -> `* 255` -> generate_clip_embeddings(images=) -> compute_cosine_embedding_loss (public calls only)",
+           "inputs": f"frame / noise / latent chunks of {CHUNK} seeded by GLOBAL chunk index (the same data whatever the GPU count)",
+           "l2_policy": "inputs larger than L2 (x + noise = 4.9 GB per step at 4096 frames); no flush needed",
+           "parallelism": f"dp{args.gpus} by observation, frozen tower replicated, PPO-agent gradient all-reduce only"}
+    if note:
+        cfg["note"] = note
+    return cfg
 
 
 # ------------------------------------------------------------------------------------------------
 # B200 arm
 # ------------------------------------------------------------------------------------------------
+def seeded_inputs(dev, first_frame: int, n: int, hw: int, out_dim: int, want_noise: bool = True):
+    """Frames [n,3,hw,hw] in [0,1] (uint8 values / 255), supplied noise, post-ReLU latents - generated chunk by chunk from
+    generators seeded with the GLOBAL chunk index, so rank r of G holds exactly rows [r n, (r+1) n) of the one global batch."""
+    xs, ns, zs = [], [], []
+    for c0 in range(first_frame, first_frame + n, CHUNK):
+        m = min(CHUNK, first_frame + n - c0)
+        g = torch.Generator(device=dev).manual_seed(100_003 + c0 // CHUNK)
+        xs.append(torch.randint(0, 256, (m, 3, hw, hw), device=dev, generator=g, dtype=torch.uint8))
+        if want_noise:
+            ns.append(torch.randn(m, 3, hw, hw, device=dev, generator=g))
+        zs.append(torch.relu(torch.randn(m, out_dim, device=dev, generator=g)))
+    x8 = torch.cat(xs)
+    return x8, (torch.cat(ns) if want_noise else None), torch.cat(zs)
+
+
+class PolicyEncoder(torch.nn.Module):
+    """The trainable side of the path: the reference's NatureCNN encoder + heads (clip_ppo_minigrid.py:229-242), 1 686 180
+    fp32 parameters with 7 actions - the gradients the data-parallel all-reduce carries."""
+
+    def __init__(self, n_actions: int = 7):
+        super().__init__()
+        nn = torch.nn
+        self.network = nn.Sequential(nn.Conv2d(3, 32, 8, stride=4), nn.ReLU(), nn.Conv2d(32, 64, 4, stride=2), nn.ReLU(),
+                                     nn.Conv2d(64, 64, 3, stride=1), nn.ReLU(), nn.Flatten(), nn.Linear(64 * 7 * 7, 512), nn.ReLU())
+        self.actor = nn.Linear(512, n_actions)
+        self.critic = nn.Linear(512, 1)
+
+    def forward(self, obs84):
+        h = self.network(obs84)
+        return h, self.actor(h), self.critic(h)
+
+
 def main():
     args = parse()
     if args.impl == "reference":
@@ -201,28 +301,49 @@ def main():
     import shared.clip_ppo_utils as U
     from shared.disturbances_gpu import DisturbanceWrapperGPU
     from shared.disturbance_types import DisturbanceSeverity
-    from clip_ppo_b200 import disturb as D
+    from clip_ppo_b200 import rollout as R
+    from clip_ppo_b200.distributed import GradBucket
 
     L = N.lib()                                   # raises if the CUDA library is missing: no fallback
     B, hw = args.batch, args.hw
     model = U.load_clip_model(args.model, device=dev)
-    engine = U._engine_for(model)
-    disturber = DisturbanceWrapperGPU(device=dev, seed=1234 + rank, severity=DisturbanceSeverity[args.severity])
-    ph, pw = D.cutout_patch(hw, hw, disturber.cutout_ratio)
+    out_dim = U._engine_for(model).cfg.out_dim
+    # identically seeded on every rank: the per-call scalars (contrast factor, cutout window) come from the CPU generator
+    disturber = DisturbanceWrapperGPU(device=dev, seed=1234, severity=DisturbanceSeverity[args.severity])
     window = (hw // 5, hw // 4)
 
-    g = torch.Generator(device=dev).manual_seed(rank)
-    x = torch.randint(0, 256, (B, 3, hw, hw), device=dev, generator=g, dtype=torch.uint8).float().div_(255.0)
-    noise = torch.randn(B, 3, hw, hw, device=dev, generator=g)
-    z = torch.relu(torch.randn(B, engine.cfg.out_dim, device=dev, generator=g))
-    grad_bucket = torch.zeros(AGENT_GRAD_ELEMS, device=dev) if world > 1 else None
+    # the disturbance kernel against the HBM roofline is a kernel timed ALONE (vs the burst copy peak): measured first, before
+    # the sustained passes push the part into its power cap
+    disturb_rows = disturb_hbm_rows(dev, peaks()) if (world == 1 and not args.no_secondary) else None
+
+    x8, noise, z = seeded_inputs(dev, rank * B, B, hw, out_dim)
+    x = x8.float().div_(255.0)
+    del x8
+
+    def path(xf, nz, zz):
+        d = disturber.apply_disturbances(xf, noise=nz, contrast_factor=1.1, cutout_start=window)
+        emb = U.generate_clip_embeddings(U.AblationMode.NONE, model, "image", xf.shape[0], dev, images=d * 255.0)
+        return U.compute_cosine_embedding_loss(zz, emb), emb
+
+    # the exchange of the path: the PPO agent's gradients.  One real backward (alignment loss of the agent's latents against
+    # the embeddings of this rank's first frames) fills them; every timed step all-reduces that same real gradient set.
+    bucket = saved_grads = agent = None
+    if world > 1:
+        torch.manual_seed(7)
+        agent = PolicyEncoder().to(dev)
+        with torch.no_grad():
+            _, emb0 = path(x[:CHUNK], noise[:CHUNK], z[:CHUNK])
+        obs84 = torch.nn.functional.interpolate(x[:CHUNK], size=(84, 84), mode="bilinear", align_corners=False)
+        h, logits, v = agent(obs84)
+        (U.compute_cosine_embedding_loss(h, emb0) + 1e-3 * logits.square().mean() + 1e-3 * v.square().mean()).backward()
+        bucket = GradBucket(agent.parameters())
+        saved_grads = [p.grad.clone() for p in bucket.params]
 
     def step_device():
-        d = disturber.apply_disturbances(x, noise=noise, contrast_factor=1.1, cutout_start=window)
-        emb = engine.encode(d, pre_scale=1.0, l2norm=True)      # == generate_clip_embeddings(images = d*255)
-        loss = U.compute_cosine_embedding_loss(z, emb)
-        if grad_bucket is not None:
-            dist.all_reduce(grad_bucket)
+        loss, _ = path(x, noise, z)
+        if bucket is not None:
+            torch._foreach_copy_([p.grad for p in bucket.params], saved_grads)
+            bucket.all_reduce_mean()
         return loss
 
     def barrier():
@@ -307,10 +428,11 @@ def main():
             # the reference benchmark's conversion on the device); randn on device + CPU-generator draws as in the reference
             d = disturber.apply_disturbances(dev_u8[b])
             consumed[b].record(main_stream)
-            emb = engine.encode(d, pre_scale=1.0, l2norm=True)
+            emb = U.generate_clip_embeddings(U.AblationMode.NONE, model, "image", B, dev, images=d * 255.0)
             ls = U.compute_cosine_embedding_loss(z, emb)
-            if grad_bucket is not None:
-                dist.all_reduce(grad_bucket)
+            if bucket is not None:
+                torch._foreach_copy_([p.grad for p in bucket.params], saved_grads)
+                bucket.all_reduce_mean()
             host_loss[b:b + 1].copy_(ls.reshape(1), non_blocking=True)
             done[b].record(main_stream)
             if i > 0:
@@ -336,7 +458,13 @@ def main():
                "ms_per_step": ms_e2e / args.steps,
                "note": "uint8 frames from pinned host memory, H2D prefetched one step ahead on a copy stream, handed to "
                        "apply_disturbances as uint8 (read as .float()/255 inside the kernel); noise drawn on device "
-                       "(randn); loss copied back to pinned memory every step"}
+                       "(randn); `* 255` and generate_clip_embeddings as in the scripts; loss copied back to pinned memory every step"}
+        del host, dev_u8
+
+    # ---- N > 1: shard-vs-whole parity and the strong-scaling figure ---------------------------------
+    parity = strong = None
+    if world > 1:
+        parity, strong = multi_gpu_checks(args, dist, dev, rank, world, path, agent, bucket, U, model, out_dim, max_over_ranks, barrier)
 
     if rank != 0:
         if dist is not None:
@@ -366,28 +494,198 @@ def main():
                      "timed_pass": f"second pass of the same {args.steps} steps with an event pair around every GEMM launch "
                                    f"({ms_total_timed / args.steps:.2f} ms/step; the headline pass runs without them)",
                      "by_shape": by_shape,
-                     "tower_tflops_incl_all_kernels": world * B * args.steps * FLOPS_PER_IMAGE_BY_MODEL[args.model] / (ms_total * 1e-3) / 1e12 / world},
+                     "tower_tflops_incl_all_kernels": B * args.steps * FLOPS_PER_IMAGE_BY_MODEL[args.model] / (ms_total * 1e-3) / 1e12},
         "loss": loss_value,
     }
     if e2e is not None:
         line["e2e"] = e2e
+    if parity is not None:
+        line["parity"], line["strong"] = parity, strong
+    del x, noise
+    torch.cuda.empty_cache()
+    if world == 1 and not args.no_secondary:
+        line["secondary"] = secondary_measurements(args, dev, pk, disturb_rows)
+        line["eager_gpu_baseline"] = eager_gpu_baseline(args, dev)
     if not args.no_cpu_baseline and world == 1:
-        from oracle import vit as ov
         torch.set_num_threads(os.cpu_count() or 1)
-        sd = ov.random_state_dict(ov.VIT_B32, 0)
+        step, kind = reference_step_fn("cpu", args.model, args.severity)
         n = args.cpu_sample
-        frames, nz, zz = cpu_inputs(n, hw)
+        frames, zz = cpu_inputs(n, hw, out_dim)
         with torch.no_grad():
-            cpu_path_step(sd, frames[:16], nz[:16], zz[:16], args.severity)
+            step(frames[:16], zz[:16])
             t0 = time.perf_counter()
-            cpu_path_step(sd, frames, nz, zz, args.severity)
+            step(frames, zz)
             dt = time.perf_counter() - t0
-        line["cpu_baseline"] = {"value": n / dt, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "port",
-                                "sample": f"{n} frames of the same workload through the fp32 CPU oracle port "
-                                          f"(torch CPU ops, all host threads), {dt:.1f} s"}
+        what = ("the reference's own functions (oracle/_ref: shared/disturbances_gpu.py, shared/clip_ppo_utils.py, unmodified) over "
+                "the fp32 tower of oracle/vit.py" if kind == "reference" else "the fp32 CPU oracle port")
+        line["cpu_baseline"] = {"value": n / dt, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": kind,
+                                "sample": f"{n} frames of the same workload through {what} (all host threads), {dt:.1f} s"}
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
+
+
+def multi_gpu_checks(args, dist, dev, rank, world, path, agent, bucket, U, model, out_dim, max_over_ranks, barrier):
+    """(parity, strong).  parity: every rank runs the path on ITS shard of one seeded global batch (CHUNK frames per rank); rank 0
+    also runs the whole batch alone.  Embeddings must agree exactly (the tower is batch-invariant bit for bit); the
+    GradBucket-averaged agent gradients must equal the single-rank full-batch gradients up to fp32 summation order.
+    strong: the same step with the TOTAL work fixed at --batch frames (--batch / N per GPU)."""
+    hw = args.hw
+    n = CHUNK
+    x8, nz, zz = seeded_inputs(dev, rank * n, n, hw, out_dim)
+    xs = x8.float() / 255.0
+    with torch.no_grad():
+        _, emb = path(xs, nz, zz)
+    gathered = [torch.empty_like(emb) for _ in range(world)]
+    dist.all_gather(gathered, emb)
+    # data-parallel gradient: local mean loss, backward, bucket average
+    agent.zero_grad(set_to_none=False)
+    obs84 = torch.nn.functional.interpolate(xs, size=(84, 84), mode="bilinear", align_corners=False)
+    h, _, _ = agent(obs84)
+    U.compute_cosine_embedding_loss(h, emb).backward()
+    bucket.all_reduce_mean()
+    dp_grads = torch.cat([p.grad.reshape(-1) for p in bucket.params]).clone()
+    parity = None
+    if rank == 0:
+        X8, NZ, ZZ = seeded_inputs(dev, 0, n * world, hw, out_dim)
+        XS = X8.float() / 255.0
+        with torch.no_grad():
+            _, emb_all = path(XS, NZ, ZZ)
+        emb_max_abs = float((torch.cat(gathered) - emb_all).abs().max().item())
+        agent.zero_grad(set_to_none=False)
+        H, _, _ = agent(torch.nn.functional.interpolate(XS, size=(84, 84), mode="bilinear", align_corners=False))
+        U.compute_cosine_embedding_loss(H, emb_all).backward()
+        full = torch.cat([p.grad.reshape(-1) for p in bucket.params])
+        grad_rel = float(((dp_grads - full).abs().max() / full.abs().max()).item())
+        # what fp32 summation order alone does to the same full-batch gradient: the rows in reversed order, one rank
+        agent.zero_grad(set_to_none=False)
+        Hr, _, _ = agent(torch.nn.functional.interpolate(XS.flip(0), size=(84, 84), mode="bilinear", align_corners=False))
+        U.compute_cosine_embedding_loss(Hr, emb_all.flip(0)).backward()
+        rev = torch.cat([p.grad.reshape(-1) for p in bucket.params])
+        reorder_rel = float(((rev - full).abs().max() / full.abs().max()).item())
+        parity = {"emb_max_abs": emb_max_abs, "grad_rel": grad_rel, "grad_rel_of_row_order_alone": reorder_rel, "frames": n * world,
+                  "what": f"{world} ranks x {n}-frame shards of one seeded global batch vs rank 0 running all {n * world} frames alone; "
+                          "grad = NatureCNN agent's alignment-loss gradients after GradBucket.all_reduce_mean vs the full-batch backward"}
+        del X8, NZ, ZZ, XS
+    del x8, nz, zz, xs
+    torch.cuda.empty_cache()
+    # strong scaling: --batch frames in total
+    per = max(CHUNK, args.batch // world // CHUNK * CHUNK)
+    x8, nz, zz = seeded_inputs(dev, rank * per, per, hw, out_dim)
+    xs = x8.float() / 255.0
+
+    def step():
+        loss, _ = path(xs, nz, zz)
+        bucket.all_reduce_mean()
+        return loss
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(args.steps):
+        step()
+    b.record()
+    barrier()
+    ms = max_over_ranks(a.elapsed_time(b))
+    strong = {"value": world * per * args.steps / (ms * 1e-3), "unit": "frames/s", "global_batch": world * per,
+              "per_gpu_batch": per, "ms_per_step": ms / args.steps, "scaling": "strong"}
+    return parity, strong
+
+
+def disturb_hbm_rows(dev, pk):
+    """The fused disturbance kernel alone against the HBM roofline: 12 algorithmic bytes per element (x + supplied noise + out)."""
+    from shared.disturbances_gpu import DisturbanceWrapperGPU
+    from shared.disturbance_types import DisturbanceSeverity
+    rows = []
+    for sev, shape in (("MODERATE", (4096, 3, 224, 224)), ("SEVERE", (4096, 3, 224, 224)), ("HARD", (16384, 1, 84, 84)),
+                       ("SEVERE", (16384, 3, 84, 84))):
+        g = torch.Generator(device=dev).manual_seed(5)
+        xx = torch.rand(shape, device=dev, generator=g)
+        nn_ = torch.randn(shape, device=dev, generator=g)
+        w = DisturbanceWrapperGPU(device=dev, seed=3, severity=DisturbanceSeverity[sev])
+        win = (shape[2] // 5, shape[3] // 4)
+        ms = event_ms(lambda: w.apply_disturbances(xx, noise=nn_, contrast_factor=1.1, cutout_start=win), 10, warm=3)
+        gbs = 12.0 * xx.numel() / (ms * 1e-3) / 1e9
+        rows.append({"severity": sev, "shape": list(shape), "us": round(ms * 1e3, 1), "gb_per_s": round(gbs, 1),
+                     "frac_of_hbm_peak": round(gbs / pk["hbm"], 4)})
+        del xx, nn_
+    torch.cuda.empty_cache()
+    return rows
+
+
+def secondary_measurements(args, dev, pk, disturb_rows):
+    """Short CUDA-event measurements of the other BASELINE configs (rank 0, N = 1), each reproducible from tools/."""
+    import shared.clip_ppo_utils as U
+    from shared.disturbances_gpu import DisturbanceWrapperGPU
+    from shared.disturbance_types import DisturbanceSeverity
+    from clip_ppo_b200 import rollout as R
+    out = {}
+    out["disturb_hbm"] = {"bytes_per_element": 12, "peak_gb_per_s": pk["hbm"], "peak_source": pk["source"], "rows": disturb_rows,
+                          "when": "first thing in the run (kernel timed alone, 10 launches after 3 warm-ups each)"}
+    # (2) BASELINE configs[3]: Atari stacks (84x84 gray x 4, HARD), one GPU's share of 256 envs x 128 steps over 8 GPUs
+    model = U.load_clip_model("ViT-B/32", device=dev)
+    stacks = 4096
+    g = torch.Generator(device=dev).manual_seed(6)
+    obs = torch.randint(0, 256, (stacks, 4, 84, 84), device=dev, generator=g).float()
+    zc = torch.relu(torch.randn(stacks, 512, device=dev, generator=g))
+    proj = torch.nn.Linear(2048, 512).to(dev)                       # temporal_projection (clip_ppo_atari.py:184-187)
+    w = DisturbanceWrapperGPU(device=dev, seed=3, severity=DisturbanceSeverity.HARD)
+
+    def atari():
+        with torch.no_grad():
+            dobs = R.disturb_atari_stack(w, obs)                                        # clip_ppo_atari.py:568-584
+            rgb = R.convert_atari_frames_for_clip(dobs / 255.0)                          # :249-269, :661 (the double /255 quirk)
+            e = R.process_multiframe_clip_embeddings(rgb, model, U.AblationMode.NONE, "image", stacks, dev)
+            return U.compute_cosine_embedding_loss(zc, proj(e))                          # :730
+    ms = event_ms(atari, 3)
+    out["atari_84_to_224"] = {"config": "BASELINE configs[3]: Atari stacks 4 x 84x84 gray, HARD disturbances per stacked frame, "
+                                        "84 -> 224 up-sampling inside the fused preprocess, 4 ViT-B/32 embeddings per stack, "
+                                        "temporal projection, alignment loss; one GPU's share (32 envs x 128 steps)",
+                              "stacks": stacks, "clip_frames": 4 * stacks, "ms": round(ms, 2),
+                              "clip_frames_per_s": round(4 * stacks / (ms * 1e-3), 1), "stacks_per_s": round(stacks / (ms * 1e-3), 1)}
+    del obs, zc, model
+    torch.cuda.empty_cache()
+    # (3) BASELINE configs[4]'s tower variant: ViT-L/14 (T = 257: the tcgen05 attention kernel), same step at 1024 frames
+    if args.model != "ViT-L/14":
+        model = U.load_clip_model("ViT-L/14", device=dev)
+        nL = 1024
+        x8, nz, zz = seeded_inputs(dev, 0, nL, 224, 768)
+        xs = x8.float() / 255.0
+        w = DisturbanceWrapperGPU(device=dev, seed=3, severity=DisturbanceSeverity.MODERATE)
+
+        def l14():
+            d = w.apply_disturbances(xs, noise=nz, contrast_factor=1.1, cutout_start=(44, 56))
+            e = U.generate_clip_embeddings(U.AblationMode.NONE, model, "image", nL, dev, images=d * 255.0)
+            return U.compute_cosine_embedding_loss(zz, e)
+        ms = event_ms(l14, 3)
+        out["vit_l14"] = {"config": "BASELINE configs[4] tower variant: ViT-L/14 (width 1024, 24 blocks, 257 tokens), 1024 frames of 224x224x3, "
+                                    "MODERATE, same public calls", "frames": nL, "ms": round(ms, 2),
+                          "frames_per_s": round(nL / (ms * 1e-3), 1),
+                          "tower_tflops_incl_all_kernels": round(nL * FLOPS_PER_IMAGE_BY_MODEL["ViT-L/14"] / (ms * 1e-3) / 1e12, 1)}
+        del x8, nz, zz, xs, model
+        torch.cuda.empty_cache()
+    return out
+
+
+def eager_gpu_baseline(args, dev):
+    """The reference's own functions on this GPU: shared/disturbances_gpu.py (torchvision transforms) and
+    shared/clip_ppo_utils.py (F.interpolate, normalise, encode_image, F.normalize, cosine loss) out of oracle/_ref, with the
+    fp16 eager tower clip.load would hand them (tools/eager_tower.py).  Same frames, 1024 per step."""
+    try:
+        step, kind = reference_step_fn(str(dev), args.model, args.severity)
+    except Exception as e:          # never lose the headline over the baseline leg
+        return {"unavailable": f"{type(e).__name__}: {e}"[:300]}
+    if step is None:
+        return {"unavailable": "oracle/_ref is not staged (run python oracle/build_ref.py where /root/reference exists)"}
+    n = 1024
+    x8, _, zz = seeded_inputs(dev, 0, n, args.hw, 512 if args.model == "ViT-B/32" else 768, want_noise=False)
+    xs = x8.float() / 255.0
+    with torch.no_grad():
+        ms = event_ms(lambda: step(xs, zz), 3)
+    return {"value": n / (ms * 1e-3), "unit": "frames/s", "frames_per_step": n, "ms_per_step": round(ms, 2), "kind": kind,
+            "what": "reference's own DisturbanceWrapperGPU.apply_disturbances (device randn, torchvision ops) -> *255 -> "
+                    "generate_clip_embeddings (fp16 eager tower: cuDNN conv, cuBLAS, SDPA) -> compute_cosine_embedding_loss, device-resident frames"}
 
 
 if __name__ == "__main__":

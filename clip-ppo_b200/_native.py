@@ -29,7 +29,7 @@ SYMBOLS = (
     "clipppo_cosine_loss_fwd", "clipppo_cosine_loss_bwd", "clipppo_gae_f32", "clipppo_ppo_loss_f32",
     "clipppo_vit_create", "clipppo_vit_destroy", "clipppo_vit_workspace_bytes", "clipppo_vit_encode",
     "clipppo_text_create", "clipppo_text_destroy", "clipppo_text_workspace_bytes", "clipppo_text_encode",
-    "clipppo_preprocess_bf16", "clipppo_layernorm_bf16", "clipppo_gemm_bf16", "clipppo_gemm_bf16_fused", "clipppo_gemm_bf16_probe", "clipppo_rowstats_bf16", "clipppo_attention_bf16",
+    "clipppo_preprocess_bf16", "clipppo_layernorm_bf16", "clipppo_gemm_bf16", "clipppo_gemm_bf16_fused", "clipppo_rowstats_bf16", "clipppo_attention_bf16",
     "clipppo_attention_causal_bf16",
 )
 
@@ -98,7 +98,8 @@ def lib() -> C.CDLL:
     L.clipppo_gemm_bf16.argtypes = [vp, vp, i, i, i, i, vp, vp, i, vp, C.c_int64, vp]
     L.clipppo_gemm_bf16_fused.argtypes = [vp, vp, i, i, i, i, vp, vp, vp, vp, C.c_int64, vp]
     L.clipppo_rowstats_bf16.argtypes = [vp, i, i, C.c_int64, vp, vp]
-    L.clipppo_gemm_bf16_probe.argtypes = [vp, vp, i, i, i, i, vp, vp, C.c_int64, i, vp]
+    if hasattr(L, "clipppo_gemm_bf16_probe"):            # probe builds only (CLIPPPO_BUILD_PROBES=1)
+        L.clipppo_gemm_bf16_probe.argtypes = [vp, vp, i, i, i, i, vp, vp, C.c_int64, i, vp]
     L.clipppo_attention_bf16.argtypes = [vp, i, i, i, i, vp, vp]
     L.clipppo_attention_causal_bf16.argtypes = [vp, i, i, i, i, vp, vp]
     L.clipppo_text_create.argtypes = [C.POINTER(vp), C.POINTER(TextConfig), C.POINTER(TextWeights)]

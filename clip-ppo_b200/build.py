@@ -44,6 +44,8 @@ def _newest_header() -> float:
 def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(BUILD, exist_ok=True)
     nvcc = _nvcc()
+    # measurement-only GEMM variants (tools/gemm_probe.py): never in the product library unless asked for
+    flags = NVCC_FLAGS + (["-DCLIPPPO_BUILD_PROBES"] if os.environ.get("CLIPPPO_BUILD_PROBES", "") not in ("", "0") else [])
     hdr = _newest_header()
     sources = [s for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
     jobs = []
@@ -51,7 +53,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         s = os.path.join(CSRC, src)
         o = os.path.join(BUILD, src.replace(".cu", ".o"))
         if force or not os.path.exists(o) or os.path.getmtime(o) < max(os.path.getmtime(s), hdr):
-            cmd = [nvcc, *NVCC_FLAGS, "-c", s, "-o", o]
+            cmd = [nvcc, *flags, "-c", s, "-o", o]
             if verbose:
                 cmd.insert(1, "-Xptxas=-v")
             jobs.append((src, cmd))

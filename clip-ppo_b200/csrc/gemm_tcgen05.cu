@@ -605,6 +605,7 @@ int make_bf16_kmajor_tmap(CUtensorMap* map, const void* ptr, int rows, int K, lo
     return CLIPPPO_OK;
 }
 
+#ifdef CLIPPPO_BUILD_PROBES
 // Probe-only dispatcher (clipppo_gemm_bf16_probe): pair mode, the three hot epilogues, DBG 1..3.
 template <int DBG>
 int launch_gemm_dbg(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& g, int epilogue, cudaStream_t stream) {
@@ -637,6 +638,8 @@ int gemm_probe_launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmAr
     }
     return CLIPPPO_ERR_UNSUPPORTED;
 }
+
+#endif  // CLIPPPO_BUILD_PROBES
 
 // Small M with the reduce-add epilogue (opt-in, CLIPPPO_GEMM_KSPLIT=auto | n): when the tiles alone leave most
 // CTA pairs idle, cut each tile's K range into slices (>= 6 k-blocks each) until the pairs are covered; every
@@ -737,6 +740,7 @@ extern "C" int clipppo_gemm_bf16_fused(const void* a_bf16, const void* w_bf16, i
     return gemm_bf16_launch(ta, tb, M, N, K, epilogue, bias, nullptr, 0, out_bf16, ldo, as_stream(stream), row_stats, colsum);
 }
 
+#ifdef CLIPPPO_BUILD_PROBES
 // Measurement probe, not part of the product path: the same GEMM with parts of the kernel switched
 // off (dbg bit 0: epilogue only drains TMEM; bit 1: no TMA loads), to attribute time to the TMA feed,
 // the MMA issue and the epilogue.  Results are garbage by construction.
@@ -752,3 +756,4 @@ extern "C" int clipppo_gemm_bf16_probe(const void* a_bf16, const void* w_bf16, i
     GemmArgs g{M, N, K, bias, nullptr, 0, out, ldo, nullptr, nullptr, 1};
     return gemm_probe_launch(ta, tb, g, epilogue, dbg, as_stream(stream));
 }
+#endif  // CLIPPPO_BUILD_PROBES

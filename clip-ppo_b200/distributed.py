@@ -22,8 +22,9 @@ def shard_range(n: int, rank: int, world: int) -> Tuple[int, int]:
 
 
 class GradBucket:
-    """Flat fp32 bucket over the trainable parameters' gradients.  ``all_reduce_mean()`` copies the
-    grads in, all-reduces once (sum), divides by the world size and copies them back - one
+    """Flat fp32 bucket over the trainable parameters' gradients.  ``all_reduce_mean()`` gathers the
+    grads with one multi-tensor copy, all-reduces once (sum), divides by the world size and scatters them back with a
+    second multi-tensor copy - four launches and one
     collective of ~6.7 MB (MiniGrid agent) / ~11 MB (Atari image agent) per optimizer step."""
 
     def __init__(self, params: Iterable[torch.nn.Parameter], group: Optional[dist.ProcessGroup] = None):
@@ -34,6 +35,12 @@ class GradBucket:
         self.numel = sum(p.numel() for p in self.params)
         self.flat = torch.zeros(self.numel, dtype=torch.float32, device=dev)
         self.group = group
+        # one view of the bucket per parameter, in parameter order: gather / scatter are single multi-tensor copies
+        self.views: List[torch.Tensor] = []
+        off = 0
+        for p in self.params:
+            self.views.append(self.flat[off:off + p.numel()].view(p.shape))
+            off += p.numel()
 
     def all_reduce_mean(self) -> None:
         if not (dist.is_available() and dist.is_initialized()):
@@ -41,24 +48,14 @@ class GradBucket:
         world = dist.get_world_size(self.group)
         if world == 1:
             return
-        off = 0
-        for p in self.params:
-            n = p.numel()
+        for p, v in zip(self.params, self.views):           # parameters the backward never reached
             if p.grad is None:
-                self.flat[off:off + n].zero_()
-            else:
-                self.flat[off:off + n].copy_(p.grad.reshape(-1))
-            off += n
+                p.grad = torch.zeros_like(v)
+        grads = [p.grad for p in self.params]
+        torch._foreach_copy_(self.views, grads)             # gather: one launch
         dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
         self.flat.div_(world)
-        off = 0
-        for p in self.params:
-            n = p.numel()
-            if p.grad is None:
-                p.grad = self.flat[off:off + n].reshape(p.shape).clone()
-            else:
-                p.grad.copy_(self.flat[off:off + n].reshape(p.shape))
-            off += n
+        torch._foreach_copy_(grads, self.views)             # scatter back: one launch
 
 
 def global_advantage_stats(adv: torch.Tensor, group: Optional[dist.ProcessGroup] = None) -> Tuple[torch.Tensor, torch.Tensor]:

@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define CLIPPPO_ABI_VERSION 2
+#define CLIPPPO_ABI_VERSION 3
 
 typedef enum clipppo_status {
     CLIPPPO_OK = 0,
@@ -259,12 +259,15 @@ int clipppo_gemm_bf16(const void* a_bf16, const void* w_bf16, int M, int N, int 
 int clipppo_gemm_bf16_fused(const void* a_bf16, const void* w_bf16, int M, int N, int K, int epilogue,
                             const float* bias, const float* row_stats, const float* colsum,
                             void* out_bf16, int64_t ldo, clipppo_stream_t stream);
-/* Measurement probe (profiles/ only, never on the product path): the GEMM above with parts switched
+#ifdef CLIPPPO_BUILD_PROBES
+/* Measurement probe - compiled only with -DCLIPPPO_BUILD_PROBES (CLIPPPO_BUILD_PROBES=1 python clip-ppo_b200/build.py --force),
+ * absent from the product library and its ABI (profiles/ only, never on the product path): the GEMM above with parts switched
  * off - dbg 1: the epilogue drains TMEM but does not compute or store; 2: no TMA operand loads;
  * 3: both; 4: boxes staged but never sent (no output traffic); 8: epilogue arithmetic only.
  * Output is garbage by construction; only the duration means anything. */
 int clipppo_gemm_bf16_probe(const void* a_bf16, const void* w_bf16, int M, int N, int K, int epilogue,
                             const float* bias, void* out, int64_t ldo, int dbg, clipppo_stream_t stream);
+#endif
 int clipppo_attention_bf16(const void* qkv_bf16, int n_images, int tokens, int heads, int head_dim,
                            void* out_bf16, clipppo_stream_t stream);
 /* the same under the text tower's causal mask ([clip] build_attention_mask): query t attends to keys 0 .. t */

@@ -1,4 +1,5 @@
-"""Not a test: attributes GEMM time to TMA feed / MMA issue / epilogue.  python tools/gemm_probe.py [M]
+"""Not a test: attributes GEMM time to TMA feed / MMA issue / epilogue.  Needs a probe build of the library:
+CLIPPPO_BUILD_PROBES=1 python clip-ppo_b200/build.py --force; python tools/gemm_probe.py [M]
 
 For each tower GEMM shape: the product kernel, the same kernel with the epilogue reduced to a TMEM
 drain (dbg 1), without TMA loads (dbg 2), with neither (dbg 3 = pure tcgen05 issue rate), and cuBLAS
