@@ -31,6 +31,7 @@ SYMBOLS = (
     "clipppo_text_create", "clipppo_text_destroy", "clipppo_text_workspace_bytes", "clipppo_text_encode",
     "clipppo_preprocess_bf16", "clipppo_layernorm_bf16", "clipppo_gemm_bf16", "clipppo_gemm_bf16_fused", "clipppo_rowstats_bf16", "clipppo_attention_bf16",
     "clipppo_attention_causal_bf16",
+    "clipppo_nature_workspace_bytes", "clipppo_nature_forward", "clipppo_nature_backward",
 )
 
 
@@ -102,6 +103,9 @@ def lib() -> C.CDLL:
         L.clipppo_gemm_bf16_probe.argtypes = [vp, vp, i, i, i, i, vp, vp, C.c_int64, i, vp]
     L.clipppo_attention_bf16.argtypes = [vp, i, i, i, i, vp, vp]
     L.clipppo_attention_causal_bf16.argtypes = [vp, i, i, i, i, vp, vp]
+    L.clipppo_nature_workspace_bytes.argtypes = [i, i, C.POINTER(sz)]
+    L.clipppo_nature_forward.argtypes = [vp, C.POINTER(C.c_int64), C.c_float, i, i] + [vp] * 8 + [vp, vp, sz, vp]
+    L.clipppo_nature_backward.argtypes = [vp, vp, vp, C.POINTER(C.c_int64), C.c_float, i, i, vp, vp] + [vp] * 8 + [vp, sz, vp]
     L.clipppo_text_create.argtypes = [C.POINTER(vp), C.POINTER(TextConfig), C.POINTER(TextWeights)]
     L.clipppo_text_destroy.argtypes = [vp]
     L.clipppo_text_workspace_bytes.argtypes = [vp, i, C.POINTER(sz)]

@@ -20,7 +20,7 @@ BUILD = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libclipppo_b200.so")
 
 SOURCES = ["capi.cu", "prof.cu", "disturb.cu", "losses.cu", "preprocess.cu", "layernorm.cu",
-           "gemm_tcgen05.cu", "attention.cu", "attention_tc.cu", "vit.cu"]
+           "gemm_tcgen05.cu", "attention.cu", "attention_tc.cu", "vit.cu", "policy.cu"]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",

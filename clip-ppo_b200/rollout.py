@@ -114,6 +114,20 @@ def action_value_and_latents(agent, obs: torch.Tensor, action: torch.Tensor):
     return action, probs.log_prob(action), probs.entropy(), agent.critic(hidden), hidden.detach()
 
 
+# ---- §8f-1: the PPO encoder on the native kernels ----------------------------------------------------
+def use_native_encoder(agent):
+    """Swap the scripts' ``agent.network`` (``nn.Sequential`` NatureCNN, clip_ppo_minigrid.py:229-242 / clip_ppo_atari.py:196-209)
+    for :class:`clip_ppo_b200.policy.NatureCNN` in place: same parameter names, values, state-dict keys and call signature
+    (``agent.network(x)``), forward + backward on csrc/policy.cu.  Build the optimizer AFTER the swap (the parameters are new
+    objects).  FROZEN_CLIP agents (``network`` is the CLIP tower / an Identity) are left alone."""
+    import torch.nn as nn
+    from .policy import NatureCNN
+    net = getattr(agent, "network", None)
+    if isinstance(net, nn.Sequential) and len(net) == 9 and isinstance(net[0], nn.Conv2d) and isinstance(net[7], nn.Linear):
+        agent.network = NatureCNN.from_sequential(net)
+    return agent
+
+
 # ---- a21: GAE (clip_ppo_minigrid.py:437-450 = clip_ppo_atari.py:619-632) ---------------------------
 def compute_gae(rewards: torch.Tensor, values: torch.Tensor, dones: torch.Tensor, next_value: torch.Tensor,
                 next_done: torch.Tensor, gamma: float = 0.99, gae_lambda: float = 0.95) -> Tuple[torch.Tensor, torch.Tensor]:

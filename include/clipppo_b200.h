@@ -274,6 +274,32 @@ int clipppo_attention_bf16(const void* qkv_bf16, int n_images, int tokens, int h
 int clipppo_attention_causal_bf16(const void* qkv_bf16, int n_seqs, int tokens, int heads, int head_dim,
                                   void* out_bf16, clipppo_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * §8f-1  the PPO encoder (NatureCNN) of the reference's Agent, forward and backward, fp32.
+ * Replaces `self.network(x)` and its autograd (minigrid_experiments/clip_ppo/clip_ppo_minigrid.py:229-242, :245-262;
+ * atari_experiments/clip_ppo/clip_ppo_atari.py:196-209, :229): conv 8x8 s4 (C -> 32), conv 4x4 s2 (32 -> 64),
+ * conv 3x3 s1 (64 -> 64), flatten, Linear 3136 -> 512, ReLU after each.
+ *   obs        fp32, logical [mb, C, 84, 84] addressed through element strides (NCHW stacks or the NHWC view of
+ *              MiniGrid frames); multiplied by in_scale on the way in (1/255 = the scripts' `/ 255.0`)
+ *   weights    PyTorch layouts: conv [OC, C, KH, KW], fc [512, 3136] (columns in (c, h, w) order), biases
+ *   hidden     [mb, 512] = network(x)
+ *   workspace  clipppo_nature_workspace_bytes(mb, C) bytes, 256-byte aligned; holds the three activations for backward
+ * No im2col matrix is ever materialised: every convolution operand is gathered inside the GEMM that consumes it.
+ * Observations whose strides do not keep every 4-element group of a filter row contiguous and 16-byte aligned return
+ * CLIPPPO_ERR_UNSUPPORTED (the caller copies them to NCHW first).
+ * backward: gradients of all eight parameters for grad_hidden = dL/d hidden, given the forward's observations and
+ * workspace and the current conv2 / conv3 weights; deterministic (no atomics, fixed-order split reductions).
+ * ---------------------------------------------------------------------------------------- */
+int clipppo_nature_workspace_bytes(int mb, int channels, size_t* bytes);
+int clipppo_nature_forward(const float* obs, const int64_t obs_strides_host[4], float in_scale, int mb, int channels,
+                           const float* w1, const float* b1, const float* w2, const float* b2, const float* w3,
+                           const float* b3, const float* wfc, const float* bfc, float* hidden, void* workspace,
+                           size_t workspace_bytes, clipppo_stream_t stream);
+int clipppo_nature_backward(const float* grad_hidden, const float* hidden, const float* obs,
+                            const int64_t obs_strides_host[4], float in_scale, int mb, int channels, const float* w2,
+                            const float* w3, float* gw1, float* gb1, float* gw2, float* gb2, float* gw3, float* gb3,
+                            float* gwfc, float* gbfc, void* workspace, size_t workspace_bytes, clipppo_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
