@@ -2,8 +2,9 @@
 when the real one is not importable.  It exposes exactly the surface the reference touches:
 ``clip.load`` (shared/clip_ppo_utils.py:90), ``clip.tokenize`` (:136), ``clip.model.CLIP`` and
 ``clip.model.VisionTransformer`` (:187, :212).  The image tower it returns runs on the sm_100a
-kernels and so does the text tower (``encode_text`` on token ids); only the BPE tokenizer is missing -
-its 1.3 MB merges file ships with the openai package and cannot be reproduced offline - so ``tokenize`` raises.
+kernels and so does the text tower (``encode_text`` on token ids).  ``tokenize`` is the byte-level BPE of
+clip_compat/tokenizer.py; its 1.3 MB merge list is DATA of the openai package that cannot be reproduced offline, so
+``CLIPPPO_BPE_PATH`` has to name it (``tokenize`` raises FileNotFoundError with that remedy otherwise).
 
 Weight sources, in order: an explicit state dict (``load(..., state_dict=...)``), a checkpoint file
 (``CLIPPPO_CLIP_WEIGHTS``: a ``torch.save``d openai state dict, module or TorchScript archive).  With neither,
@@ -24,7 +25,7 @@ import torch
 from . import model
 from .model import CLIP, VisionTransformer, random_visual_state_dict, random_text_state_dict, ARCHS
 
-__all__ = ["load", "tokenize", "available_models", "model", "CLIP", "VisionTransformer"]
+__all__ = ["load", "tokenize", "tokenizer_available", "available_models", "model", "CLIP", "VisionTransformer"]
 
 
 def available_models():
@@ -70,5 +71,12 @@ def load(name: str = "ViT-B/32", device: str | torch.device = "cuda", jit: bool 
 
 
 def tokenize(texts, context_length: int = 77, truncate: bool = False):
-    raise NotImplementedError("clip_compat has no BPE tokenizer (the merges file ships with openai/CLIP): install it for "
-                              "string descriptions, or pass pre-tokenised [N, 77] ids to generate_clip_embeddings / encode_text")
+    """``clip.tokenize`` on the byte-level BPE of clip_compat/tokenizer.py.  The merge list is data of the openai package:
+    ``CLIPPPO_BPE_PATH`` must name it (FileNotFoundError with the remedy otherwise)."""
+    from .tokenizer import tokenize as _tokenize
+    return _tokenize(texts, context_length, truncate)
+
+
+def tokenizer_available() -> bool:
+    p = os.environ.get("CLIPPPO_BPE_PATH", "")
+    return bool(p) and os.path.exists(p)

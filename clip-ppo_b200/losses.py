@@ -133,11 +133,19 @@ def ppo_loss(newlogprob: torch.Tensor, entropy: torch.Tensor, newvalue: torch.Te
              advantages: torch.Tensor, returns: torch.Tensor, old_values: torch.Tensor,
              clip_loss: Optional[torch.Tensor] = None, clip_lambda: float = 0.0, clip_coef: float = 0.1,
              ent_coef: float = 0.01, vf_coef: float = 0.5, norm_adv: bool = True,
-             clip_vloss: bool = True) -> Dict[str, torch.Tensor]:
+             clip_vloss: bool = True, adv_stats: Optional[tuple] = None) -> Dict[str, torch.Tensor]:
     """The reference's minibatch loss (clip_ppo_minigrid.py:498-531,559) as one launch.  Returns
     a dict of 0-d tensors: the differentiable total `loss` (gradients flow to newlogprob, entropy,
-    newvalue and clip_loss) plus the detached diagnostics - no `.item()` sync is forced."""
+    newvalue and clip_loss) plus the detached diagnostics - no `.item()` sync is forced.
+
+    ``adv_stats=(mean, std)`` (additive; 0-d tensors or floats): normalise the advantages with THESE statistics instead of
+    the minibatch's own (reference :509).  Data-parallel runs pass ``distributed.global_advantage_stats(adv)`` so that every
+    rank's shard is normalised exactly as the single-GPU run normalises the whole minibatch."""
     _require_cuda(newlogprob, "ppo_loss")
+    if adv_stats is not None and norm_adv:
+        mean, std = adv_stats
+        advantages = (advantages - mean) / (std + 1e-8)
+        norm_adv = False
     if clip_loss is not None and not torch.is_tensor(clip_loss):
         clip_loss = torch.tensor(float(clip_loss), dtype=torch.float32, device=newlogprob.device)
     loss, stats = _PpoLoss.apply(newlogprob, entropy, newvalue, old_logprob, advantages, returns, old_values,

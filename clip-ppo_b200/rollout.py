@@ -138,6 +138,6 @@ def compute_gae(rewards: torch.Tensor, values: torch.Tensor, dones: torch.Tensor
 def ppo_minibatch_loss(newlogprob, entropy, newvalue, old_logprob, advantages, returns, old_values,
                        clip_loss: Optional[torch.Tensor] = None, clip_lambda: float = 0.0, clip_coef: float = 0.1,
                        ent_coef: float = 0.01, vf_coef: float = 0.5, norm_adv: bool = True,
-                       clip_vloss: bool = True) -> Dict[str, torch.Tensor]:
+                       clip_vloss: bool = True, adv_stats: Optional[tuple] = None) -> Dict[str, torch.Tensor]:
     return L.ppo_loss(newlogprob, entropy, newvalue, old_logprob, advantages, returns, old_values, clip_loss,
-                      clip_lambda, clip_coef, ent_coef, vf_coef, norm_adv, clip_vloss)
+                      clip_lambda, clip_coef, ent_coef, vf_coef, norm_adv, clip_vloss, adv_stats)

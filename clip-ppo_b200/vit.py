@@ -115,6 +115,7 @@ class VitEngine:
     # the FROZEN_CLIP policy path (reference clip_ppo_minigrid.py:249-254, clip_ppo_atari.py:213-228: E
     # frames inside every policy forward), so small batches replay one captured CUDA graph instead.
     GRAPH_MAX_IMAGES = 512
+    GRAPH_CACHE_ENTRIES = 4           # call shapes kept captured at a time (LRU): env-step batch, eval batch, a tail minibatch ...
 
     @torch.no_grad()
     def encode_graphed(self, images: torch.Tensor, pre_scale: float = 1.0 / 255.0, l2norm: bool = True,
@@ -128,8 +129,10 @@ class VitEngine:
         if images.dtype not in (torch.float32, torch.uint8):
             images = images.float()
         key = (tuple(images.shape), images.dtype, float(pre_scale), bool(l2norm), bool(prenormalized))
-        ent = self._graphs.get(key)
+        ent = self._graphs.pop(key, None)                 # re-inserted below: the dict is kept in least-recently-used order
         if ent is None:
+            while len(self._graphs) >= self.GRAPH_CACHE_ENTRIES:       # each entry owns an input, an output and a full workspace
+                self._graphs.pop(next(iter(self._graphs)))
             n = images.shape[0]
             static_in = torch.empty(images.shape, dtype=images.dtype, device=self.device)
             static_out = torch.empty((n, self.cfg.out_dim), dtype=torch.float32, device=self.device)
@@ -148,7 +151,7 @@ class VitEngine:
             with torch.cuda.graph(graph):
                 self._encode_into(static_in, static_out, ws, pre_scale, l2norm, prenormalized)
             ent = (graph, static_in, static_out, ws)
-            self._graphs[key] = ent
+        self._graphs[key] = ent
         graph, static_in, static_out, _ = ent
         static_in.copy_(images)
         graph.replay()

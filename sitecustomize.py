@@ -1,7 +1,13 @@
-"""Imported automatically by Python when this repository is on PYTHONPATH: installs the top-level aliases
-(`import clip_ppo_utils` -> this repository's shared.clip_ppo_utils) the reference scripts' sys.path hack needs.
-See clip-ppo_b200/dropin.py.  Nothing else happens here - in particular torch is not imported.  A `sitecustomize`
-further down sys.path (e.g. the distribution's) is shadowed by this file, so it is run from here afterwards."""
+"""OPT-IN drop-in hook.  Python imports a module named `sitecustomize` at start-up when it finds one on sys.path; with this
+repository on PYTHONPATH that is this file.  It does NOTHING unless CLIPPPO_DROPIN=1 is set: a repository on the path should
+not change how `import clip_ppo_utils` resolves for unrelated programs.
+
+    CLIPPPO_DROPIN=1 PYTHONPATH=/path/to/this/repo python clip_ppo_minigrid.py ...      # unmodified reference script
+
+With the variable set it installs the top-level aliases (`import clip_ppo_utils` -> this repository's shared.clip_ppo_utils)
+that the reference scripts' sys.path hack needs - see clip-ppo_b200/dropin.py.  The explicit, preferred route is two lines at
+the top of the script:   `from clip_ppo_b200 import dropin; dropin.install()`   (INTEGRATION.md).
+A `sitecustomize` further down sys.path (e.g. the distribution's) is shadowed by this file, so it is always chained to."""
 import importlib.util
 import os
 import sys
@@ -10,6 +16,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 
 
 def _install():
+    if os.environ.get("CLIPPPO_DROPIN", "") in ("", "0"):
+        return
     spec = importlib.util.spec_from_file_location("_clipppo_dropin", os.path.join(_HERE, "clip-ppo_b200", "dropin.py"))
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)

@@ -294,6 +294,57 @@ def test_numpy_shims_and_minigrid_call_site(native):
     assert diff.max().item() <= 1 and (diff > 0).float().mean().item() < 1e-3      # floor-boundary flips only
 
 
+@pytest.mark.parametrize("batched", [False, True])
+def test_numpy_shims_values_vs_oracle(native, batched):
+    """a8: every `*_numpy` shim (reference shared/disturbances_gpu.py:75-95, 101-115, 121-135, 141-155, 174-194) returns the
+    VALUES of the reference expression  (stage(x / 255) * 255).byte()  for the randomness a seeded reference call would draw:
+    each stage's own draws are replayed from the same global-generator state and pushed through the oracle.
+    Bytes may differ by one where the float result sits on a floor boundary (< 1e-3 of the pixels)."""
+    cfg = od.SEVERITY_TABLE["HARD"]
+    rng = np.random.RandomState(5)
+    arr = rng.randint(0, 256, (5, 84, 84, 3) if batched else (84, 84, 3), dtype=np.uint8)
+    x = torch.from_numpy(arr).float().div(255.0)
+    x = (x if batched else x.unsqueeze(0)).permute(0, 3, 1, 2)             # the reference's NHWC-strided NCHW view
+    H, W = 84, 84
+
+    def ref_noise():
+        n = torch.randn_like(x.cuda()).cpu()
+        return od.add_noise(x, n, cfg["noise_sigma"])
+
+    def ref_contrast():
+        torch.randperm(4)
+        c = float(torch.empty(1).uniform_(*cfg["contrast"]))
+        return od.contrast(x, c)
+
+    def ref_blur():
+        sigma = torch.empty(1).uniform_(cfg["blur_sigma"], cfg["blur_sigma"]).item()
+        return od.blur(x, od.gaussian_kernel1d(od.blur_kernel_size(cfg["blur_sigma"]), sigma))
+
+    def ref_cutout():
+        ph, pw = od.cutout_patch(H, W, cfg["cutout"])
+        sh = torch.randint(0, max(1, H - ph + 1), (1,)).item()
+        sw = torch.randint(0, max(1, W - pw + 1), (1,)).item()
+        return od.cutout(x, sh, sw, ph, pw)
+
+    def ref_all():
+        r = od.draw_call_randomness(x.cuda(), cfg)           # device randn_like on the same strided view, then the CPU draws
+        return od.disturb(x, r["noise"].cpu(), cfg["noise_sigma"], r["c"], od.gaussian_kernel1d(r["k"], r["sigma_b"]),
+                          r["sh"], r["sw"], r["ph"], r["pw"])
+
+    w = _wrapper("HARD")
+    for name, ref_fn in (("apply_gaussian_noise_numpy", ref_noise), ("apply_contrast_jitter_numpy", ref_contrast),
+                         ("apply_gaussian_blur_numpy", ref_blur), ("apply_cutout_numpy", ref_cutout),
+                         ("apply_disturbances_numpy", ref_all)):
+        torch.manual_seed(11)
+        got = getattr(w, name)(arr)
+        torch.manual_seed(11)
+        want = (ref_fn().permute(0, 2, 3, 1) * 255.0).byte().numpy()
+        want = want if batched else want[0]
+        assert got.shape == arr.shape and got.dtype == np.uint8, name
+        diff = np.abs(got.astype(np.int32) - want.astype(np.int32))
+        assert diff.max() <= 1 and (diff > 0).mean() < 1e-3, (name, int(diff.max()), float((diff > 0).mean()))
+
+
 def test_atari_call_site(native):
     from clip_ppo_b200 import rollout
     w = _wrapper("HARD")

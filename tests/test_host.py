@@ -131,8 +131,10 @@ def test_compat_text_state_dict_matches_oracle_weights():
     assert not torch.equal(other.state_dict()["ln_final.bias"], sd["ln_final.bias"])
     other.load_state_dict(sd)
     assert torch.equal(other.state_dict()["ln_final.bias"], sd["ln_final.bias"])
-    with pytest.raises(NotImplementedError):
-        clip_compat.tokenize(["a red door"])
+    import os
+    if not os.environ.get("CLIPPPO_BPE_PATH"):             # the merge list is data of the openai package: absent -> a clear error
+        with pytest.raises(FileNotFoundError):
+            clip_compat.tokenize(["a red door"])
 
 
 def test_single_forward_latents_equal_the_scripts_second_forward():
@@ -205,10 +207,58 @@ def test_dropin_import_resolution_with_the_scripts_sys_path_hacks(tmp_path):
         "import shared.clip_ppo_utils as U2\n"
         "print(clip_ppo_utils.__file__); print(sys.modules['shared.disturbances_gpu'].__file__)\n"
         "print(disturbances.WHO, ck.WHO, clip_ppo_utils is U2, clip_ppo_utils.__name__, hasattr(clip_ppo_utils, 'generate_clip_embeddings'))\n")
-    env = dict(os.environ, PYTHONPATH=root)
-    out = subprocess.run([sys.executable, str(ref / "exp" / "clip" / "script.py")], capture_output=True, text=True, env=env, timeout=300)
+    script = str(ref / "exp" / "clip" / "script.py")
+    # route 1: the opt-in start-up hook (CLIPPPO_DROPIN=1 with the repository on PYTHONPATH), script untouched
+    env = dict(os.environ, PYTHONPATH=root, CLIPPPO_DROPIN="1")
+    out = subprocess.run([sys.executable, script], capture_output=True, text=True, env=env, timeout=300)
     assert out.returncode == 0, out.stderr[-2000:]
     lines = out.stdout.strip().splitlines()
     assert lines[0] == os.path.join(root, "shared", "clip_ppo_utils.py")
     assert lines[1] == os.path.join(root, "shared", "disturbances_gpu.py")
     assert lines[2] == "cv2 twin reference True shared.clip_ppo_utils True"
+    # route 2 (the documented default): two explicit lines in front of the script, no hook
+    env = dict(os.environ, PYTHONPATH=root)
+    env.pop("CLIPPPO_DROPIN", None)
+    code = f"from clip_ppo_b200 import dropin; dropin.install(); import runpy; runpy.run_path({script!r}, run_name='__main__')"
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert out.stdout.strip().splitlines()[0] == os.path.join(root, "shared", "clip_ppo_utils.py")
+    # without either, the repository on the path changes nothing about top-level `clip_ppo_utils`
+    out = subprocess.run([sys.executable, script], capture_output=True, text=True, env=env, timeout=300)
+    assert out.returncode == 0 and out.stdout.strip().splitlines()[0] == str(ref / "exp" / "clip" / ".." / ".." / "shared" / "clip_ppo_utils.py")
+
+
+def test_clip_weight_sources(tmp_path, monkeypatch):
+    """clip_compat.load: a checkpoint named by CLIPPPO_CLIP_WEIGHTS is what the model holds (round trip through torch.save);
+    with no weights at all it RAISES unless random initialisation was asked for - never a silent untrained tower."""
+    import warnings
+    from clip_ppo_b200 import clip_compat
+    sd = clip_compat.random_visual_state_dict("ViT-B/32", 3)
+    sd.update(clip_compat.random_text_state_dict("ViT-B/32", 3))
+    path = tmp_path / "clip_b32.pt"
+    torch.save(sd, path)
+    monkeypatch.setenv("CLIPPPO_CLIP_WEIGHTS", str(path))
+    monkeypatch.delenv("CLIPPPO_ALLOW_RANDOM_WEIGHTS", raising=False)
+    with warnings.catch_warnings():
+        warnings.simplefilter("error")                      # loading real weights must not warn
+        model, _ = clip_compat.load("ViT-B/32", device="cpu")
+    assert model.weight_source == f"checkpoint {path}"
+    got = model.state_dict()
+    for k in ("visual.conv1.weight", "visual.transformer.resblocks.5.attn.in_proj_weight", "visual.proj", "text_projection",
+              "token_embedding.weight"):
+        assert torch.equal(got[k], sd[k]), k
+    # a pickled module works too (what `torch.save(model)` leaves behind)
+    torch.save(model, tmp_path / "module.pt")
+    monkeypatch.setenv("CLIPPPO_CLIP_WEIGHTS", str(tmp_path / "module.pt"))
+    again, _ = clip_compat.load("ViT-B/32", device="cpu")
+    assert torch.equal(again.state_dict()["visual.proj"], sd["visual.proj"])
+    # nothing available
+    monkeypatch.delenv("CLIPPPO_CLIP_WEIGHTS")
+    with pytest.raises(RuntimeError, match="no CLIP weights"):
+        clip_compat.load("ViT-B/32", device="cpu")
+    with pytest.warns(UserWarning, match="RANDOM"):
+        m, _ = clip_compat.load("ViT-B/32", device="cpu", random_init=True)
+    assert m.weight_source == "random(seed=0)"
+    monkeypatch.setenv("CLIPPPO_ALLOW_RANDOM_WEIGHTS", "1")
+    with pytest.warns(UserWarning):
+        clip_compat.load("ViT-B/32", device="cpu", seed=2)

@@ -117,3 +117,33 @@ def test_ppo_loss_random_vs_oracle(native, n, norm_adv, clip_vloss):
         assert abs(out[k].item() - ref[k].item()) <= 1e-3 * abs(ref[k].item()) + 1e-6, k
     for a, b in zip(og, rg):
         assert torch.allclose(a, b, rtol=1e-3, atol=1e-8)
+
+
+def test_ppo_loss_with_global_advantage_stats_matches_the_whole_minibatch(native):
+    """Data parallelism: two ranks' half-minibatches normalised with the GLOBAL advantage statistics
+    (distributed.global_advantage_stats -> ppo_loss(adv_stats=...)) give, averaged, the loss and the gradients of the one-GPU
+    run on the whole minibatch (reference clip_ppo_minigrid.py:509 normalises over the minibatch it sees)."""
+    from clip_ppo_b200 import losses as L
+    from clip_ppo_b200.distributed import global_advantage_stats
+    g = torch.Generator(device="cuda").manual_seed(4)
+    n = 512
+    mk = lambda: torch.randn(n, device="cuda", generator=g)
+    nlp, ent, nv, adv, ret, ov = -1 + 0.1 * mk(), mk().abs(), mk(), 2 * mk() + 0.5, mk(), mk()
+    olp = nlp + 0.05 * mk()
+
+    def run(sl, stats):
+        a, b, c = (t[sl].clone().requires_grad_(True) for t in (nlp, ent, nv))
+        out = L.ppo_loss(a, b, c, olp[sl], adv[sl], ret[sl], ov[sl], adv_stats=stats)
+        out["loss"].backward()
+        return out["loss"].detach(), (a.grad, b.grad, c.grad)
+
+    whole, gw = run(slice(0, n), None)
+    stats = global_advantage_stats(adv)                    # single process: the statistics of all rows
+    assert torch.allclose(stats[0], adv.mean(), atol=1e-6) and torch.allclose(stats[1], adv.std(), rtol=1e-5)
+    (l0, g0), (l1, g1) = run(slice(0, n // 2), stats), run(slice(n // 2, n), stats)
+    assert abs(float((l0 + l1) / 2 - whole)) <= 1e-5 * abs(float(whole)) + 1e-7
+    for i in range(3):                                     # d(mean over n)/dx = half of d(mean over n/2)/dx
+        assert torch.allclose(torch.cat([g0[i], g1[i]]) / 2, gw[i], rtol=1e-4, atol=1e-8)
+    # and with each half's OWN statistics the result differs (what adv_stats is for)
+    (m0, _), (m1, _) = run(slice(0, n // 2), None), run(slice(n // 2, n), None)
+    assert abs(float((m0 + m1) / 2 - whole)) > 1e-6

@@ -93,8 +93,10 @@ def test_generate_clip_embeddings_text_modality(native):
     assert torch.allclose(torch.nn.functional.normalize(raw, dim=-1), e, atol=1e-6)
     with pytest.raises(ValueError):
         U.generate_clip_embeddings(U.AblationMode.NONE, model, "text", 4, "cuda")
-    with pytest.raises(NotImplementedError):                       # no BPE merges file offline
-        U.generate_clip_embeddings(U.AblationMode.NONE, model, "text", 1, "cuda", descriptions=["a red door"])
+    import os
+    if not os.environ.get("CLIPPPO_BPE_PATH"):                     # the BPE merge list is data of the openai package
+        with pytest.raises(FileNotFoundError):
+            U.generate_clip_embeddings(U.AblationMode.NONE, model, "text", 1, "cuda", descriptions=["a red door"])
     eng = model.text_engine()
     with pytest.raises(ValueError):
         eng.encode(tokens[:, :50].cuda())
@@ -123,3 +125,27 @@ def test_repeated_descriptions_are_encoded_once(native, monkeypatch):
     assert calls == [["a key", "a red door", "an empty room"]]
     every_row = model.text_engine().encode(table[[vocab[t] for t in descriptions]].cuda(), l2norm=True)
     assert e.shape == (300, 512) and torch.equal(e, every_row)
+
+
+def test_string_descriptions_end_to_end_with_a_merge_list(native, tmp_path, monkeypatch):
+    """The MiniGrid default modality (clip_ppo_minigrid.py:44, :394-403): description STRINGS -> BPE ids -> text tower, with the
+    tokenizer given a (synthetic) merge list through CLIPPPO_BPE_PATH.  Embeddings equal the oracle's on the same ids."""
+    import shared.clip_ppo_utils as U
+    from clip_ppo_b200 import clip_compat
+    from clip_ppo_b200.clip_compat import tokenizer as T
+    b2u = T.bytes_to_unicode()
+    merges = [(b2u[ord("t")], b2u[ord("h")]), (b2u[ord("t")] + b2u[ord("h")], b2u[ord("e")] + "</w>"), (b2u[ord("d")], b2u[ord("o")]),
+              (b2u[ord("o")], b2u[ord("r")] + "</w>"), (b2u[ord("a")], b2u[ord("g")]), (b2u[ord("e")], b2u[ord("n")])]
+    path = tmp_path / "merges.txt"
+    path.write_text("#version: 0.2\n" + "\n".join(" ".join(m) for m in merges) + "\n", encoding="utf-8")
+    monkeypatch.setenv("CLIPPPO_BPE_PATH", str(path))
+    if U.clip is not clip_compat:
+        pytest.skip("the real openai clip package is installed: its own tokenizer is used")
+    model = U.load_clip_model("ViT-B/32", "cuda")
+    texts = ["the agent is in front of the red door", "the agent carries a key", "the agent is in front of the red door"]
+    ids = clip_compat.tokenize(texts)
+    assert ids.max().item() < 49408 and torch.equal(ids[0], ids[2])
+    e = U.generate_clip_embeddings(U.AblationMode.NONE, model, "text", 3, "cuda", descriptions=texts)
+    ref = ot.text_embeddings(ot.random_state_dict(ot.TEXT_B32, 0), ids)
+    assert e.shape == (3, 512) and torch.sum(e.cpu() * ref, dim=-1).min().item() >= 0.999
+    assert torch.equal(e[0], e[2])

@@ -436,3 +436,19 @@ def test_full_size_batches_of_the_baseline_configs(native):
     pick = torch.tensor([0, 20000, 32767], device="cuda")
     e_sub = rollout.process_multiframe_clip_embeddings(rgb[pick], model, U.AblationMode.NONE, "image", 3, "cuda")
     assert torch.equal(e_sub, e[pick])
+
+
+def test_graph_cache_is_bounded(native):
+    """encode_graphed keeps at most GRAPH_CACHE_ENTRIES captured call shapes (least recently used out first): varying batch
+    sizes (eval, tail minibatches) no longer grow device memory without bound; evicted shapes are simply captured again."""
+    from clip_ppo_b200.vit import VitEngine
+    eng = VitEngine(ov.random_state_dict(ov.VIT_B32, 0), device="cuda")
+    g = torch.Generator(device="cuda").manual_seed(1)
+    outs = {}
+    for n in (3, 5, 7, 9, 11, 13, 3, 5):
+        x = torch.rand(n, 3, 84, 84, device="cuda", generator=g)
+        e = eng.encode_graphed(x, pre_scale=1.0, l2norm=False)
+        assert torch.equal(e, eng.encode(x, pre_scale=1.0, l2norm=False))
+        assert len(eng._graphs) <= eng.GRAPH_CACHE_ENTRIES
+        outs[n] = e
+    assert [k[0][0] for k in eng._graphs] == [11, 13, 3, 5]          # LRU order, oldest first
