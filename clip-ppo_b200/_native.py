@@ -19,7 +19,7 @@ ERR_WORKSPACE, ERR_UNSUPPORTED, ERR_ALIGN, ERR_CUDA, ERR_DIM_MISMATCH = -5, -6, 
 STAGE_NOISE, STAGE_CONTRAST, STAGE_BLUR, STAGE_CUTOUT, STAGE_ALL = 1, 2, 4, 8, 15
 IMG_F32, IMG_U8 = 0, 1
 VIT_L2NORM, VIT_PRENORMALIZED = 1, 2
-EPI_ROWAFFINE_BF16, EPI_ROWAFFINE_GELU_BF16, EPI_RESID_BF16 = 6, 7, 8
+EPI_ROWAFFINE_BF16, EPI_ROWAFFINE_GELU_BF16, EPI_RESID_BF16, EPI_RESID_STATS_BF16 = 6, 7, 8, 9
 EPI_BIAS_BF16, EPI_BIAS_GELU_BF16, EPI_BIAS_RESID_F32, EPI_PATCH_F32, EPI_F32 = 0, 1, 2, 3, 4
 
 # every symbol the header declares; tests/test_abi.py checks the .so exports all of them
@@ -29,7 +29,7 @@ SYMBOLS = (
     "clipppo_cosine_loss_fwd", "clipppo_cosine_loss_bwd", "clipppo_gae_f32", "clipppo_ppo_loss_f32",
     "clipppo_vit_create", "clipppo_vit_destroy", "clipppo_vit_workspace_bytes", "clipppo_vit_encode",
     "clipppo_text_create", "clipppo_text_destroy", "clipppo_text_workspace_bytes", "clipppo_text_encode",
-    "clipppo_preprocess_bf16", "clipppo_layernorm_bf16", "clipppo_gemm_bf16", "clipppo_gemm_bf16_fused", "clipppo_rowstats_bf16", "clipppo_attention_bf16",
+    "clipppo_preprocess_bf16", "clipppo_layernorm_bf16", "clipppo_gemm_bf16", "clipppo_gemm_bf16_fused", "clipppo_gemm_bf16_resid_stats", "clipppo_gemm_bf16_fused_parts", "clipppo_rowstats_bf16", "clipppo_attention_bf16",
     "clipppo_attention_causal_bf16",
     "clipppo_nature_workspace_bytes", "clipppo_nature_forward", "clipppo_nature_backward",
 )
@@ -98,6 +98,8 @@ def lib() -> C.CDLL:
     L.clipppo_layernorm_bf16.argtypes = [vp, vp, vp, i, i, C.c_int64, vp, vp]
     L.clipppo_gemm_bf16.argtypes = [vp, vp, i, i, i, i, vp, vp, i, vp, C.c_int64, vp]
     L.clipppo_gemm_bf16_fused.argtypes = [vp, vp, i, i, i, i, vp, vp, vp, vp, C.c_int64, vp]
+    L.clipppo_gemm_bf16_resid_stats.argtypes = [vp, vp, i, i, i, vp, vp, C.c_int64, vp, vp]
+    L.clipppo_gemm_bf16_fused_parts.argtypes = [vp, vp, i, i, i, i, vp, vp, i, vp, vp, C.c_int64, vp]
     L.clipppo_rowstats_bf16.argtypes = [vp, i, i, C.c_int64, vp, vp]
     if hasattr(L, "clipppo_gemm_bf16_probe"):            # probe builds only (CLIPPPO_BUILD_PROBES=1)
         L.clipppo_gemm_bf16_probe.argtypes = [vp, vp, i, i, i, i, vp, vp, C.c_int64, i, vp]

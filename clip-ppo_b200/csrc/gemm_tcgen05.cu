@@ -45,8 +45,13 @@ constexpr int EPI_RESID_TMA = 5;    // internal: CLIPPPO_EPI_BIAS_RESID_F32 exec
 // bf16 outputs that leave through the TMA unit (store, or reduce-add into the bf16 residual stream):
 // the epilogue warps only write a swizzled 32 x 64 staging tile; no LDS / STG on the SM.
 constexpr bool is_bf16_tma(int epi) {
-    return epi == CLIPPPO_EPI_ROWAFFINE_BF16 || epi == CLIPPPO_EPI_ROWAFFINE_GELU_BF16 || epi == CLIPPPO_EPI_RESID_BF16;
+    return epi == CLIPPPO_EPI_ROWAFFINE_BF16 || epi == CLIPPPO_EPI_ROWAFFINE_GELU_BF16 || epi == CLIPPPO_EPI_RESID_BF16 ||
+           epi == CLIPPPO_EPI_RESID_STATS_BF16;
 }
+// RESID_STATS: the residual update is done ON the SM (x_old box by TMA load into the staging tile, fp32 add, one
+// rounding, TMA store) so that the row statistics of the NEW stream - all that is left of the next LayerNorm -
+// fall out of the epilogue registers: no rowstats pass over the stream, no reduce-add in L2.
+constexpr bool is_resid_stats(int epi) { return epi == CLIPPPO_EPI_RESID_STATS_BF16; }
 
 template <int MODE, int EPI>
 struct Cfg {
@@ -61,7 +66,9 @@ struct Cfg {
     static constexpr int OFF_B = OFF_A + STAGES * A_STAGE_BYTES;
     static constexpr int OFF_EPI = OFF_B + STAGES * B_STAGE_BYTES;
     static constexpr int OFF_BAR = OFF_EPI + EPI_WARPS * EPI_BUFS * EPI_STAGE_BYTES;
-    static constexpr int NUM_BARS = 2 * STAGES + 2 * ACC_STAGES;
+    static constexpr int NUM_PIPE_BARS = 2 * STAGES + 2 * ACC_STAGES;
+    // RESID_STATS: one "x_old box has landed" barrier per epilogue warp and staging buffer
+    static constexpr int NUM_BARS = NUM_PIPE_BARS + (is_resid_stats(EPI) ? 2 * EPI_WARPS : 0);
     static constexpr int SMEM_BYTES = OFF_BAR + NUM_BARS * 8 + 16 + 1024;   // + tmem slot + alignment slack
 };
 
@@ -74,6 +81,9 @@ struct GemmArgs {
     long long ldo;         // elements
     const float2* stats;   // ROWAFFINE: per-row (mean, rstd) of the un-normalised A rows, or null (=> 0, 1)
     const float* colsum;   // ROWAFFINE: s[n] = sum_k W[n,k] (LayerNorm gamma already folded into W)
+    int stat_parts;        // ROWAFFINE: 0 = `stats` holds (mean, rstd); P > 0 = it holds P partial (sum, sum of squares) pairs per row
+                           //            (written by RESID_STATS epilogues over 128-column slices) that are combined here
+    float2* stats_out;     // RESID_STATS: [M, N/128] partial (sum, sum of squares) of the updated rows
     int ksplit;            // RESID_BF16 only: a tile's K range is cut into ksplit work items that each reduce-add
                            // their partial sum (the first one carries the bias); 1 everywhere else
 };
@@ -145,6 +155,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
         // the leader's "accumulator drained" barrier collects the epilogue warps of BOTH CTAs
         for (int a = 0; a < ACC_STAGES; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), EPI_WARPS * CL); }
+        if constexpr (is_resid_stats(EPI)) {
+            for (int i = 0; i < 2 * EPI_WARPS; ++i) mbar_init(bar0 + 8u * (C::NUM_PIPE_BARS + i), 1);
+        }
         fence_barrier_init();
         fence_proxy_async_smem();
     }
@@ -225,6 +238,26 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         uint8_t* stg0 = smem + C::OFF_EPI + e * C::EPI_BUFS * EPI_STAGE_BYTES;
         uint8_t* stg = stg0;
         int as = 0; uint32_t aphase = 0;
+        // RESID_STATS: x_old boxes are TMA-loaded straight into the two staging buffers of this warp (lane 0 issues)
+        [[maybe_unused]] uint32_t xphase = 0;
+        [[maybe_unused]] auto xbar = [&](int b) { return bar0 + 8u * (C::NUM_PIPE_BARS + e * 2 + b); };
+        [[maybe_unused]] auto issue_xold = [&](int w2) {
+            const int mg2 = w2 / n_tiles, nb2 = w2 - mg2 * n_tiles;
+            const int rb2 = (mg2 * CL + rank) * BM + q * 32;
+#pragma unroll
+            for (int ch = 0; ch < 2; ++ch) {
+                const int c0 = nb2 * BN + hh * 128 + ch * 64;
+                if (c0 < g.N) {
+                    // the store that last read this buffer must have drained it (ch 0: all but the newest group)
+                    if (ch == 0) bulk_wait_group_read<1>(); else bulk_wait_group_read<0>();
+                    mbar_arrive_expect_tx(xbar(ch), EPI_STAGE_BYTES);
+                    tma_load_2d(smem_u32(stg0 + ch * EPI_STAGE_BYTES), &tmap_out, xbar(ch), c0, rb2);
+                }
+            }
+        };
+        if constexpr (is_resid_stats(EPI)) {
+            if (lane == 0 && unit < num_work) issue_xold(unit);
+        }
         for (int w = unit; w < num_work; w += num_units) {
             const int t = w / ksplit, ks = w - t * ksplit;
             const int mg = t / n_tiles, n_blk = t - mg * n_tiles, m_blk = mg * CL + rank;
@@ -237,13 +270,25 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 //   is LayerNorm folded through the GEMM: A holds the UN-normalised rows, gamma lives
                 //   in W, beta in the bias; with stats == null it is the plain bias epilogue.
                 float mean = 0.0f, rstd = 1.0f;
-                if constexpr (EPI != CLIPPPO_EPI_RESID_BF16) {
+                if constexpr (EPI == CLIPPPO_EPI_ROWAFFINE_BF16 || EPI == CLIPPPO_EPI_ROWAFFINE_GELU_BF16) {
                     if (g.stats != nullptr && row_base + lane < g.M) {
-                        const float2 st = __ldg(g.stats + row_base + lane);
-                        mean = st.x; rstd = st.y;
+                        if (g.stat_parts > 0) {
+                            // partial (sum, sum of squares) pairs left by the RESID_STATS epilogue that wrote these rows,
+                            // combined in a fixed order; K is the row width of A
+                            const float2* pp = g.stats + static_cast<size_t>(row_base + lane) * g.stat_parts;
+                            float sm = 0.f, sq = 0.f;
+                            for (int p = 0; p < g.stat_parts; ++p) { const float2 v2 = __ldg(pp + p); sm += v2.x; sq += v2.y; }
+                            const float inv = 1.0f / static_cast<float>(g.K);
+                            mean = sm * inv;
+                            rstd = rsqrtf(fmaxf(fmaf(-mean, mean, sq * inv), 0.0f) + 1e-5f);
+                        } else {
+                            const float2 st = __ldg(g.stats + row_base + lane);
+                            mean = st.x; rstd = st.y;
+                        }
                     }
                 }
                 const float nmean = -mean;
+                float2 sum2 = make_float2(0.f, 0.f), sq2 = make_float2(0.f, 0.f);     // RESID_STATS: this row's 128 columns
                 mbar_wait(tfull_bar(as), aphase);
                 tc_fence_after();
                 const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN + hh * 128;
@@ -267,8 +312,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     const int col0 = n_blk * BN + hh * 128 + ch * 64;
                     if (col0 < g.N) {
                         uint8_t* buf = stg0 + (ch & 1) * EPI_STAGE_BYTES;
-                        if (lane == 0) bulk_wait_group_read<1>();      // the box issued two chunks ago has left buf
-                        __syncwarp();
+                        if constexpr (is_resid_stats(EPI)) {
+                            mbar_wait(xbar(ch), xphase);                // the x_old box of this chunk has landed in buf
+                        } else {
+                            if (lane == 0) bulk_wait_group_read<1>();      // the box issued two chunks ago has left buf
+                            __syncwarp();
+                        }
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {                  // 16-byte piece j = columns 8j .. 8j+7
                             const uint32_t* vv = &v[j >> 2][(j & 3) * 8];
@@ -281,10 +330,21 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                             // so (v[2i], v[2i+1]) is an aligned pair - half the instructions of the scalar form
                             float2 o2[4];
                             const float2 bb[4] = {make_float2(b0.x, b0.y), make_float2(b0.z, b0.w), make_float2(b1.x, b1.y), make_float2(b1.z, b1.w)};
+                            uint4* slot = reinterpret_cast<uint4*>(buf + lane * 128 + ((j ^ (lane & 7)) << 4));
                             if constexpr (EPI == CLIPPPO_EPI_RESID_BF16) {
 #pragma unroll
                                 for (int t = 0; t < 4; ++t)
                                     o2[t] = __fadd2_rn(make_float2(__uint_as_float(vv[2 * t]), __uint_as_float(vv[2 * t + 1])), bb[t]);
+                            } else if constexpr (is_resid_stats(EPI)) {
+                                // x_new = bf16(x_old + acc + bias): fp32 add, ONE rounding; the statistics are taken of
+                                // the rounded values, the ones the next GEMM multiplies
+                                const uint4 xo = *slot;
+                                const uint32_t xw[4] = {xo.x, xo.y, xo.z, xo.w};
+#pragma unroll
+                                for (int t = 0; t < 4; ++t) {
+                                    const float2 xf = make_float2(__uint_as_float(xw[t] << 16), __uint_as_float(xw[t] & 0xffff0000u));
+                                    o2[t] = __fadd2_rn(__fadd2_rn(make_float2(__uint_as_float(vv[2 * t]), __uint_as_float(vv[2 * t + 1])), bb[t]), xf);
+                                }
                             } else {
                                 float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0;
                                 if (g.colsum != nullptr) {
@@ -306,10 +366,19 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                             const float o[8] = {o2[0].x, o2[0].y, o2[1].x, o2[1].y, o2[2].x, o2[2].y, o2[3].x, o2[3].y};
                             // the XOR is the TMA 128-byte swizzle of a box with 128-byte rows; conflict-free STS.128
                             const uint4 pk = make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7]));
+                            if constexpr (is_resid_stats(EPI)) {
+                                const uint32_t pw[4] = {pk.x, pk.y, pk.z, pk.w};
+#pragma unroll
+                                for (int t = 0; t < 4; ++t) {
+                                    const float2 r = make_float2(__uint_as_float(pw[t] << 16), __uint_as_float(pw[t] & 0xffff0000u));
+                                    sum2 = __fadd2_rn(sum2, r);
+                                    sq2 = __ffma2_rn(r, r, sq2);
+                                }
+                            }
                             if constexpr ((DBG & 8) != 0) {          // probe: math only, nothing leaves the registers
                                 if (pk.x == 0x7fc17fc2u && pk.w == 0x12345678u) static_cast<float*>(g.out)[0] = 1.0f;
                             } else {
-                                *reinterpret_cast<uint4*>(buf + lane * 128 + ((j ^ (lane & 7)) << 4)) = pk;
+                                *slot = pk;
                             }
                         }
                         fence_proxy_async_smem();                      // generic-proxy writes -> visible to the TMA
@@ -320,6 +389,16 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                             bulk_commit_group();
                         }
                     }
+                }
+                if constexpr (is_resid_stats(EPI)) {
+                    if (n_blk * BN + hh * 128 < g.N) {
+                        if (row_base + lane < g.M)
+                            g.stats_out[static_cast<size_t>(row_base + lane) * ((g.N + 127) >> 7) + n_blk * 2 + hh] =
+                                make_float2(sum2.x + sum2.y, sq2.x + sq2.y);
+                    }
+                    // the x_old boxes of my next tile: in flight while its MMAs run
+                    if (lane == 0 && w + num_units < num_work) issue_xold(w + num_units);
+                    xphase ^= 1;
                 }
                 if (++as == ACC_STAGES) { as = 0; aphase ^= 1; }
             } else {
@@ -664,10 +743,12 @@ int gemm_b_box_rows() { return BN / 2; }   // W is fetched as two 128-row halves
 
 int gemm_bf16_launch(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, int epilogue,
                      const float* bias, const float* pos, int tokens, void* out, long long ldo, cudaStream_t stream,
-                     const float* row_stats, const float* colsum) {
+                     const float* row_stats, const float* colsum, int stat_parts, float* stats_out) {
     if (M <= 0 || N <= 0 || K <= 0 || (K % BK) || (N % 32)) return CLIPPPO_ERR_BAD_SHAPE;
     if (!out) return CLIPPPO_ERR_NULL;
-    GemmArgs g{M, N, K, bias, pos, tokens, out, ldo, reinterpret_cast<const float2*>(row_stats), colsum, 1};
+    if (stat_parts < 0 || stat_parts > 64) return CLIPPPO_ERR_BAD_SHAPE;
+    GemmArgs g{M, N, K, bias, pos, tokens, out, ldo, reinterpret_cast<const float2*>(row_stats), colsum, stat_parts,
+               reinterpret_cast<float2*>(stats_out), 1};
     if (epilogue == CLIPPPO_EPI_RESID_BF16) g.ksplit = pick_ksplit(M, N, K);
     const bool bf16_out = epilogue == CLIPPPO_EPI_BIAS_BF16 || epilogue == CLIPPPO_EPI_BIAS_GELU_BF16 || is_bf16_tma(epilogue);
     if ((reinterpret_cast<uintptr_t>(out) & 15) || ((ldo * (bf16_out ? 2 : 4)) & 15)) return CLIPPPO_ERR_ALIGN;
@@ -681,6 +762,11 @@ int gemm_bf16_launch(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N,
         if (st) return st;
         if (epilogue == CLIPPPO_EPI_ROWAFFINE_BF16) return launch_gemm<CLIPPPO_EPI_ROWAFFINE_BF16>(ta, tb, tout, g, stream);
         if (epilogue == CLIPPPO_EPI_ROWAFFINE_GELU_BF16) return launch_gemm<CLIPPPO_EPI_ROWAFFINE_GELU_BF16>(ta, tb, tout, g, stream);
+        if (epilogue == CLIPPPO_EPI_RESID_STATS_BF16) {
+            if (!stats_out) return CLIPPPO_ERR_NULL;
+            if (reinterpret_cast<uintptr_t>(stats_out) & 7) return CLIPPPO_ERR_ALIGN;
+            return launch_gemm<CLIPPPO_EPI_RESID_STATS_BF16>(ta, tb, tout, g, stream);
+        }
         return launch_gemm<CLIPPPO_EPI_RESID_BF16>(ta, tb, tout, g, stream);
     }
     switch (epilogue) {
@@ -722,7 +808,7 @@ extern "C" int clipppo_gemm_bf16(const void* a_bf16, const void* w_bf16, int M, 
     if (st) return st;
     st = make_bf16_kmajor_tmap(&tb, w_bf16, N, K, K, gemm_b_box_rows());
     if (st) return st;
-    return gemm_bf16_launch(ta, tb, M, N, K, epilogue, bias, pos, tokens, out, ldo, as_stream(stream), nullptr, nullptr);
+    return gemm_bf16_launch(ta, tb, M, N, K, epilogue, bias, pos, tokens, out, ldo, as_stream(stream), nullptr, nullptr, 0, nullptr);
 }
 
 extern "C" int clipppo_gemm_bf16_fused(const void* a_bf16, const void* w_bf16, int M, int N, int K, int epilogue,
@@ -737,7 +823,35 @@ extern "C" int clipppo_gemm_bf16_fused(const void* a_bf16, const void* w_bf16, i
     if (st) return st;
     st = make_bf16_kmajor_tmap(&tb, w_bf16, N, K, K, gemm_b_box_rows());
     if (st) return st;
-    return gemm_bf16_launch(ta, tb, M, N, K, epilogue, bias, nullptr, 0, out_bf16, ldo, as_stream(stream), row_stats, colsum);
+    return gemm_bf16_launch(ta, tb, M, N, K, epilogue, bias, nullptr, 0, out_bf16, ldo, as_stream(stream), row_stats, colsum, 0, nullptr);
+}
+
+extern "C" int clipppo_gemm_bf16_resid_stats(const void* a_bf16, const void* w_bf16, int M, int N, int K, const float* bias,
+                                             void* x_bf16, int64_t ldo, float* row_parts_out, clipppo_stream_t stream) {
+    if (!a_bf16 || !w_bf16 || !row_parts_out) return CLIPPPO_ERR_NULL;
+    if (M <= 0 || N <= 0 || K <= 0 || (K % 64)) return CLIPPPO_ERR_BAD_SHAPE;
+    CUtensorMap ta, tb;
+    int st = make_bf16_kmajor_tmap(&ta, a_bf16, M, K, K, gemm_a_box_rows());
+    if (st) return st;
+    st = make_bf16_kmajor_tmap(&tb, w_bf16, N, K, K, gemm_b_box_rows());
+    if (st) return st;
+    return gemm_bf16_launch(ta, tb, M, N, K, CLIPPPO_EPI_RESID_STATS_BF16, bias, nullptr, 0, x_bf16, ldo, as_stream(stream),
+                            nullptr, nullptr, 0, row_parts_out);
+}
+
+extern "C" int clipppo_gemm_bf16_fused_parts(const void* a_bf16, const void* w_bf16, int M, int N, int K, int epilogue,
+                                             const float* bias, const float* row_parts, int n_parts, const float* colsum,
+                                             void* out_bf16, int64_t ldo, clipppo_stream_t stream) {
+    if (!a_bf16 || !w_bf16 || !row_parts || !colsum) return CLIPPPO_ERR_NULL;
+    if (M <= 0 || N <= 0 || K <= 0 || (K % 64) || n_parts <= 0) return CLIPPPO_ERR_BAD_SHAPE;
+    if (epilogue != CLIPPPO_EPI_ROWAFFINE_BF16 && epilogue != CLIPPPO_EPI_ROWAFFINE_GELU_BF16) return CLIPPPO_ERR_UNSUPPORTED;
+    CUtensorMap ta, tb;
+    int st = make_bf16_kmajor_tmap(&ta, a_bf16, M, K, K, gemm_a_box_rows());
+    if (st) return st;
+    st = make_bf16_kmajor_tmap(&tb, w_bf16, N, K, K, gemm_b_box_rows());
+    if (st) return st;
+    return gemm_bf16_launch(ta, tb, M, N, K, epilogue, bias, nullptr, 0, out_bf16, ldo, as_stream(stream), row_parts, colsum,
+                            n_parts, nullptr);
 }
 
 #ifdef CLIPPPO_BUILD_PROBES
@@ -753,7 +867,7 @@ extern "C" int clipppo_gemm_bf16_probe(const void* a_bf16, const void* w_bf16, i
     if (st) return st;
     st = make_bf16_kmajor_tmap(&tb, w_bf16, N, K, K, gemm_b_box_rows());
     if (st) return st;
-    GemmArgs g{M, N, K, bias, nullptr, 0, out, ldo, nullptr, nullptr, 1};
+    GemmArgs g{M, N, K, bias, nullptr, 0, out, ldo, nullptr, nullptr, 0, nullptr, 1};
     return gemm_probe_launch(ta, tb, g, epilogue, dbg, as_stream(stream));
 }
 #endif  // CLIPPPO_BUILD_PROBES

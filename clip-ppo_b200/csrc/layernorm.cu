@@ -29,7 +29,7 @@ __device__ __forceinline__ float4 load4(const __nv_bfloat16* p) {
 // lane, lane+32, ...  Two passes over registers: exact mean first, then centred squares.
 template <int NV>
 __global__ void __launch_bounds__(256)
-rowstats_kernel(const __nv_bfloat16* __restrict__ x, int rows, long long row_stride, float2* __restrict__ stats) {
+rowstats_kernel(const __nv_bfloat16* __restrict__ x, int rows, long long row_stride, float2* __restrict__ stats, int nparts) {
     pdl_launch_dependents();
     pdl_wait();
     const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -57,14 +57,21 @@ rowstats_kernel(const __nv_bfloat16* __restrict__ x, int rows, long long row_str
 #pragma unroll
         for (int t = 0; t < 4; ++t) { const float2 d = __fadd2_rn(v[i][t], nm); q2 = __ffma2_rn(d, d, q2); }
     }
-    const float rstd = rsqrtf(warp_sum(q2.x + q2.y) * (1.0f / width) + 1e-5f);
+    const float m2 = warp_sum(q2.x + q2.y);
+    if (nparts > 0) {
+        // partial-sum layout of the RESID_STATS epilogue: (sum, sum of squares) in slice 0, zeros in the others
+        const float sm = mean * width;
+        if (lane < nparts) stats[static_cast<size_t>(row) * nparts + lane] = lane == 0 ? make_float2(sm, fmaf(mean, sm, m2)) : make_float2(0.f, 0.f);
+        return;
+    }
+    const float rstd = rsqrtf(m2 * (1.0f / width) + 1e-5f);
     if (lane == 0) stats[row] = make_float2(mean, rstd);
 }
 
 template <int NV, typename OutT, typename InT = float>
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const InT* x, const float* __restrict__ gamma, const float* __restrict__ beta,
-                 int rows, long long row_stride, OutT* y) {
+                 int rows, long long row_stride, OutT* y, float2* __restrict__ parts = nullptr, int nparts = 0) {
     pdl_launch_dependents();
     pdl_wait();
     const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -87,6 +94,7 @@ layernorm_kernel(const InT* x, const float* __restrict__ gamma, const float* __r
         q += (a * a + b * b) + (c * c + d * d);
     }
     const float rstd = rsqrtf(warp_sum(q) * (1.0f / width) + 1e-5f);
+    float so = 0.f, qo = 0.f;                          // (sum, sum of squares) of the ROUNDED output row
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
         const int c4 = lane + 32 * i;
@@ -106,6 +114,17 @@ layernorm_kernel(const InT* x, const float* __restrict__ gamma, const float* __r
         pk.x = *reinterpret_cast<uint32_t*>(&lo);
         pk.y = *reinterpret_cast<uint32_t*>(&hi);
         *reinterpret_cast<uint2*>(yr + 4 * c4) = pk;
+        const float2 a = __bfloat1622float2(lo), c = __bfloat1622float2(hi);
+        so += (a.x + a.y) + (c.x + c.y);
+        qo += (a.x * a.x + a.y * a.y) + (c.x * c.x + c.y * c.y);
+    }
+    if constexpr (sizeof(OutT) == 2) {
+        // the row statistics the first block's ln_1 needs, in the partial-sum layout of the RESID_STATS epilogue
+        // (gemm_tcgen05.cu): everything in slice 0, zeros in the others
+        if (parts != nullptr) {
+            so = warp_sum(so); qo = warp_sum(qo);
+            if (lane < nparts) parts[static_cast<size_t>(row) * nparts + lane] = lane == 0 ? make_float2(so, qo) : make_float2(0.f, 0.f);
+        }
     }
 }
 
@@ -113,14 +132,14 @@ layernorm_kernel(const InT* x, const float* __restrict__ gamma, const float* __r
 
 template <typename OutT>
 static int layernorm_dispatch(const float* x, const float* gamma, const float* beta, int rows, int width,
-                              long long row_stride, OutT* y, cudaStream_t stream) {
+                              long long row_stride, OutT* y, cudaStream_t stream, float2* parts = nullptr, int nparts = 0) {
     const int warps_per_block = 8;
     const unsigned grid = (rows + warps_per_block - 1) / warps_per_block;
     switch (width / 128) {
-        case 4: CLIPPPO_CUDA_TRY(launch_pdl(layernorm_kernel<4, OutT>, grid, 256, 0, stream, 1, x, gamma, beta, rows, row_stride, y)); break;
-        case 6: CLIPPPO_CUDA_TRY(launch_pdl(layernorm_kernel<6, OutT>, grid, 256, 0, stream, 1, x, gamma, beta, rows, row_stride, y)); break;
-        case 8: CLIPPPO_CUDA_TRY(launch_pdl(layernorm_kernel<8, OutT>, grid, 256, 0, stream, 1, x, gamma, beta, rows, row_stride, y)); break;
-        case 10: CLIPPPO_CUDA_TRY(launch_pdl(layernorm_kernel<10, OutT>, grid, 256, 0, stream, 1, x, gamma, beta, rows, row_stride, y)); break;
+        case 4: CLIPPPO_CUDA_TRY(launch_pdl(layernorm_kernel<4, OutT>, grid, 256, 0, stream, 1, x, gamma, beta, rows, row_stride, y, parts, nparts)); break;
+        case 6: CLIPPPO_CUDA_TRY(launch_pdl(layernorm_kernel<6, OutT>, grid, 256, 0, stream, 1, x, gamma, beta, rows, row_stride, y, parts, nparts)); break;
+        case 8: CLIPPPO_CUDA_TRY(launch_pdl(layernorm_kernel<8, OutT>, grid, 256, 0, stream, 1, x, gamma, beta, rows, row_stride, y, parts, nparts)); break;
+        case 10: CLIPPPO_CUDA_TRY(launch_pdl(layernorm_kernel<10, OutT>, grid, 256, 0, stream, 1, x, gamma, beta, rows, row_stride, y, parts, nparts)); break;
         default: return CLIPPPO_ERR_UNSUPPORTED;
     }
     prof_count_launch();
@@ -136,14 +155,15 @@ int layernorm_inplace_f32_launch(float* x, const float* gamma, const float* beta
 }
 
 int layernorm_launch(const float* x, const float* gamma, const float* beta, int rows, int width,
-                     long long row_stride, void* y_bf16, cudaStream_t stream) {
+                     long long row_stride, void* y_bf16, cudaStream_t stream, float* row_parts, int n_parts) {
     if (!x || !gamma || !beta || !y_bf16) return CLIPPPO_ERR_NULL;
-    if (rows <= 0 || width <= 0) return CLIPPPO_ERR_BAD_SHAPE;
+    if (rows <= 0 || width <= 0 || n_parts < 0 || n_parts > 32) return CLIPPPO_ERR_BAD_SHAPE;
     if (width % 128 || (row_stride % 4) || (reinterpret_cast<uintptr_t>(x) % 16) ||
-        (reinterpret_cast<uintptr_t>(y_bf16) % 8))
+        (reinterpret_cast<uintptr_t>(y_bf16) % 8) || (reinterpret_cast<uintptr_t>(row_parts) % 8))
         return CLIPPPO_ERR_ALIGN;
     return layernorm_dispatch<__nv_bfloat16>(x, gamma, beta, rows, width, row_stride,
-                                             static_cast<__nv_bfloat16*>(y_bf16), stream);
+                                             static_cast<__nv_bfloat16*>(y_bf16), stream,
+                                             reinterpret_cast<float2*>(row_parts), row_parts ? n_parts : 0);
 }
 
 // ln_post: bf16 rows (the CLS token of every image, row_stride = T*D) -> dense bf16 rows
@@ -157,29 +177,29 @@ int layernorm_bf16in_launch(const void* x_bf16, const float* gamma, const float*
     __nv_bfloat16* y = static_cast<__nv_bfloat16*>(y_bf16);
     const unsigned grid = (rows + 7) / 8;
     switch (width / 128) {
-        case 4: CLIPPPO_CUDA_TRY(launch_pdl(layernorm_kernel<4, __nv_bfloat16, __nv_bfloat16>, grid, 256, 0, stream, 1, x, gamma, beta, rows, row_stride, y)); break;
-        case 6: CLIPPPO_CUDA_TRY(launch_pdl(layernorm_kernel<6, __nv_bfloat16, __nv_bfloat16>, grid, 256, 0, stream, 1, x, gamma, beta, rows, row_stride, y)); break;
-        case 8: CLIPPPO_CUDA_TRY(launch_pdl(layernorm_kernel<8, __nv_bfloat16, __nv_bfloat16>, grid, 256, 0, stream, 1, x, gamma, beta, rows, row_stride, y)); break;
-        case 10: CLIPPPO_CUDA_TRY(launch_pdl(layernorm_kernel<10, __nv_bfloat16, __nv_bfloat16>, grid, 256, 0, stream, 1, x, gamma, beta, rows, row_stride, y)); break;
+        case 4: CLIPPPO_CUDA_TRY(launch_pdl(layernorm_kernel<4, __nv_bfloat16, __nv_bfloat16>, grid, 256, 0, stream, 1, x, gamma, beta, rows, row_stride, y, static_cast<float2*>(nullptr), 0)); break;
+        case 6: CLIPPPO_CUDA_TRY(launch_pdl(layernorm_kernel<6, __nv_bfloat16, __nv_bfloat16>, grid, 256, 0, stream, 1, x, gamma, beta, rows, row_stride, y, static_cast<float2*>(nullptr), 0)); break;
+        case 8: CLIPPPO_CUDA_TRY(launch_pdl(layernorm_kernel<8, __nv_bfloat16, __nv_bfloat16>, grid, 256, 0, stream, 1, x, gamma, beta, rows, row_stride, y, static_cast<float2*>(nullptr), 0)); break;
+        case 10: CLIPPPO_CUDA_TRY(launch_pdl(layernorm_kernel<10, __nv_bfloat16, __nv_bfloat16>, grid, 256, 0, stream, 1, x, gamma, beta, rows, row_stride, y, static_cast<float2*>(nullptr), 0)); break;
         default: return CLIPPPO_ERR_UNSUPPORTED;
     }
     prof_count_launch();
     return CLIPPPO_OK;
 }
 
-int rowstats_launch(const void* x_bf16, int rows, int width, long long row_stride, float* stats, cudaStream_t stream) {
+int rowstats_launch(const void* x_bf16, int rows, int width, long long row_stride, float* stats, cudaStream_t stream, int n_parts) {
     if (!x_bf16 || !stats) return CLIPPPO_ERR_NULL;
-    if (rows <= 0 || width <= 0) return CLIPPPO_ERR_BAD_SHAPE;
+    if (rows <= 0 || width <= 0 || n_parts < 0 || n_parts > 32) return CLIPPPO_ERR_BAD_SHAPE;
     if (width % 256 || (row_stride % 8) || (reinterpret_cast<uintptr_t>(x_bf16) % 16) || (reinterpret_cast<uintptr_t>(stats) % 8))
         return CLIPPPO_ERR_ALIGN;
     const __nv_bfloat16* x = static_cast<const __nv_bfloat16*>(x_bf16);
     float2* st = reinterpret_cast<float2*>(stats);
     const unsigned grid = (rows + 7) / 8;
     switch (width / 256) {
-        case 2: CLIPPPO_CUDA_TRY(launch_pdl(rowstats_kernel<2>, grid, 256, 0, stream, 1, x, rows, row_stride, st)); break;
-        case 3: CLIPPPO_CUDA_TRY(launch_pdl(rowstats_kernel<3>, grid, 256, 0, stream, 1, x, rows, row_stride, st)); break;
-        case 4: CLIPPPO_CUDA_TRY(launch_pdl(rowstats_kernel<4>, grid, 256, 0, stream, 1, x, rows, row_stride, st)); break;
-        case 5: CLIPPPO_CUDA_TRY(launch_pdl(rowstats_kernel<5>, grid, 256, 0, stream, 1, x, rows, row_stride, st)); break;
+        case 2: CLIPPPO_CUDA_TRY(launch_pdl(rowstats_kernel<2>, grid, 256, 0, stream, 1, x, rows, row_stride, st, n_parts)); break;
+        case 3: CLIPPPO_CUDA_TRY(launch_pdl(rowstats_kernel<3>, grid, 256, 0, stream, 1, x, rows, row_stride, st, n_parts)); break;
+        case 4: CLIPPPO_CUDA_TRY(launch_pdl(rowstats_kernel<4>, grid, 256, 0, stream, 1, x, rows, row_stride, st, n_parts)); break;
+        case 5: CLIPPPO_CUDA_TRY(launch_pdl(rowstats_kernel<5>, grid, 256, 0, stream, 1, x, rows, row_stride, st, n_parts)); break;
         default: return CLIPPPO_ERR_UNSUPPORTED;
     }
     prof_count_launch();
@@ -190,7 +210,7 @@ int rowstats_launch(const void* x_bf16, int rows, int width, long long row_strid
 
 extern "C" int clipppo_rowstats_bf16(const void* x_bf16, int rows, int width, int64_t row_stride, float* stats,
                                      clipppo_stream_t stream) {
-    return clipppo::rowstats_launch(x_bf16, rows, width, row_stride, stats, clipppo::as_stream(stream));
+    return clipppo::rowstats_launch(x_bf16, rows, width, row_stride, stats, clipppo::as_stream(stream), 0);
 }
 
 extern "C" int clipppo_layernorm_bf16(const float* x, const float* gamma, const float* beta, int rows,

@@ -1,15 +1,19 @@
 // Frozen CLIP image tower driver: owns the weight TMA descriptors and sequences the kernels
-//   V0 preprocess+im2col -> V1 patch-embed GEMM (+pos) -> ln_pre ->
-//   L x [ row stats -> QKV GEMM (ln_1 folded) -> attention -> out-proj GEMM (+= residual) ->
-//         row stats -> c_fc GEMM (ln_2 folded, +QuickGELU) -> c_proj GEMM (+= residual) ]
+//   V0 preprocess+im2col -> V1 patch-embed GEMM (+pos) -> ln_pre (+ row statistics) ->
+//   L x [ QKV GEMM (ln_1 folded) -> attention -> out-proj GEMM (+= residual, + row statistics) ->
+//         c_fc GEMM (ln_2 folded, +QuickGELU) -> c_proj GEMM (+= residual, + row statistics) ]
 //   -> ln_post(CLS) -> head GEMM -> optional L2 normalise
 // Replaces [clip] VisionTransformer.forward / CLIP.encode_image as called by reference
 // shared/clip_ppo_utils.py:163-164 and :212-217 (spec: SURVEY.md Appendix B).
 //
 // The residual stream X is bf16 [n*T, D] and is the A operand of the QKV / c_fc GEMMs as it stands:
 // ln_1 / ln_2 are folded through those GEMMs (gamma in the weights, beta in the bias, mean / rstd
-// applied per row in the epilogue), so a block is  rowstats -> QKV -> attention -> out_proj(+=) ->
-// rowstats -> c_fc(+GELU) -> c_proj(+=)  with both residual updates done by TMA reduce-adds in L2.
+// applied per row in the epilogue), and the row statistics they need are a by-product of the epilogue
+// that WROTE the rows (RESID_STATS: x_old by TMA load, fp32 add, one rounding, TMA store, per-row partial
+// sums from the registers), so a block is five launches:  QKV -> attention -> out_proj(+=) -> c_fc(+GELU) ->
+// c_proj(+=).  The round-1 schedule (residual updates as TMA reduce-adds in L2 + a rowstats pass in front
+// of each folded GEMM) is kept for the opt-in split-K latency schedule and for A/B measurements
+// (CLIPPPO_GEMM_RESID=reduce).
 // Accumulation is fp32 everywhere; patch embedding + ln_pre run in fp32.  Images are processed in
 // chunks so the activation workspace stays bounded whatever N is; buffers that are never live
 // together (im2col patches / QKV / MLP hidden) share one allocation.
@@ -104,7 +108,7 @@ fold_ln_kernel(const float* __restrict__ W, const float* __restrict__ gamma, con
 struct Workspace {
     float* X0;                // [n*T, D] fp32: patch embedding + positional embedding, input of ln_pre
     __nv_bfloat16* X;         // [n*T, D] bf16 residual stream (A operand of the QKV / c_fc GEMMs as is)
-    float* stats;             // [n*T, 2] (mean, rstd) of the rows of X
+    float* stats;             // [n*T, D/128, 2] partial (sum, sum of squares) of the rows of X  (legacy schedule: [n*T, 2] (mean, rstd))
     __nv_bfloat16* Y;         // [n*T, D] attention output
     __nv_bfloat16* H;         // max(patches [n*G*G, kpatch], QKV [n*T, 3D], hidden [n*T, 4D])
     __nv_bfloat16* Ycls;      // [n, D]
@@ -123,7 +127,7 @@ Workspace carve(const clipppo_vit_s* h, int n, void* base) {
     uint8_t* b = static_cast<uint8_t*>(base);
     ws.X0 = reinterpret_cast<float*>(b + off);           off += align_up(rows * D * 4, 1024);
     ws.X = reinterpret_cast<__nv_bfloat16*>(b + off);    off += align_up(rows * D * 2, 1024);
-    ws.stats = reinterpret_cast<float*>(b + off);        off += align_up(rows * 2 * 4, 1024);
+    ws.stats = reinterpret_cast<float*>(b + off);        off += align_up(rows * (D / 128) * 2 * 4, 1024);
     ws.Y = reinterpret_cast<__nv_bfloat16*>(b + off);    off += align_up(rows * D * 2, 1024);
     ws.H = reinterpret_cast<__nv_bfloat16*>(b + off);    off += align_up(h_elems * 2, 1024);
     ws.Ycls = reinterpret_cast<__nv_bfloat16*>(b + off); off += align_up(static_cast<size_t>(n) * D * 2, 1024);
@@ -154,14 +158,39 @@ __global__ void l2norm_rows_kernel(float* __restrict__ out, int rows, int dim) {
 
 #define VIT_TRY(expr) do { int st__ = (expr); if (st__ != CLIPPPO_OK) return st__; } while (0)
 
+// Residual schedule: fused row statistics (default) unless the split-K latency schedule or the round-1 reduce-add
+// path is asked for by environment.
+bool fused_stats() {                                   // read per tower pass (two getenv calls), so tests can switch it
+    const char* r = getenv("CLIPPPO_GEMM_RESID");
+    const char* k = getenv("CLIPPPO_GEMM_KSPLIT");
+    return !((r && r[0] == 'r') || (k && k[0]));
+}
+
 // L x [ x += out_proj(attn(ln_1(x)));  x += c_proj(QuickGELU(c_fc(ln_2(x)))) ] on the bf16 residual stream X [rows, D]
+// fused = true: `stats` arrives holding the partial sums of the rows of X (written by ln_pre / rowstats) and every
+// residual GEMM refreshes them.
 int run_blocks(const std::vector<clipppo_tower_layer>& layers, int n, int T, int D, int heads, bool causal,
-               __nv_bfloat16* X, float* stats, __nv_bfloat16* Y, __nv_bfloat16* H, cudaStream_t stream) {
+               __nv_bfloat16* X, float* stats, __nv_bfloat16* Y, __nv_bfloat16* H, cudaStream_t stream, bool fused) {
     const int rows = n * T;
     CUtensorMap tmX, tmY, tmH;
     VIT_TRY(make_bf16_kmajor_tmap(&tmX, X, rows, D, D, gemm_a_box_rows()));
     VIT_TRY(make_bf16_kmajor_tmap(&tmY, Y, rows, D, D, gemm_a_box_rows()));
     VIT_TRY(make_bf16_kmajor_tmap(&tmH, H, rows, 4 * D, 4 * D, gemm_a_box_rows()));
+    if (fused) {
+        const int P = D / 128;
+        for (const clipppo_tower_layer& w : layers) {
+            VIT_TRY(gemm_bf16_launch(tmX, w.tm_qkv, rows, 3 * D, D, CLIPPPO_EPI_ROWAFFINE_BF16, w.b_qkv, nullptr, 0,
+                                     H, 3 * D, stream, stats, w.s_qkv, P));
+            VIT_TRY(attention_launch(H, n, T, heads, D / heads, Y, stream, causal));
+            VIT_TRY(gemm_bf16_launch(tmY, w.tm_out, rows, D, D, CLIPPPO_EPI_RESID_STATS_BF16, w.b_out, nullptr, 0, X, D, stream,
+                                     nullptr, nullptr, 0, stats));
+            VIT_TRY(gemm_bf16_launch(tmX, w.tm_fc, rows, 4 * D, D, CLIPPPO_EPI_ROWAFFINE_GELU_BF16, w.b_fc, nullptr, 0,
+                                     H, 4 * D, stream, stats, w.s_fc, P));
+            VIT_TRY(gemm_bf16_launch(tmH, w.tm_proj, rows, D, 4 * D, CLIPPPO_EPI_RESID_STATS_BF16, w.b_proj, nullptr, 0, X, D, stream,
+                                     nullptr, nullptr, 0, stats));
+        }
+        return CLIPPPO_OK;
+    }
     for (const clipppo_tower_layer& w : layers) {
         // ln_1 lives in the QKV GEMM's epilogue
         VIT_TRY(rowstats_launch(X, rows, D, D, stats, stream));
@@ -229,7 +258,7 @@ TextWorkspace carve_text(const clipppo_text_s* h, int n, void* base) {
     size_t off = 0;
     uint8_t* b = static_cast<uint8_t*>(base);
     ws.X = reinterpret_cast<__nv_bfloat16*>(b + off);    off += align_up(rows * D * 2, 1024);
-    ws.stats = reinterpret_cast<float*>(b + off);        off += align_up(rows * 2 * 4, 1024);
+    ws.stats = reinterpret_cast<float*>(b + off);        off += align_up(rows * (D / 128) * 2 * 4, 1024);
     ws.Y = reinterpret_cast<__nv_bfloat16*>(b + off);    off += align_up(rows * D * 2, 1024);
     ws.H = reinterpret_cast<__nv_bfloat16*>(b + off);    off += align_up(rows * 4 * D * 2, 1024);
     ws.Xe = reinterpret_cast<__nv_bfloat16*>(b + off);   off += align_up(static_cast<size_t>(n) * D * 2, 1024);
@@ -243,7 +272,9 @@ int encode_text_chunk(const clipppo_text_s* h, const int* tokens, int n, int fla
     const int D = h->cfg.width, T = h->cfg.context, O = h->cfg.out_dim, rows = n * T;
     text_embed_kernel<<<(rows + 7) / 8, 256, 0, stream>>>(tokens, h->tok_emb, h->pos, ws.X, rows, T, D, h->cfg.vocab);
     CLIPPPO_CHECK_LAUNCH();
-    VIT_TRY(run_blocks(h->layers, n, T, D, h->cfg.heads, true, ws.X, ws.stats, ws.Y, ws.H, stream));
+    const bool fused = fused_stats();
+    if (fused) VIT_TRY(rowstats_launch(ws.X, rows, D, D, ws.stats, stream, D / 128));
+    VIT_TRY(run_blocks(h->layers, n, T, D, h->cfg.heads, true, ws.X, ws.stats, ws.Y, ws.H, stream, fused));
     // ln_final is row-wise, so normalising only the EOT rows equals normalising everything and selecting them
     text_gather_eot_kernel<<<(n + 7) / 8, 256, 0, stream>>>(tokens, ws.X, ws.Xe, n, T, D);
     CLIPPPO_CHECK_LAUNCH();
@@ -273,8 +304,10 @@ int encode_chunk(const clipppo_vit_s* h, const void* images, int img_dtype, cons
     CLIPPPO_CHECK_LAUNCH();
     VIT_TRY(gemm_bf16_launch(tmP, h->tm_patch, prow, D, h->kpatch, CLIPPPO_EPI_PATCH_F32, nullptr, h->pos, T,
                              ws.X0, D, stream));
-    VIT_TRY(layernorm_launch(ws.X0, h->ln_pre_g, h->ln_pre_b, rows, D, D, ws.X, stream));          // ln_pre -> bf16 residual
-    VIT_TRY(run_blocks(h->layers, n, T, D, h->cfg.heads, false, ws.X, ws.stats, ws.Y, ws.H, stream));
+    const bool fused = fused_stats();
+    VIT_TRY(layernorm_launch(ws.X0, h->ln_pre_g, h->ln_pre_b, rows, D, D, ws.X, stream,                // ln_pre -> bf16 residual
+                             fused ? ws.stats : nullptr, D / 128));                                   //  (+ the statistics block 0's ln_1 needs)
+    VIT_TRY(run_blocks(h->layers, n, T, D, h->cfg.heads, false, ws.X, ws.stats, ws.Y, ws.H, stream, fused));
     VIT_TRY(layernorm_bf16in_launch(ws.X, h->ln_post_g, h->ln_post_b, n, D, static_cast<long long>(T) * D, ws.Ycls, stream));
     VIT_TRY(gemm_bf16_launch(tmC, h->tm_head, n, O, D, CLIPPPO_EPI_F32, nullptr, nullptr, 0, out, O, stream));
     if (flags & CLIPPPO_VIT_L2NORM) {

@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define CLIPPPO_ABI_VERSION 3
+#define CLIPPPO_ABI_VERSION 4
 
 typedef enum clipppo_status {
     CLIPPPO_OK = 0,
@@ -247,6 +247,7 @@ int clipppo_rowstats_bf16(const void* x_bf16, int rows, int width, int64_t row_s
 #define CLIPPPO_EPI_ROWAFFINE_BF16      6   /* out bf16 = rstd[m]*(acc - mean[m]*colsum[n]) + bias[n]          */
 #define CLIPPPO_EPI_ROWAFFINE_GELU_BF16 7   /* ... followed by QuickGELU                                        */
 #define CLIPPPO_EPI_RESID_BF16          8   /* out bf16 += bf16(acc + bias)  (in-place bf16 residual stream)    */
+#define CLIPPPO_EPI_RESID_STATS_BF16    9   /* out bf16 = bf16(out + acc + bias), + per-row partial statistics   */
 /* out[M,N] = epilogue(A[M,K] @ W[N,K]^T); A, W bf16 K-major, 16-byte aligned rows. */
 int clipppo_gemm_bf16(const void* a_bf16, const void* w_bf16, int M, int N, int K, int epilogue,
                       const float* bias, const float* pos, int tokens, void* out, int64_t ldo,
@@ -259,6 +260,18 @@ int clipppo_gemm_bf16(const void* a_bf16, const void* w_bf16, int M, int N, int 
 int clipppo_gemm_bf16_fused(const void* a_bf16, const void* w_bf16, int M, int N, int K, int epilogue,
                             const float* bias, const float* row_stats, const float* colsum,
                             void* out_bf16, int64_t ldo, clipppo_stream_t stream);
+/* The residual update with the NEXT LayerNorm's row statistics fused in ([clip] ResidualAttentionBlock:
+ * x = x + attn(ln_1(x)); x = x + mlp(ln_2(x)) - the statistics ln_2 / the next block's ln_1 need are those of
+ * the rows this epilogue has just written): x[M,N] (bf16, in place) = bf16(x + A W^T + bias) with ONE rounding,
+ * and row_parts_out fp32 [M, ceil(N/128), 2] = (sum, sum of squares) of the updated row over each 128-column slice.
+ * N % 64 == 0. */
+int clipppo_gemm_bf16_resid_stats(const void* a_bf16, const void* w_bf16, int M, int N, int K, const float* bias,
+                                  void* x_bf16, int64_t ldo, float* row_parts_out, clipppo_stream_t stream);
+/* clipppo_gemm_bf16_fused's ROWAFFINE epilogues (6, 7) fed with those partial sums instead of (mean, rstd):
+ * row_parts fp32 [M, n_parts, 2]; mean = sum/K, rstd = 1/sqrt(max(sumsq/K - mean^2, 0) + 1e-5), parts added in index order. */
+int clipppo_gemm_bf16_fused_parts(const void* a_bf16, const void* w_bf16, int M, int N, int K, int epilogue,
+                                  const float* bias, const float* row_parts, int n_parts, const float* colsum,
+                                  void* out_bf16, int64_t ldo, clipppo_stream_t stream);
 #ifdef CLIPPPO_BUILD_PROBES
 /* Measurement probe - compiled only with -DCLIPPPO_BUILD_PROBES (CLIPPPO_BUILD_PROBES=1 python clip-ppo_b200/build.py --force),
  * absent from the product library and its ABI (profiles/ only, never on the product path): the GEMM above with parts switched

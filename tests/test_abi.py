@@ -26,7 +26,7 @@ def test_binding_lists_every_header_symbol():
 
 
 def test_version_and_strerror(native):
-    assert native.clipppo_abi_version() == 3
+    assert native.clipppo_abi_version() == 4
     assert native.clipppo_strerror(0) == b"ok"
     assert b"channels" in native.clipppo_strerror(-2)
     assert native.clipppo_strerror(-12345) == b"unknown status"

@@ -124,6 +124,75 @@ def test_gemm_bf16_residual_reduce_add(native, monkeypatch, M, N, K, split):
         assert (err > 0).float().mean().item() < 0.05
 
 
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (1000, 768, 768), (6400, 768, 3072), (19000, 768, 768), (50, 64, 64),
+                                   (3200, 1024, 4096), (77 * 9, 512, 2048), (40000, 768, 768)])
+def test_gemm_resid_stats_epilogue(native, M, N, K):
+    """RESID_STATS: X (bf16, in place) = bf16(X + A W^T + bias) with one rounding, and the (sum, sum of squares) of every
+    updated row over each 128-column slice - what is left of the LayerNorm that follows the residual add
+    ([clip] ResidualAttentionBlock: ln_2 after the attention branch, the next block's ln_1 after the MLP)."""
+    from clip_ppo_b200 import _native as Nn
+    gen = torch.Generator(device="cuda").manual_seed(M + N + K)
+    a = (torch.randn(M, K, device="cuda", generator=gen) * 0.5).bfloat16()
+    w = (torch.randn(N, K, device="cuda", generator=gen) * (K ** -0.5)).bfloat16()
+    bias = torch.randn(N, device="cuda", generator=gen) * 0.1
+    x0 = (torch.randn(M, N, device="cuda", generator=gen) * 2 + 0.3).bfloat16()
+    X = x0.clone()
+    P = (N + 127) // 128
+    parts = torch.full((M, P, 2), float("nan"), device="cuda")
+    Nn.check(native.clipppo_gemm_bf16_resid_stats(a.data_ptr(), w.data_ptr(), M, N, K, bias.data_ptr(), X.data_ptr(), N,
+                                                  parts.data_ptr(), _stream()))
+    torch.cuda.synchronize()
+    ref32 = x0.float() + a.float() @ w.float().t() + bias
+    ref = ref32.bfloat16()
+    err = (X.float() - ref.float()).abs()
+    # one rounding of the fp32 sum: differences only where accumulation order moves a value across a rounding boundary
+    assert err.max().item() <= 2 ** -7 * max(1.0, ref32.abs().max().item()), err.max().item()
+    assert (err > 0).float().mean().item() < 0.02
+    # the statistics are those of the rows as STORED
+    xs = X.float()
+    assert not torch.isnan(parts).any()
+    pad = P * 128 - N
+    xp = torch.nn.functional.pad(xs, (0, pad)).view(M, P, 128)
+    assert torch.allclose(parts[:, :, 0], xp.sum(2), atol=2e-3, rtol=1e-5)
+    assert torch.allclose(parts[:, :, 1], (xp * xp).sum(2), atol=2e-3, rtol=1e-5)
+
+
+@pytest.mark.parametrize("M,N,K,epi", [(1000, 768, 768, 6), (6400, 2304, 768, 6), (12800, 3072, 768, 7), (77 * 5, 1536, 512, 6)])
+def test_gemm_rowaffine_from_partial_sums(native, M, N, K, epi):
+    """The folded-LayerNorm epilogue fed with the partial sums of RESID_STATS must equal the same epilogue fed with
+    two-pass (mean, rstd) up to fp32 rounding of the variance."""
+    from clip_ppo_b200 import _native as Nn
+    gen = torch.Generator(device="cuda").manual_seed(M + N + K + epi)
+    x = (torch.randn(M, K, device="cuda", generator=gen) * 1.5 + 0.7).bfloat16()
+    x[:, 3] *= 40.0                                                     # an outlier channel, as real CLIP streams have
+    W = torch.randn(N, K, device="cuda", generator=gen) * (K ** -0.5)
+    b = torch.randn(N, device="cuda", generator=gen) * 0.1
+    gamma = 1 + 0.1 * torch.randn(K, device="cuda", generator=gen)
+    beta = 0.1 * torch.randn(K, device="cuda", generator=gen)
+    Wf = (W * gamma).bfloat16()
+    colsum = Wf.float().sum(1).contiguous()
+    bias2 = (b + W @ beta).contiguous()
+    xf = x.float()
+    P = K // 128
+    xp = xf.view(M, P, 128)
+    parts = torch.stack([xp.sum(2), (xp * xp).sum(2)], 2).contiguous()
+    stats = torch.stack([xf.mean(1), torch.rsqrt(xf.var(1, unbiased=False) + 1e-5)], 1).contiguous()
+    o1 = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    o2 = torch.empty_like(o1)
+    Nn.check(native.clipppo_gemm_bf16_fused(x.data_ptr(), Wf.data_ptr(), M, N, K, epi, bias2.data_ptr(), stats.data_ptr(),
+                                            colsum.data_ptr(), o1.data_ptr(), N, _stream()))
+    Nn.check(native.clipppo_gemm_bf16_fused_parts(x.data_ptr(), Wf.data_ptr(), M, N, K, epi, bias2.data_ptr(), parts.data_ptr(), P,
+                                                  colsum.data_ptr(), o2.data_ptr(), N, _stream()))
+    torch.cuda.synchronize()
+    d = (o1.float() - o2.float()).abs()
+    assert d.max().item() <= 2 ** -7 * max(1.0, o1.float().abs().max().item()), d.max().item()
+    assert (d > 0).float().mean().item() < 0.01
+    ref = torch.nn.functional.layer_norm(xf, (K,), gamma, beta, 1e-5) @ W.t() + b
+    if epi == 7:
+        ref = ref * torch.sigmoid(1.702 * ref)
+    assert (o2.float() - ref).abs().mean().item() <= 4e-3
+
+
 @pytest.mark.parametrize("rows,width", [(50, 768), (6401, 768), (257, 1024)])
 def test_rowstats_vs_torch(native, rows, width):
     from clip_ppo_b200 import _native as Nn
@@ -325,6 +394,22 @@ def test_chunked_batch_and_uint8_input(native, monkeypatch):
     whole = eng.encode(u8, pre_scale=1 / 255.0, l2norm=True)                  # one pass over all 1500 images
     assert torch.equal(whole, a)
     assert torch.isfinite(a).all()
+
+
+def test_fused_row_statistics_schedule_matches_the_rowstats_schedule(native, monkeypatch):
+    """The default schedule (residual GEMM epilogues leave the next LayerNorm's row statistics) against the round-1
+    schedule (TMA reduce-add + a rowstats pass per folded GEMM): same embeddings up to the bf16 rounding of the stream."""
+    eng = _engine(0)
+    gen = torch.Generator().manual_seed(11)
+    x = torch.rand(300, 3, 224, 224, generator=gen).cuda()
+    a = eng.encode(x, pre_scale=1.0, l2norm=True)
+    monkeypatch.setenv("CLIPPPO_GEMM_RESID", "reduce")
+    b = eng.encode(x, pre_scale=1.0, l2norm=True)
+    monkeypatch.delenv("CLIPPPO_GEMM_RESID")
+    c = eng.encode(x, pre_scale=1.0, l2norm=True)
+    assert torch.equal(a, c)                                  # deterministic
+    cos = torch.nn.functional.cosine_similarity(a, b, dim=1)
+    assert cos.min().item() >= 0.9995, cos.min().item()
 
 
 def test_frozen_features_and_encode_image(native):
