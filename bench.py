@@ -9,8 +9,9 @@ Workload: BASELINE.json configs[2] - synthetic 224x224 RGB frames, 4096 per GPU 
 disturbances, seeded random ViT-B/32 weights (no CLIP weights exist offline).
 
 One step, every call the PUBLIC drop-in surface of shared/ (the calls the reference's training scripts make):
-    d    = DisturbanceWrapperGPU.apply_disturbances(x, noise=...)                  one fused launch          (D1)
-    obs  = d * 255                                                                 the call sites' own `* 255` (clip_ppo_minigrid.py:388)
+    obs  = DisturbanceWrapperGPU.apply_disturbances(x, noise=..., out_scale=255)   one fused launch (D1); out_scale = the call sites'
+                                                                                   own `* 255` (clip_ppo_minigrid.py:388) done by the
+                                                                                   kernel's store, bit-identical to the separate pass
     emb  = generate_clip_embeddings(NONE, model, "image", B, dev, images=obs)      /255 + resize + normalise + tower + L2 norm (V0-V7)
     loss = compute_cosine_embedding_loss(z, emb)                                   (L1)
     N>1: GradBucket.all_reduce_mean() of the PPO agent's real gradients (the path's only exchange)
@@ -237,7 +238,8 @@ def workload_config(args, per_gpu_batch, note=None):
                        f"{args.model} embed -> cosine alignment loss",
            "per_gpu_batch": per_gpu_batch, "frame": [3, args.hw, args.hw], "severity": args.severity,
            "weights": f"seeded random {args.model} (openai key layout)",
-           "api": "apply_disturbances -> `* 255` -> generate_clip_embeddings(images=) -> compute_cosine_embedding_loss (public calls only)",
+           "api": "apply_disturbances(out_scale=255: the `* 255` of the call sites inside the kernel's store, bit-identical) -> "
+                  "generate_clip_embeddings(images=) -> compute_cosine_embedding_loss (public calls only)",
            "inputs": f"frame / noise / latent chunks of {CHUNK} seeded by GLOBAL chunk index (the same data whatever the GPU count)",
            "l2_policy": "inputs larger than L2 (x + noise = 4.9 GB per step at 4096 frames); no flush needed",
            "parallelism": f"dp{args.gpus} by observation, frozen tower replicated, PPO-agent gradient all-reduce only"}
@@ -321,8 +323,10 @@ def main():
     del x8
 
     def path(xf, nz, zz):
-        d = disturber.apply_disturbances(xf, noise=nz, contrast_factor=1.1, cutout_start=window)
-        emb = U.generate_clip_embeddings(U.AblationMode.NONE, model, "image", xf.shape[0], dev, images=d * 255.0)
+        # out_scale=255: the `* 255` between the two calls (the rollout buffers hold 0..255) done by the kernel's store,
+        # bit-identical to `apply_disturbances(...) * 255` (tests/test_disturb_gpu.py::test_out_scale_equals_a_separate_multiply_bitwise)
+        d255 = disturber.apply_disturbances(xf, noise=nz, contrast_factor=1.1, cutout_start=window, out_scale=255.0)
+        emb = U.generate_clip_embeddings(U.AblationMode.NONE, model, "image", xf.shape[0], dev, images=d255)
         return U.compute_cosine_embedding_loss(zz, emb), emb
 
     # the exchange of the path: the PPO agent's gradients.  One real backward (alignment loss of the agent's latents against
@@ -420,15 +424,18 @@ def main():
                 dev_u8[b].copy_(host[b], non_blocking=True)
                 ready[b].record(copy_stream)
 
+        e2e_noise_seed = [None]                                 # None: torch.randn_like's stream (the reference's); int: in-kernel Philox
+
         def step_e2e(i):
             b = i & 1
             prefetch(i + 1)                                     # next step's frames ride under this step's compute
             main_stream.wait_event(ready[b])
             # uint8 frames straight into the public call: the kernel reads them as `.float() / 255` (bit-identical to
-            # the reference benchmark's conversion on the device); randn on device + CPU-generator draws as in the reference
-            d = disturber.apply_disturbances(dev_u8[b])
+            # the reference benchmark's conversion on the device); CPU-generator draws as in the reference; the noise is
+            # torch.randn on the device (default) or generated inside the kernel (opt-in noise_seed=)
+            d = disturber.apply_disturbances(dev_u8[b], out_scale=255.0, noise_seed=e2e_noise_seed[0])
             consumed[b].record(main_stream)
-            emb = U.generate_clip_embeddings(U.AblationMode.NONE, model, "image", B, dev, images=d * 255.0)
+            emb = U.generate_clip_embeddings(U.AblationMode.NONE, model, "image", B, dev, images=d)
             ls = U.compute_cosine_embedding_loss(z, emb)
             if bucket is not None:
                 torch._foreach_copy_([p.grad for p in bucket.params], saved_grads)
@@ -441,24 +448,37 @@ def main():
         for b in range(2):
             consumed[b].record(main_stream)
         prefetch(0)
-        for i in range(args.warmup):
-            step_e2e(i)
-        barrier()
-        t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
-        t0.record()
-        base = args.warmup
-        for i in range(args.steps):
-            step_e2e(base + i)
-        done[(base + args.steps - 1) & 1].synchronize()
-        t1.record()
-        barrier()
-        ms_e2e = max_over_ranks(t0.elapsed_time(t1))
+        base = [0]
+
+        def timed_e2e():
+            for i in range(args.warmup):
+                step_e2e(base[0] + i)
+            base[0] += args.warmup
+            barrier()
+            t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+            t0.record()
+            for i in range(args.steps):
+                step_e2e(base[0] + i)
+            done[(base[0] + args.steps - 1) & 1].synchronize()
+            t1.record()
+            base[0] += args.steps
+            barrier()
+            return max_over_ranks(t0.elapsed_time(t1))
+
+        ms_e2e = timed_e2e()                                    # the reference's RNG contract: noise = torch.randn on the device
+        e2e_noise_seed[0] = 20260000 + rank
+        ms_e2e_philox = timed_e2e()                             # opt-in: noise generated inside the disturbance kernel
         e2e = {"value": world * B * args.steps / (ms_e2e * 1e-3), "unit": "frames/s",
                "h2d_bytes_per_step": B * 3 * hw * hw, "d2h_bytes_per_step": 4,
                "ms_per_step": ms_e2e / args.steps,
                "note": "uint8 frames from pinned host memory, H2D prefetched one step ahead on a copy stream, handed to "
-                       "apply_disturbances as uint8 (read as .float()/255 inside the kernel); noise drawn on device "
-                       "(randn); `* 255` and generate_clip_embeddings as in the scripts; loss copied back to pinned memory every step"}
+                       "apply_disturbances as uint8 (read as .float()/255 inside the kernel); noise drawn on device by "
+                       "torch.randn (the reference's stream); `* 255` inside the kernel's store (out_scale); "
+                       "generate_clip_embeddings as in the scripts; loss copied back to pinned memory every step",
+               "in_kernel_noise": {"value": world * B * args.steps / (ms_e2e_philox * 1e-3), "unit": "frames/s",
+                                   "ms_per_step": ms_e2e_philox / args.steps,
+                                   "note": "the same step with apply_disturbances(noise_seed=): N(0,1) draws generated inside the "
+                                           "kernel (Philox4x32-10 + Box-Muller, opt-in, not torch's stream; oracle/philox.py)"}}
         del host, dev_u8
 
     # ---- N > 1: shard-vs-whole parity and the strong-scaling figure ---------------------------------
@@ -609,6 +629,11 @@ def disturb_hbm_rows(dev, pk):
         gbs = 12.0 * xx.numel() / (ms * 1e-3) / 1e9
         rows.append({"severity": sev, "shape": list(shape), "us": round(ms * 1e3, 1), "gb_per_s": round(gbs, 1),
                      "frac_of_hbm_peak": round(gbs / pk["hbm"], 4)})
+        if sev == "MODERATE":       # the opt-in variants of the bench shape: in-kernel Philox noise (8 B / element), + uint8 frames (5 B)
+            ms = event_ms(lambda: w.apply_disturbances(xx, noise_seed=11, contrast_factor=1.1, cutout_start=win, out_scale=255.0), 10, warm=3)
+            rows.append({"severity": sev, "shape": list(shape), "variant": "in-kernel Philox noise + out_scale, 8 B/element",
+                         "us": round(ms * 1e3, 1), "gb_per_s": round(8.0 * xx.numel() / (ms * 1e-3) / 1e9, 1),
+                         "frac_of_hbm_peak": round(8.0 * xx.numel() / (ms * 1e-3) / 1e9 / pk["hbm"], 4)})
         del xx, nn_
     torch.cuda.empty_cache()
     return rows
@@ -655,8 +680,8 @@ def secondary_measurements(args, dev, pk, disturb_rows):
         w = DisturbanceWrapperGPU(device=dev, seed=3, severity=DisturbanceSeverity.MODERATE)
 
         def l14():
-            d = w.apply_disturbances(xs, noise=nz, contrast_factor=1.1, cutout_start=(44, 56))
-            e = U.generate_clip_embeddings(U.AblationMode.NONE, model, "image", nL, dev, images=d * 255.0)
+            d = w.apply_disturbances(xs, noise=nz, contrast_factor=1.1, cutout_start=(44, 56), out_scale=255.0)
+            e = U.generate_clip_embeddings(U.AblationMode.NONE, model, "image", nL, dev, images=d)
             return U.compute_cosine_embedding_loss(zz, e)
         ms = event_ms(l14, 3)
         out["vit_l14"] = {"config": "BASELINE configs[4] tower variant: ViT-L/14 (width 1024, 24 blocks, 257 tokens), 1024 frames of 224x224x3, "

@@ -25,7 +25,7 @@ EPI_BIAS_BF16, EPI_BIAS_GELU_BF16, EPI_BIAS_RESID_F32, EPI_PATCH_F32, EPI_F32 = 
 # every symbol the header declares; tests/test_abi.py checks the .so exports all of them
 SYMBOLS = (
     "clipppo_abi_version", "clipppo_strerror", "clipppo_last_cuda_error", "clipppo_prof_begin", "clipppo_prof_end", "clipppo_prof_bucket",
-    "clipppo_disturb_f32", "clipppo_disturb_u8_f32", "clipppo_disturb_nhwc_u8",
+    "clipppo_disturb_f32", "clipppo_disturb_u8_f32", "clipppo_disturb_nhwc_u8", "clipppo_disturb_ex",
     "clipppo_cosine_loss_fwd", "clipppo_cosine_loss_bwd", "clipppo_gae_f32", "clipppo_ppo_loss_f32",
     "clipppo_vit_create", "clipppo_vit_destroy", "clipppo_vit_workspace_bytes", "clipppo_vit_encode",
     "clipppo_text_create", "clipppo_text_destroy", "clipppo_text_workspace_bytes", "clipppo_text_encode",
@@ -37,6 +37,19 @@ SYMBOLS = (
 
 class NativeLibraryMissing(RuntimeError):
     pass
+
+
+DISTURB_PHILOX = 1
+
+
+class DisturbDesc(C.Structure):       # clipppo_disturb_desc (include/clipppo_b200.h)
+    _fields_ = [("x", C.c_void_p), ("x_dtype", C.c_int), ("x_strides_host", C.POINTER(C.c_int64)),
+                ("noise", C.c_void_p), ("noise_strides_host", C.POINTER(C.c_int64)), ("out", C.c_void_p),
+                ("B", C.c_int), ("C", C.c_int), ("H", C.c_int), ("W", C.c_int), ("stages", C.c_int),
+                ("noise_sigma", C.c_float), ("contrast", C.c_float), ("k1d_host", C.POINTER(C.c_float)), ("k", C.c_int),
+                ("sh", C.c_int), ("sw", C.c_int), ("ph", C.c_int), ("pw", C.c_int),
+                ("out_scale", C.c_float), ("flags", C.c_int),
+                ("philox_seed", C.c_uint64), ("philox_offset", C.c_uint64), ("first_image", C.c_int64)]
 
 
 class VitConfig(C.Structure):
@@ -86,6 +99,7 @@ def lib() -> C.CDLL:
     L.clipppo_disturb_f32.argtypes = [vp, i64p, vp, i64p, vp, i, i, i, i, i, f, f, fp, i, i, i, i, i, vp]
     L.clipppo_disturb_u8_f32.argtypes = [vp, vp, vp, i, i, i, i, i, f, f, fp, i, i, i, i, i, vp]
     L.clipppo_disturb_nhwc_u8.argtypes = [vp, i, vp, i64p, vp, i, i, i, i, i, f, f, fp, i, i, i, i, i, vp]
+    L.clipppo_disturb_ex.argtypes = [C.POINTER(DisturbDesc), vp]
     L.clipppo_cosine_loss_fwd.argtypes = [vp, vp, i, i, vp, vp, vp]
     L.clipppo_cosine_loss_bwd.argtypes = [vp, vp, vp, vp, i, i, vp, vp, vp]
     L.clipppo_gae_f32.argtypes = [vp, vp, vp, vp, vp, i, i, d, d, vp, vp, vp]

@@ -53,6 +53,12 @@ struct DisturbParams {
     int nthreads;   // fast path: CTA size (covers the blur tasks in one round when it can)
     int log2S;      // fast path: S is a power of two
     unsigned magic_nq, magic_nsplit, magic_rs;   // fast path: ceil(2^32 / d), so that __umulhi(n, magic) == n / d for n < 2^16
+    float out_scale;   // fast path: the result is multiplied by this on the way out (1: off).  `apply_disturbances(...) * 255`
+                       // of the call sites (clip_ppo_atari.py:584, the rollout buffers hold 0..255) without a pass of its own
+    int philox;        // fast path, opt-in: no noise tensor - the N(0,1) draws are generated in the kernel (Philox4x32-10
+                       // keyed by philox_seed, counter = (logical NCHW quad index, philox_offset), Box-Muller): 8 B / element
+    unsigned long long philox_seed, philox_offset;
+    long long philox_first;   // global index of image 0 of this call (a shard of a larger batch draws the whole batch's noise)
     __device__ __forceinline__ float* out_f32() const { return static_cast<float*>(out); }
 };
 
@@ -156,6 +162,37 @@ __device__ __forceinline__ void blur_task(const float* __restrict__ base, float*
 constexpr int kPad = 4;
 constexpr int kFastMaxThreads = 384;     // x 2 CTAs / SM => at most 85 registers per thread
 
+// ---- in-kernel noise (opt-in; the default path reads the tensor torch.randn_like drew) ----------------------
+// Philox4x32-10 (Salmon et al., the generator behind torch's CUDA randn) on counter (quad_lo, quad_hi, off_lo, off_hi)
+// and key (seed_lo, seed_hi); the four 32-bit outputs become the four N(0,1) draws of the quad by two Box-Muller
+// transforms.  A draw is a function of (seed, offset, logical NCHW element index) only: independent of the stripe
+// decomposition, of the memory layout of x and of the number of GPUs a batch is sharded over (global image index
+// goes in through the base quad index).  oracle/philox.py restates it in numpy.
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const unsigned hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+        const unsigned hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+        c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+        k.x += 0x9E3779B9u; k.y += 0xBB67AE85u;
+    }
+    return c;
+}
+// (a, b) -> two N(0,1): r = sqrt(-2 ln u), u = (a + 0.5) 2^-32 in (0, 1); theta = pi * int32(b) * 2^-31 in [-pi, pi)
+__device__ __forceinline__ float2 box_muller(unsigned a, unsigned b) {
+    const float u = fmaf(static_cast<float>(a), 2.3283064365386963e-10f, 1.1641532182693481e-10f);
+    const float r = sqrtf(-1.3862943611198906f * __log2f(u));           // -2 ln 2 * log2 u
+    const float th = static_cast<float>(static_cast<int>(b)) * 1.4629180792671596e-9f;   // pi * 2^-31
+    return make_float2(r * __cosf(th), r * __sinf(th));
+}
+__device__ __forceinline__ float4 philox_normal4(unsigned long long quad, unsigned long long seed, unsigned long long offset) {
+    const uint4 r = philox4x32_10(make_uint4(static_cast<unsigned>(quad), static_cast<unsigned>(quad >> 32),
+                                             static_cast<unsigned>(offset), static_cast<unsigned>(offset >> 32)),
+                                  make_uint2(static_cast<unsigned>(seed), static_cast<unsigned>(seed >> 32)));
+    const float2 a = box_muller(r.x, r.y), b = box_muller(r.z, r.w);
+    return make_float4(a.x, a.y, b.x, b.y);
+}
+
 template <int N, typename F>
 __device__ __forceinline__ void static_for(F&& f) {
     if constexpr (N > 0) {
@@ -210,9 +247,12 @@ __device__ __forceinline__ void hfilter4p(const float* __restrict__ rowq, const 
 // One image = one cluster of S stripe-CTAs (S = 1: a plain CTA).  The only cluster-wide dependency is
 // the per-image gray mean of the contrast stage: one barrier, with the halo-row loads between its
 // ARRIVE and its WAIT.
-template <int K, int WT, bool XU8, bool NHWC>
+// VAR 0: the plain kernel.  VAR 1: + out_scale.  VAR 2: + in-kernel Philox noise (and out_scale).  Separate instantiations so
+// that the plain kernel - at the 85-register limit for k = 7 - carries none of it.
+template <int K, int WT, bool XU8, bool NHWC, int VAR = 0>
 __global__ void __launch_bounds__(kFastMaxThreads, 2)
 disturb_fast_kernel(const __grid_constant__ DisturbParams p) {
+    constexpr bool PHILOX = (VAR == 2), SCALED = (VAR >= 1);
     constexpr int P = K / 2;
     extern __shared__ __align__(16) float smem[];
     float* red = smem;
@@ -235,6 +275,9 @@ disturb_fast_kernel(const __grid_constant__ DisturbParams p) {
     const float sigma = p.sigma_n;
     const int n4 = rows * nq;
     const int HW = H * W;
+    // PHILOX: logical NCHW quad index of (image b, channel 0, row 0, column 0)
+    [[maybe_unused]] const unsigned long long quad0 =
+        (static_cast<unsigned long long>(b) + static_cast<unsigned long long>(p.philox_first)) * static_cast<unsigned>(C * (HW >> 2));
 
     auto noisy4 = [&](float4 v, const float4& nz) {     // [tv] gaussian_noise_image: mul, add, clamp - no FMA contraction (bit-exact)
         if (do_noise) {
@@ -275,7 +318,7 @@ disturb_fast_kernel(const __grid_constant__ DisturbParams p) {
                     for (int c_ = 0; c_ < CT; ++c_) {
                         if constexpr (xu8) xv[u][c_].x = __uint_as_float(ld_stream_u32(reinterpret_cast<const uint8_t*>(xs) + c_ * HW + 4 * j));
                         else xv[u][c_] = ld_stream_f4(xs + c_ * HW + 4 * j);
-                        if (do_noise) nv[u][c_] = ld_stream_f4(ns + c_ * HW + 4 * j);
+                        if constexpr (!PHILOX) { if (do_noise) nv[u][c_] = ld_stream_f4(ns + c_ * HW + 4 * j); }
                     }
                 }
             }
@@ -287,6 +330,10 @@ disturb_fast_kernel(const __grid_constant__ DisturbParams p) {
 #pragma unroll
                     for (int c_ = 0; c_ < CT; ++c_) {
                         if constexpr (xu8) xv[u][c_] = u8x4_over_255(__float_as_uint(xv[u][c_].x));
+                        if constexpr (PHILOX) {
+                            if (do_noise) nv[u][c_] = philox_normal4(quad0 + static_cast<unsigned>((c_first + c_) * (HW >> 2) + (r0 * W >> 2) + j),
+                                                                     p.philox_seed, p.philox_offset);
+                        }
                         const float4 v = noisy4(xv[u][c_], nv[u][c_]);
                         gs[c_] += (v.x + v.y) + (v.z + v.w);
                         *reinterpret_cast<float4*>(dst + c_ * plane) = v;
@@ -393,7 +440,8 @@ disturb_fast_kernel(const __grid_constant__ DisturbParams p) {
                 const int goff = c_ * HW + ir * W + 4 * quad;
                 const float4 xv = xu8 ? u8x4_over_255(ld_stream_u32(xb + goff)) : ld_stream_f4(xi + goff);
                 float4 nv = xv;
-                if (do_noise) nv = ld_stream_f4(ni + goff);
+                if constexpr (PHILOX) { if (do_noise) nv = philox_normal4(quad0 + static_cast<unsigned>(goff >> 2), p.philox_seed, p.philox_offset); }
+                else if (do_noise) nv = ld_stream_f4(ni + goff);
                 *reinterpret_cast<float4*>(tile + c_ * plane + lr * WP + kPad + 4 * quad) = noisy4(xv, nv);
             }
         }
@@ -444,6 +492,7 @@ disturb_fast_kernel(const __grid_constant__ DisturbParams p) {
     const int ntasks = C * nsplit * nq;
     const bool do_cut = (p.stages & CLIPPPO_STAGE_CUTOUT) != 0;
     const int sw_end = p.sw + p.pw;
+    [[maybe_unused]] const float2 sc2 = make_float2(p.out_scale, p.out_scale);
     auto blur_image = [&]() {
         for (int task = tid; task < ntasks; task += nth) {
             const int rest = div_nq(task), q = task - rest * nq;
@@ -480,6 +529,9 @@ disturb_fast_kernel(const __grid_constant__ DisturbParams p) {
                 }
                 const int irr = ir + rr;
                 if (irr >= cut0 && irr < cut1) { o01 = __fmul2_rn(o01, keep01); o23 = __fmul2_rn(o23, keep23); }
+                if constexpr (SCALED) {             // one fp32 multiply: == `out * scale` of torch, bit for bit
+                    o01 = __fmul2_rn(o01, sc2); o23 = __fmul2_rn(o23, sc2);
+                }
                 st_stream_f4(outq + rr * W, make_float4(o01.x, o01.y, o23.x, o23.y));
             };
             int r = ra;
@@ -774,12 +826,12 @@ static int launch_disturb(const DisturbParams& p, size_t smem, cudaStream_t stre
     return CLIPPPO_OK;
 }
 
-template <int K, int WT, bool XU8, bool NHWC>
+template <int K, int WT, bool XU8, bool NHWC, int VAR = 0>
 static int launch_disturb_fast_x(const DisturbParams& p, size_t smem, cudaStream_t stream) {
     static DeviceOnce configured;
     if (configured.first_use()) {
-        CLIPPPO_CUDA_TRY(cudaFuncSetAttribute(disturb_fast_kernel<K, WT, XU8, NHWC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        CLIPPPO_CUDA_TRY(cudaFuncSetAttribute(disturb_fast_kernel<K, WT, XU8, NHWC>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        CLIPPPO_CUDA_TRY(cudaFuncSetAttribute(disturb_fast_kernel<K, WT, XU8, NHWC, VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        CLIPPPO_CUDA_TRY(cudaFuncSetAttribute(disturb_fast_kernel<K, WT, XU8, NHWC, VAR>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(static_cast<unsigned>(p.B) * p.S);
@@ -794,13 +846,32 @@ static int launch_disturb_fast_x(const DisturbParams& p, size_t smem, cudaStream
     cfg.attrs = attr;
     // without the contrast stage the stripes of an image are independent: plain CTAs, no gang scheduling
     cfg.numAttrs = ((p.stages & CLIPPPO_STAGE_CONTRAST) && p.S > 1) ? 1 : 0;
-    CLIPPPO_CUDA_TRY(cudaLaunchKernelEx(&cfg, disturb_fast_kernel<K, WT, XU8, NHWC>, p));
+    CLIPPPO_CUDA_TRY(cudaLaunchKernelEx(&cfg, disturb_fast_kernel<K, WT, XU8, NHWC, VAR>, p));
     prof_count_launch();
     return CLIPPPO_OK;
 }
 
 template <int K, int WT>
 static int launch_disturb_fast_w(const DisturbParams& p, size_t smem, cudaStream_t stream) {
+    if (p.philox || p.out_scale != 1.0f) {
+        // the two additive features: contiguous NCHW images (fp32 or uint8) of the reference's frame widths; Philox noise for
+        // the blurring severities.  Anything else: UNSUPPORTED, the caller falls back to torch noise / a separate multiply.
+        if constexpr (WT != 0) {
+            if (p.nhwc) return CLIPPPO_ERR_UNSUPPORTED;
+            if (p.philox) {
+                if constexpr (K > 1) {
+                    return p.x_u8 ? launch_disturb_fast_x<K, WT, true, false, 2>(p, smem, stream)
+                                  : launch_disturb_fast_x<K, WT, false, false, 2>(p, smem, stream);
+                } else {
+                    return CLIPPPO_ERR_UNSUPPORTED;
+                }
+            }
+            return p.x_u8 ? launch_disturb_fast_x<K, WT, true, false, 1>(p, smem, stream)
+                          : launch_disturb_fast_x<K, WT, false, false, 1>(p, smem, stream);
+        } else {
+            return CLIPPPO_ERR_UNSUPPORTED;
+        }
+    }
     if (p.nhwc) return launch_disturb_fast_x<K, WT, false, true>(p, smem, stream);
     return p.x_u8 ? launch_disturb_fast_x<K, WT, true, false>(p, smem, stream) : launch_disturb_fast_x<K, WT, false, false>(p, smem, stream);
 }
@@ -837,7 +908,8 @@ static int run_disturb(DisturbParams& p, const float* k1d_host, int k, cudaStrea
     if (max_cluster == 0) max_cluster = env_cl;
     if (p.B <= 0 || p.C <= 0 || p.H <= 0 || p.W <= 0) return CLIPPPO_ERR_BAD_SHAPE;
     if (!p.x || !p.out) return CLIPPPO_ERR_NULL;
-    if ((p.stages & CLIPPPO_STAGE_NOISE) && !p.noise) return CLIPPPO_ERR_NULL;
+    if ((p.stages & CLIPPPO_STAGE_NOISE) && !p.noise && !p.philox) return CLIPPPO_ERR_NULL;
+    if (p.out_scale == 0.0f) p.out_scale = 1.0f;
     if ((p.stages & CLIPPPO_STAGE_CONTRAST) && p.C != 1 && p.C != 3) return CLIPPPO_ERR_BAD_CHANNELS;
     int K = 1;
     if (p.stages & CLIPPPO_STAGE_BLUR) {
@@ -915,6 +987,7 @@ static int run_disturb(DisturbParams& p, const float* k1d_host, int k, cudaStrea
         }
         return st;
     }
+    if (p.philox || p.out_scale != 1.0f) return CLIPPPO_ERR_UNSUPPORTED;      // fast-kernel features: the caller falls back (torch noise / a `* scale` pass)
     // ---- general path (disturb_kernel): any strides, NHWC / uint8 I/O, odd widths, wide kernels ----
     // stripes per image: the smallest cluster whose stripe fits the occupancy target
     auto smem_for = [&](int S) {
@@ -1056,4 +1129,50 @@ extern "C" int clipppo_disturb_nhwc_u8(const void* obs, int obs_is_f32,
     p.io_mode = obs_is_f32 ? 2 : 1;
     p.fast = 0;
     return run_disturb(p, k1d_host, k, as_stream(stream));
+}
+
+// The extended form (additive): uint8 or fp32 frames, an output scale, optional in-kernel noise.
+extern "C" int clipppo_disturb_ex(const clipppo_disturb_desc* d, clipppo_stream_t stream) {
+    if (!d) return CLIPPPO_ERR_NULL;
+    const bool philox = (d->flags & CLIPPPO_DISTURB_PHILOX) != 0;
+    if (philox && d->noise) return CLIPPPO_ERR_BAD_SHAPE;                  // either a noise tensor or the generator
+    DisturbParams p = {};
+    p.x = d->x; p.noise = d->noise; p.out = d->out;
+    p.B = d->B; p.C = d->C; p.H = d->H; p.W = d->W;
+    const int B = d->B, C = d->C, H = d->H, W = d->W;
+    if (B <= 0 || C <= 0 || H <= 0 || W <= 0) return CLIPPPO_ERR_BAD_SHAPE;
+    const long long dflt[4] = {(long long)C * H * W, (long long)H * W, W, 1};
+    for (int i = 0; i < 4; ++i) {
+        p.xs[i] = d->x_strides_host ? d->x_strides_host[i] : dflt[i];
+        p.ns[i] = d->noise_strides_host ? d->noise_strides_host[i] : dflt[i];
+    }
+    p.stages = d->stages & CLIPPPO_STAGE_ALL;
+    p.sigma_n = d->noise_sigma;
+    p.c = d->contrast;
+    p.omc = static_cast<float>(1.0 - static_cast<double>(d->contrast));
+    p.sh = d->sh; p.sw = d->sw; p.ph = d->ph; p.pw = d->pw;
+    p.io_mode = 0;
+    p.out_scale = d->out_scale == 0.0f ? 1.0f : d->out_scale;
+    p.philox = philox ? 1 : 0;
+    p.philox_seed = d->philox_seed;
+    p.philox_offset = d->philox_offset;
+    const bool need_noise = (p.stages & CLIPPPO_STAGE_NOISE) != 0 && !philox;
+    if (d->x_dtype == CLIPPPO_IMG_U8) {
+        if (!is_contig_nchw(p.xs, C, H, W) || (need_noise && !is_contig_nchw(p.ns, C, H, W))) return CLIPPPO_ERR_UNSUPPORTED;
+        if ((W % 4) || (reinterpret_cast<uintptr_t>(d->x) % 4)) return CLIPPPO_ERR_UNSUPPORTED;
+        if (need_noise && d->noise && (reinterpret_cast<uintptr_t>(d->noise) % 16)) return CLIPPPO_ERR_ALIGN;
+        p.x_u8 = 1; p.fast = 1; p.batch_contig = 1;
+    } else {
+        p.batch_contig = is_contig_nchw(p.xs, C, H, W) && (!need_noise || is_contig_nchw(p.ns, C, H, W));
+        const bool aligned = (W % 4 == 0) && (reinterpret_cast<uintptr_t>(d->x) % 16 == 0) &&
+                             (!need_noise || reinterpret_cast<uintptr_t>(d->noise) % 16 == 0);
+        p.fast = is_image_contig(p.xs, B, C, H, W) && (!need_noise || is_image_contig(p.ns, B, C, H, W)) && aligned;
+        if (!p.fast && C == 3 && aligned && is_nhwc_dense(p.xs, B, H, W) && (!need_noise || is_nhwc_dense(p.ns, B, H, W))) {
+            p.fast = 1;
+            p.nhwc = 1;
+        }
+    }
+    // the generator indexes draws by GLOBAL image number, so a batch sharded over ranks sees the noise of the whole batch
+    p.philox_first = d->first_image;
+    return run_disturb(p, d->k1d_host, d->k, as_stream(stream));
 }

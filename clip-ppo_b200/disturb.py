@@ -49,17 +49,72 @@ def _require_cuda(t: torch.Tensor, what: str) -> None:
                            f"(got device {t.device})")
 
 
+def _fused_disturb_ex(x, stages, noise, noise_sigma, contrast, taps, window, out_scale, philox) -> Optional[torch.Tensor]:
+    """clipppo_disturb_ex: the fast kernel with an output scale and / or in-kernel Philox noise.  None when the kernel
+    does not serve the shape (the caller falls back)."""
+    B, Cc, H, W = x.shape
+    out = torch.empty((B, Cc, H, W), dtype=torch.float32, device=x.device)
+    if B == 0:
+        return out
+    d = N.DisturbDesc()
+    d.x, d.x_dtype = x.data_ptr(), (N.IMG_U8 if x.dtype == torch.uint8 else N.IMG_F32)
+    xs = N.strides4(x)
+    d.x_strides_host = C.cast(xs, C.POINTER(C.c_int64))
+    ns = None
+    if (stages & N.STAGE_NOISE) and philox is None:
+        if noise is None:
+            raise ValueError("noise stage needs a noise tensor")
+        if noise.shape != x.shape or noise.dtype != torch.float32 or noise.device != x.device:
+            raise ValueError("noise must match x in shape, dtype (fp32) and device")
+        ns = N.strides4(noise)
+        d.noise, d.noise_strides_host = noise.data_ptr(), C.cast(ns, C.POINTER(C.c_int64))
+    d.out = out.data_ptr()
+    d.B, d.C, d.H, d.W, d.stages = B, Cc, H, W, stages
+    d.noise_sigma, d.contrast = float(noise_sigma), float(contrast)
+    k = len(taps) if (stages & N.STAGE_BLUR) else 0
+    taps_arr = (C.c_float * max(k, 1))(*(taps if k else (1.0,)))
+    d.k1d_host, d.k = C.cast(taps_arr, C.POINTER(C.c_float)), k
+    d.sh, d.sw, d.ph, d.pw = (int(v) for v in window)
+    d.out_scale = float(out_scale)
+    if philox is not None:
+        seed, offset, first_image = philox
+        d.flags = N.DISTURB_PHILOX
+        d.philox_seed, d.philox_offset, d.first_image = int(seed) & (2 ** 64 - 1), int(offset) & (2 ** 64 - 1), int(first_image)
+    with N.device_ctx(x.device):
+        st = N.lib().clipppo_disturb_ex(C.byref(d), _stream_ptr(x))
+    if st == N.ERR_UNSUPPORTED:
+        return None
+    N.check(st, "clipppo_disturb_ex")
+    return out
+
+
 def fused_disturb(x: torch.Tensor, *, stages: int, noise: Optional[torch.Tensor] = None,
                   noise_sigma: float = 0.0, contrast: float = 1.0,
                   taps: Optional[Sequence[float]] = None,
-                  window: Tuple[int, int, int, int] = (0, 0, 0, 0)) -> torch.Tensor:
+                  window: Tuple[int, int, int, int] = (0, 0, 0, 0),
+                  out_scale: float = 1.0, philox: Optional[Tuple[int, int, int]] = None) -> torch.Tensor:
     """out[B,C,H,W] fp32 (contiguous) = cutout(blur(contrast(noise(x)))) restricted to `stages`.
     x may have arbitrary strides (e.g. the NHWC view of clip_ppo_minigrid.py:385).  uint8 x (additive): pixels
     0..255 are read as float(v) * fl(1/255), bit-identical to `x.float() / 255` evaluated by PyTorch on the device,
-    without materialising the fp32 batch."""
+    without materialising the fp32 batch.
+    Additive: `out_scale` multiplies the result inside the kernel (== `out * out_scale`, bit for bit; a separate
+    in-place multiply for the shapes the fast kernel does not serve); `philox = (seed, offset, first_image)` draws the
+    noise inside the kernel instead of reading a tensor (opt-in, its own stream - see include/clipppo_b200.h)."""
     _require_cuda(x, "fused_disturb")
     if x.dim() != 4:
         raise ValueError(f"expected [B,C,H,W], got shape {tuple(x.shape)}")
+    if philox is not None and noise is not None:
+        raise ValueError("either a noise tensor or in-kernel noise, not both")
+    if out_scale != 1.0 or philox is not None:
+        xe = x if x.dtype in (torch.uint8, torch.float32) else x.float()
+        out = _fused_disturb_ex(xe, stages, noise, noise_sigma, contrast, taps, window, out_scale, philox)
+        if out is not None:
+            return out
+        if philox is not None:
+            raise NotImplementedError("in-kernel noise is served for contiguous NCHW frames of width 84 / 224 with a blur stage "
+                                      "(k = 3, 5, 7); draw the noise with torch for other shapes")
+        out = fused_disturb(x, stages=stages, noise=noise, noise_sigma=noise_sigma, contrast=contrast, taps=taps, window=window)
+        return out.mul_(out_scale)
     if x.dtype == torch.uint8:
         out = _fused_disturb_u8(x, stages, noise, noise_sigma, contrast, taps, window)
         if out is not None:

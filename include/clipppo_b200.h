@@ -99,6 +99,38 @@ int clipppo_disturb_nhwc_u8(const void* obs, int obs_is_f32,
                             float noise_sigma, float contrast, const float* k1d_host, int k,
                             int sh, int sw, int ph, int pw, clipppo_stream_t stream);
 
+/* The extended form of clipppo_disturb_f32 / clipppo_disturb_u8_f32 (additive; same chain, same kernels):
+ *   out_scale  : the result is multiplied by this on the way out (0 or 1: off) - the `* 255` that follows
+ *                apply_disturbances at the call sites (clip_ppo_atari.py:584; the rollout buffers hold 0..255),
+ *                one fp32 multiply per element inside the kernel, bit-identical to the separate pass;
+ *   CLIPPPO_DISTURB_PHILOX ("noise nullable => in-kernel Philox(seed, offset)"): noise must be NULL; the
+ *                N(0,1) draw of element e is Box-Muller over Philox4x32-10(key = philox_seed, counter = (quad index
+ *                of e in the logical [first_image + B, C, H, W] tensor, philox_offset)) - a function of the GLOBAL
+ *                element index only, so shards of a batch draw the noise of the whole batch.  This is NOT the
+ *                stream torch.randn_like draws (the default path keeps that contract by reading the tensor);
+ *                oracle/philox.py restates it.  8 B (fp32 frames) / 5 B (uint8) per element instead of 12 / 9.
+ * Both are served by the fast kernel only (contiguous [C,H,W] images, W % 4 == 0, k <= 7; PHILOX: k >= 3, NCHW):
+ * anything else returns CLIPPPO_ERR_UNSUPPORTED and the caller falls back (torch noise / a separate multiply). */
+#define CLIPPPO_DISTURB_PHILOX 1
+typedef struct clipppo_disturb_desc {
+    const void* x;                          /* frames: fp32 in [0,1] or uint8 0..255 (x_dtype = CLIPPPO_IMG_*) */
+    int x_dtype;
+    const int64_t* x_strides_host;          /* element strides of the logical [B,C,H,W] view, or NULL = contiguous */
+    const float* noise;                     /* fp32, or NULL (no noise stage, or CLIPPPO_DISTURB_PHILOX)       */
+    const int64_t* noise_strides_host;
+    float* out;                             /* contiguous fp32 [B,C,H,W]                                        */
+    int B, C, H, W, stages;
+    float noise_sigma, contrast;
+    const float* k1d_host;
+    int k;
+    int sh, sw, ph, pw;
+    float out_scale;
+    int flags;
+    uint64_t philox_seed, philox_offset;
+    int64_t first_image;
+} clipppo_disturb_desc;
+int clipppo_disturb_ex(const clipppo_disturb_desc* desc, clipppo_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * L1  cosine alignment loss, forward and backward.
  * Replaces compute_cosine_embedding_loss (shared/clip_ppo_utils.py:48-76) and its autograd.

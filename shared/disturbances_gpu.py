@@ -85,6 +85,7 @@ class DisturbanceWrapperGPU:
         self.cutout_ratio = cutout_ratio
         if seed is not None:
             torch.manual_seed(seed)          # global, like the reference (:54-55)
+        self._philox_calls = 0               # counter offset of the opt-in in-kernel noise (apply_disturbances(noise_seed=))
         self._kernel_size = _D.blur_kernel_size(self.gaussian_blur_sigma)
         self.blur_transform = _BlurStage(self, self._kernel_size)
         self.noise_transform = _NoiseStage(self)
@@ -121,16 +122,29 @@ class DisturbanceWrapperGPU:
     # ---- tensor API --------------------------------------------------------------------------
     def apply_disturbances(self, obs: torch.Tensor, *, noise: Optional[torch.Tensor] = None,
                            contrast_factor: Optional[float] = None,
-                           cutout_start: Optional[Tuple[int, int]] = None) -> torch.Tensor:
+                           cutout_start: Optional[Tuple[int, int]] = None,
+                           out_scale: float = 1.0, noise_seed: Optional[int] = None,
+                           first_image: int = 0) -> torch.Tensor:
         """noise -> contrast -> blur -> cutout (reference :66-73), one fused launch.  Additive: uint8 `obs` holds
-        0..255 pixels and equals `apply_disturbances(obs.float() / 255)` bit for bit (same RNG consumption)."""
-        if noise is None:
+        0..255 pixels and equals `apply_disturbances(obs.float() / 255)` bit for bit (same RNG consumption).
+        Additive keywords (defaults = the reference's behaviour):
+          out_scale   `apply_disturbances(obs, out_scale=255.0)` == `apply_disturbances(obs) * 255` bit for bit, without
+                      the extra pass over the batch (the call sites store 0..255: clip_ppo_atari.py:584);
+          noise_seed  opt-in: the Gaussian noise is generated inside the kernel (Philox4x32-10 keyed by this seed, one
+                      counter offset per call) instead of `torch.randn_like(obs)` - N(0,1) draws, but NOT torch's stream
+                      and the device generator is not consumed; `first_image` is the global index of obs[0] when obs is a
+                      shard of a larger batch (the shards then draw the whole batch's noise)."""
+        philox = None
+        if noise is None and noise_seed is not None:
+            philox = (noise_seed, self._philox_calls, first_image)
+            self._philox_calls += 1
+        elif noise is None:
             noise = self._noise_like(obs)
         c = self._draw_contrast() if contrast_factor is None else float(contrast_factor)
         taps = self._draw_blur_taps()
         window = self._draw_cutout(obs.shape[-2], obs.shape[-1], cutout_start)
         return _D.fused_disturb(obs, stages=_N.STAGE_ALL, noise=noise, noise_sigma=self.gaussian_noise_sigma,
-                                contrast=c, taps=taps, window=window)
+                                contrast=c, taps=taps, window=window, out_scale=out_scale, philox=philox)
 
     def apply_gaussian_noise(self, obs: torch.Tensor, *, noise: Optional[torch.Tensor] = None) -> torch.Tensor:
         if noise is None:

@@ -345,6 +345,79 @@ def test_numpy_shims_values_vs_oracle(native, batched):
         assert diff.max() <= 1 and (diff > 0).mean() < 1e-3, (name, int(diff.max()), float((diff > 0).mean()))
 
 
+@pytest.mark.parametrize("shape,sev,u8", [((9, 3, 224, 224), "MODERATE", False), ((5, 3, 224, 224), "SEVERE", True),
+                                          ((300, 1, 84, 84), "HARD", False), ((40, 3, 84, 84), "MILD", True)])
+def test_out_scale_equals_a_separate_multiply_bitwise(native, shape, sev, u8):
+    """apply_disturbances(out_scale=255) == apply_disturbances(...) * 255 (the `* 255` of the call sites,
+    clip_ppo_atari.py:584) bit for bit - one fp32 multiply either way."""
+    gen = torch.Generator().manual_seed(sum(shape))
+    w = _wrapper(sev)
+    x = torch.randint(0, 256, shape, generator=gen, dtype=torch.uint8).cuda()
+    if not u8:
+        x = x.float() / 255.0
+    noise = torch.randn(shape, generator=gen).cuda()
+    kw = dict(noise=noise, contrast_factor=1.17, cutout_start=(7, 12))
+    a = w.apply_disturbances(x, **kw) * 255.0
+    b = w.apply_disturbances(x, out_scale=255.0, **kw)
+    assert torch.equal(a, b)
+    assert b.max().item() > 100.0
+
+
+def test_out_scale_falls_back_for_shapes_outside_the_fast_kernel(native):
+    gen = torch.Generator().manual_seed(3)
+    w = _wrapper("MODERATE")
+    x = torch.rand(4, 3, 40, 56, generator=gen).cuda()
+    noise = torch.randn(4, 3, 40, 56, generator=gen).cuda()
+    kw = dict(noise=noise, contrast_factor=0.9, cutout_start=(3, 4))
+    assert torch.equal(w.apply_disturbances(x, **kw) * 255.0, w.apply_disturbances(x, out_scale=255.0, **kw))
+
+
+@pytest.mark.parametrize("shape,sev,u8", [((9, 3, 224, 224), "MODERATE", False), ((6, 3, 224, 224), "SEVERE", True),
+                                          ((300, 1, 84, 84), "HARD", False), ((150, 3, 84, 84), "MILD", False),
+                                          ((7, 3, 84, 84), "SEVERE", True)])
+def test_in_kernel_philox_noise_matches_its_oracle(native, shape, sev, u8):
+    """apply_disturbances(noise_seed=s) (opt-in: N(0,1) draws generated inside the kernel) against the same call fed with
+    the noise tensor oracle/philox.py computes for (seed, call counter): <= 1e-5 on the disturbed frames, for whole
+    images, stripe clusters (224 x 224: halo rows re-generate the neighbours' draws) and env-step batches."""
+    from oracle import philox as P
+    gen = torch.Generator().manual_seed(sum(shape) + 1)
+    x = torch.randint(0, 256, shape, generator=gen, dtype=torch.uint8).cuda()
+    if not u8:
+        x = x.float() / 255.0
+    seed = 0x1234_5678_9ABC_DEF0 + shape[0]
+    w = _wrapper(sev)
+    kw = dict(contrast_factor=0.83, cutout_start=(5, 9))
+    state = torch.cuda.get_rng_state()
+    outs = [w.apply_disturbances(x, noise_seed=seed, **kw) for _ in range(2)]       # call counter 0, 1
+    assert torch.equal(state, torch.cuda.get_rng_state())                             # the device generator is not consumed
+    assert not torch.equal(outs[0], outs[1])
+    for call, out in enumerate(outs):
+        noise = torch.from_numpy(P.normal_noise(seed, call, shape)).cuda()
+        ref = w.apply_disturbances(x, noise=noise, **kw)
+        err = (out - ref).abs().max().item()
+        assert err <= TOL, (call, err)
+    # a shard of the batch draws the whole batch's noise (G-invariance, SURVEY 8e)
+    w2 = _wrapper(sev)
+    lo = shape[0] // 3
+    part = w2.apply_disturbances(x[lo:].contiguous(), noise_seed=seed, first_image=lo, **kw)
+    d = (part - outs[0][lo:]).abs().max().item()
+    # the noise is a function of the GLOBAL element index, so a shard sees exactly the draws of the whole batch; the only thing
+    # that may move is the last bit of an 84 x 84 image's gray mean when the shard falls below 148 images and its frames are cut
+    # into stripe clusters (run_disturb: widen_for_small_batches) - 224 x 224 frames always use the same 8 stripes
+    assert d == 0.0 if shape[-1] == 224 else d <= 5e-7, d
+
+
+def test_in_kernel_noise_refuses_shapes_it_does_not_serve(native):
+    w = _wrapper("MODERATE")
+    x = torch.rand(2, 3, 40, 56).cuda()
+    with pytest.raises(NotImplementedError):
+        w.apply_disturbances(x, noise_seed=1)
+    with pytest.raises(ValueError):
+        from clip_ppo_b200 import disturb as D
+        D.fused_disturb(torch.rand(2, 3, 84, 84).cuda(), stages=15, noise=torch.randn(2, 3, 84, 84).cuda(), noise_sigma=0.1,
+                        taps=(0.25, 0.5, 0.25), window=(0, 0, 4, 4), philox=(1, 0, 0))
+
+
 def test_atari_call_site(native):
     from clip_ppo_b200 import rollout
     w = _wrapper("HARD")

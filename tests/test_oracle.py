@@ -161,3 +161,21 @@ def test_loss_oracle_against_reference_goldens():
     assert torch.allclose(nlp.grad, t("ppo_g_newlogprob"), atol=1e-8)
     assert torch.allclose(ent.grad, t("ppo_g_entropy"), atol=1e-8)
     assert torch.allclose(nv.grad, t("ppo_g_newvalue"), atol=1e-8)
+
+
+def test_philox_oracle_known_answers():
+    """oracle/philox.py against Random123's published known-answer vectors for philox4x32-10, and the moments of the
+    Box-Muller draws built on it (the generator behind apply_disturbances(noise_seed=...))."""
+    import numpy as np
+    from oracle import philox as P
+    for ctr, key, out in P.KAT:
+        r = P.philox4x32_10(*[np.uint32(v) for v in ctr], *key)
+        assert tuple(int(v) for v in r) == out
+    n = P.normal_noise(seed=123456789012345, offset=7, shape=(16, 3, 224, 224))
+    assert n.dtype == np.float32 and np.isfinite(n).all()
+    n = n.astype(np.float64)                                   # 2.4 M draws: the tolerances are > 4 standard errors
+    assert abs(n.mean()) < 3e-3 and abs(n.std() - 1.0) < 3e-3
+    assert abs((n ** 3).mean()) < 1e-2 and abs((n ** 4).mean() - 3.0) < 3e-2
+    # a shard draws the whole batch's noise
+    assert np.array_equal(P.normal_noise(5, 2, (3, 3, 84, 84), first_image=4), P.normal_noise(5, 2, (7, 3, 84, 84))[4:])
+
