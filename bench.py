@@ -273,8 +273,10 @@ class PolicyEncoder(torch.nn.Module):
     def __init__(self, n_actions: int = 7):
         super().__init__()
         nn = torch.nn
-        self.network = nn.Sequential(nn.Conv2d(3, 32, 8, stride=4), nn.ReLU(), nn.Conv2d(32, 64, 4, stride=2), nn.ReLU(),
-                                     nn.Conv2d(64, 64, 3, stride=1), nn.ReLU(), nn.Flatten(), nn.Linear(64 * 7 * 7, 512), nn.ReLU())
+        from clip_ppo_b200.policy import NatureCNN
+        # the encoder runs on this repository's fp32 implicit-GEMM kernels (csrc/policy.cu): the gradients the
+        # all-reduce carries are produced by them, deterministically
+        self.network = NatureCNN(3)
         self.actor = nn.Linear(512, n_actions)
         self.critic = nn.Linear(512, 1)
 

@@ -1,5 +1,6 @@
 """Not a test: in-situ kernel time breakdown of the bench step (torch.profiler / CUPTI, real clocks,
-kernels overlapping as they do in the step).  python tools/step_profile.py [frames]"""
+kernels overlapping as they do in the step; a kernel launched with PDL counts the time it waits for its predecessor).
+python tools/step_profile.py [frames] [ViT-B/32 | ViT-L/14]"""
 import os
 import re
 import sys
@@ -16,19 +17,20 @@ from shared.disturbance_types import DisturbanceSeverity
 from shared.disturbances_gpu import DisturbanceWrapperGPU
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
+NAME = sys.argv[2] if len(sys.argv) > 2 else "ViT-B/32"
 dev = torch.device("cuda", 0)
-model = U.load_clip_model("ViT-B/32", device=dev)
+model = U.load_clip_model(NAME, device=dev)
 engine = U._engine_for(model)
 w = DisturbanceWrapperGPU(device=dev, seed=1, severity=DisturbanceSeverity.MODERATE)
 g = torch.Generator(device=dev).manual_seed(0)
 x = torch.rand(B, 3, 224, 224, device=dev, generator=g)
 noise = torch.randn(B, 3, 224, 224, device=dev, generator=g)
-z = torch.relu(torch.randn(B, 512, device=dev, generator=g))
+z = torch.relu(torch.randn(B, engine.cfg.out_dim, device=dev, generator=g))
 
 
 def step():
-    d = w.apply_disturbances(x, noise=noise, contrast_factor=1.1, cutout_start=(44, 56))
-    emb = engine.encode(d, pre_scale=1.0, l2norm=True)
+    d = w.apply_disturbances(x, noise=noise, contrast_factor=1.1, cutout_start=(44, 56), out_scale=255.0)
+    emb = U.generate_clip_embeddings(U.AblationMode.NONE, model, "image", B, dev, images=d)
     return U.compute_cosine_embedding_loss(z, emb)
 
 
