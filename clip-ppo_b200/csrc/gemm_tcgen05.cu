@@ -577,6 +577,17 @@ EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
+// Work units (CTAs, or CTA pairs) a GEMM launch may occupy.  Default: the whole part.  CLIPPPO_GEMM_MAX_SMS=n leaves
+// 148 - n SMs to kernels running on other streams (tools/probe_two_stream.py: the half-batch overlap experiment).
+int gemm_max_units(int cl) {
+    static int sms = 0;
+    if (!sms) {
+        const char* e = getenv("CLIPPPO_GEMM_MAX_SMS");
+        sms = (e && atoi(e) >= 2 && atoi(e) <= kNumSMs) ? atoi(e) : kNumSMs;
+    }
+    return sms / cl;
+}
+
 int cluster_mode() {
     static int mode = 0;
     if (!mode) {
@@ -596,7 +607,7 @@ int launch_gemm_mode(const CUtensorMap& ta, const CUtensorMap& tb, const CUtenso
     }
     const int m_tiles = (g.M + BM - 1) / BM, n_tiles = (g.N + BN - 1) / BN;
     const int work = ((m_tiles + C::CL - 1) / C::CL) * n_tiles * (EPI == CLIPPPO_EPI_RESID_BF16 ? g.ksplit : 1);
-    const int grid = min(work, kNumSMs / C::CL) * C::CL;
+    const int grid = min(work, gemm_max_units(C::CL)) * C::CL;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(NUM_THREADS);

@@ -72,7 +72,7 @@ class TextEngine:
             torch.cuda.synchronize(self.device)          # staging copies above ran on torch's stream
             N.check(N.lib().clipppo_text_create(C.byref(self._handle), C.byref(ncfg), C.byref(W)), "clipppo_text_create")
         del keep
-        self._workspace: Optional[torch.Tensor] = None
+        self._workspaces = {}                # one cached workspace per CUDA stream (concurrent passes on two streams must not share one)
 
     def __del__(self):
         h = getattr(self, "_handle", None)
@@ -86,10 +86,15 @@ class TextEngine:
     def _workspace_for(self, n: int) -> torch.Tensor:
         need = C.c_size_t()
         N.check(N.lib().clipppo_text_workspace_bytes(self._handle, n, C.byref(need)), "clipppo_text_workspace_bytes")
-        if self._workspace is None or self._workspace.numel() < need.value:
-            self._workspace = None
-            self._workspace = torch.empty(need.value, dtype=torch.uint8, device=self.device)
-        return self._workspace
+        key = torch.cuda.current_stream(self.device).cuda_stream
+        ws = self._workspaces.pop(key, None)
+        if ws is None or ws.numel() < need.value:
+            ws = None
+            while len(self._workspaces) >= 4:
+                self._workspaces.pop(next(iter(self._workspaces)))
+            ws = torch.empty(need.value, dtype=torch.uint8, device=self.device)
+        self._workspaces[key] = ws
+        return ws
 
     @torch.no_grad()
     def encode(self, tokens: torch.Tensor, l2norm: bool = True) -> torch.Tensor:

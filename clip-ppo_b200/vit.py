@@ -90,7 +90,7 @@ class VitEngine:
             torch.cuda.synchronize(self.device)          # staging copies above ran on torch's stream
             N.check(N.lib().clipppo_vit_create(C.byref(self._handle), C.byref(ncfg), C.byref(W)), "clipppo_vit_create")
         del keep                                         # create() has repacked into handle-owned memory
-        self._workspace: Optional[torch.Tensor] = None
+        self._workspaces: Dict[int, torch.Tensor] = {}   # one cached workspace per CUDA stream that has called encode()
         self._graphs: Dict[tuple, tuple] = {}            # small-batch schedule: one captured CUDA graph per call shape
 
     def __del__(self):
@@ -102,13 +102,22 @@ class VitEngine:
                 pass
             self._handle = None
 
+    WORKSPACE_STREAMS = 4             # cached workspaces kept (least recently used stream evicted)
+
     def _workspace_for(self, n: int) -> torch.Tensor:
+        """The activation workspace of a tower pass, cached PER STREAM: two passes enqueued on different streams may run
+        concurrently and must not share one (a pass owns its workspace from its first kernel to its last)."""
         need = C.c_size_t()
         N.check(N.lib().clipppo_vit_workspace_bytes(self._handle, n, C.byref(need)), "clipppo_vit_workspace_bytes")
-        if self._workspace is None or self._workspace.numel() < need.value:
-            self._workspace = None
-            self._workspace = torch.empty(need.value, dtype=torch.uint8, device=self.device)
-        return self._workspace
+        key = torch.cuda.current_stream(self.device).cuda_stream
+        ws = self._workspaces.pop(key, None)
+        if ws is None or ws.numel() < need.value:
+            ws = None
+            while len(self._workspaces) >= self.WORKSPACE_STREAMS:
+                self._workspaces.pop(next(iter(self._workspaces)))
+            ws = torch.empty(need.value, dtype=torch.uint8, device=self.device)
+        self._workspaces[key] = ws
+        return ws
 
     # A tower pass is ~90 launches; below a few hundred images the host cannot enqueue them as fast as the
     # GPU runs them (measured on B200: 64 frames = 1.0 ms eager, of which 0.8 ms is host enqueue).  That is

@@ -412,6 +412,28 @@ def test_fused_row_statistics_schedule_matches_the_rowstats_schedule(native, mon
     assert cos.min().item() >= 0.9995, cos.min().item()
 
 
+def test_two_streams_encode_concurrently_without_sharing_a_workspace(native):
+    """Two tower passes enqueued on two streams may overlap on the device: each stream gets its own cached workspace, and
+    the halves equal the whole batch bit for bit (batch invariance)."""
+    eng = _engine(0)
+    gen = torch.Generator().manual_seed(12)
+    x = torch.rand(600, 3, 224, 224, generator=gen).cuda()
+    whole = eng.encode(x, pre_scale=1.0, l2norm=True)
+    cur = torch.cuda.current_stream()
+    streams = [torch.cuda.Stream() for _ in range(2)]
+    outs = []
+    for st, h in zip(streams, (x[:300], x[300:])):
+        st.wait_stream(cur)
+        with torch.cuda.stream(st):
+            for _ in range(3):                                  # several passes in flight per stream
+                o = eng.encode(h, pre_scale=1.0, l2norm=True)
+            outs.append(o)
+    for st in streams:
+        cur.wait_stream(st)
+    torch.cuda.synchronize()
+    assert torch.equal(torch.cat(outs), whole)
+
+
 def test_frozen_features_and_encode_image(native):
     import shared.clip_ppo_utils as U
     model = U.load_clip_model("ViT-B/32", device="cuda")
