@@ -554,6 +554,207 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
     }
 }
 
+// =============================================================================================
+// Short sequences (T <= 64; ViT-B/32: T = 50) on the same machinery, two images per tensor-core tile.
+//
+// At T = 50 a head is a 50 x 50 x 64 problem: the kernel is bound by HBM (25.6 KB per (image, head)) and, at the
+// power-capped clock of a real step, by instruction issue - the mma.sync version (attention.cu) executes ~1600 warp
+// instructions per item.  Here a work item is (image PAIR, head): the two images' Q / K / V slices land by TMA in
+// rows 0 .. T-1 and 64 .. 64+T-1 of 128-row tiles (the other rows stay zero), ONE 128 x 128 x 64 tcgen05.mma
+// computes both score blocks (the off-diagonal blocks are never read), thread = query row reads its own image's
+// 64 columns straight out of TMEM, exponentiates T of them, writes P back as a block-diagonal bf16 operand
+// (zeros in the other image's half), and O = P V is one more MMA chain over the 128 keys with V as the MN-major
+// shared-memory operand.  ~400 warp instructions per item.
+//   warps 0-3 / 4-7   two softmax warpgroups, one per TMEM slot: warpgroup g owns the CTA's items g, g + 2, ...
+//   warp 8            lane 0 issues every tcgen05.mma: S(i), then P V of item i - 1
+//   warp 9            lane 0 issues the TMA loads, up to four items ahead (4 x 48 KB stages)
+constexpr int TP_STAGES = 4;
+constexpr int TP_STAGE_BYTES = 3 * TILE_BYTES;                  // Q | K | V tiles of one item: 48 KB
+constexpr int TP_OFF_BAR = TP_STAGES * TP_STAGE_BYTES;
+enum { PB_LOAD = 0, PB_FREE = TP_STAGES, PB_S = 2 * TP_STAGES, PB_P = 2 * TP_STAGES + 2, PB_O = 2 * TP_STAGES + 4,
+       PB_TFREE = 2 * TP_STAGES + 6, TP_NUM_BARS = 2 * TP_STAGES + 8 };
+constexpr int TP_SMEM_BYTES = TP_OFF_BAR + TP_NUM_BARS * 8 + 16 + 1024;
+constexpr int TP_THREADS = 320;
+constexpr int TP_SLOT_COLS = 192;                               // per TMEM slot: S / P 128 columns, O 64 columns
+
+struct TpArgs {
+    int n_items, T, heads;
+    uint32_t v_lbo, v_sbo, p_kstep_cols;
+};
+
+__global__ void __launch_bounds__(TP_THREADS, 1)
+attention_tc_pair_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_out, const TpArgs g) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const uint32_t sbase = smem_u32(smem);
+    auto bar = [&](int i) { return sbase + TP_OFF_BAR + 8u * i; };
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + TP_OFF_BAR + TP_NUM_BARS * 8);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int WP_MMA = 8, WP_TMA = 9;
+
+    pdl_launch_dependents();
+    const int T = g.T, heads = g.heads, D = heads * DH;
+    if (warp == WP_TMA && lane == 0) {
+        prefetch_tmap(&tm_in);
+        prefetch_tmap(&tm_out);
+        for (int i = 0; i < TP_STAGES; ++i) { mbar_init(bar(PB_LOAD + i), 1); mbar_init(bar(PB_FREE + i), 4); }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(bar(PB_S + i), 1); mbar_init(bar(PB_P + i), 4); mbar_init(bar(PB_O + i), 1); mbar_init(bar(PB_TFREE + i), 4);
+        }
+        fence_barrier_init();
+    }
+    if (warp == WP_MMA) tmem_alloc(smem_u32(tmem_slot), ATC_TMEM_COLS);
+    // rows T .. 63 and 64 + T .. 127 of every tile are never written by a TMA box: zero everything once
+    for (int i = threadIdx.x; i < TP_OFF_BAR / 16; i += TP_THREADS) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0u, 0u, 0u, 0u);
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();
+
+    if (warp == WP_TMA) {
+        if (lane == 0) {
+            int it = 0;
+            for (int item = blockIdx.x; item < g.n_items; item += gridDim.x, ++it) {
+                const int pair = item / heads, head = item - pair * heads;
+                const int stg = it % TP_STAGES, use = it / TP_STAGES;
+                if (use > 0) mbar_wait_cold(bar(PB_FREE + stg), (use - 1) & 1);
+                const uint32_t base = sbase + stg * TP_STAGE_BYTES;
+                mbar_arrive_expect_tx(bar(PB_LOAD + stg), 6u * static_cast<uint32_t>(T) * 128u);
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {                 // an image beyond the batch (odd n) is zero-filled by the TMA unit
+#pragma unroll
+                    for (int m = 0; m < 3; ++m)
+                        tma_load_3d(base + m * TILE_BYTES + h * 64 * 128, &tm_in, bar(PB_LOAD + stg), m * D + head * DH, 0, 2 * pair + h);
+                }
+            }
+        }
+    } else if (warp == WP_MMA) {
+        if (lane == 0) {
+            constexpr uint32_t idesc_s = make_idesc_bf16(TILE, TILE);
+            const uint32_t idesc_pv = make_idesc_bf16(TILE, DH) | (1u << 16);     // B (= V) is MN-major
+            auto issue_pv = [&](int j) {                       // O_j = P_j V_j over all 128 key rows of the tile
+                const int slot = j & 1, stg = j % TP_STAGES;
+                mbar_wait_hot(bar(PB_P + slot), (j >> 1) & 1);
+                tc_fence_after();
+                const uint32_t v_addr = sbase + stg * TP_STAGE_BYTES + 2 * TILE_BYTES;
+                const uint32_t ts = tmem_base + TP_SLOT_COLS * slot;
+#pragma unroll
+                for (int k = 0; k < TILE / 16; ++k)
+                    umma_bf16_ts(ts + 128, ts + g.p_kstep_cols * k, make_mnmajor_sw128_desc(v_addr + k * 2048, g.v_lbo, g.v_sbo), idesc_pv, k != 0);
+                umma_commit(bar(PB_O + slot));
+            };
+            int it = 0;
+            for (int item = blockIdx.x; item < g.n_items; item += gridDim.x, ++it) {
+                const int slot = it & 1, stg = it % TP_STAGES;
+                mbar_wait_cold(bar(PB_LOAD + stg), (it / TP_STAGES) & 1);
+                if (it >= 2) mbar_wait_hot(bar(PB_TFREE + slot), ((it >> 1) - 1) & 1);      // the slot's previous item has left TMEM
+                tc_fence_after();
+                const uint32_t base = sbase + stg * TP_STAGE_BYTES;
+                const uint64_t dq = make_kmajor_sw128_desc(base), dk = make_kmajor_sw128_desc(base + TILE_BYTES);
+#pragma unroll
+                for (int k = 0; k < DH / 16; ++k) umma_bf16(tmem_base + TP_SLOT_COLS * slot, dq + 2 * k, dk + 2 * k, idesc_s, k != 0);
+                umma_commit(bar(PB_S + slot));
+                if (it >= 1) issue_pv(it - 1);
+            }
+            if (it >= 1) issue_pv(it - 1);
+        }
+    } else {
+        // ===================== softmax + epilogue: warpgroup wg owns TMEM slot wg, thread = row of the tile =====================
+        const int wg = warp >> 2, wq = warp & 3;
+        const int r = wq * 32 + lane;                           // tile row = TMEM lane
+        const int half = wq >> 1, t = r & 63;                   // which image of the pair, token
+        const uint32_t trow = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + TP_SLOT_COLS * wg;
+        const float sl2 = 0.125f * 1.4426950408889634f;
+        int it = 0;
+        for (int item = blockIdx.x; item < g.n_items; item += gridDim.x, ++it) {
+            if ((it & 1) != wg) continue;
+            const int pair = item / heads, head = item - pair * heads;
+            const int stg = it % TP_STAGES;
+            const uint32_t ph = (it >> 1) & 1;
+            mbar_wait_hot(bar(PB_S + wg), ph);
+            tc_fence_after();
+            uint32_t v[2][32];
+            tmem_ld_32x32(trow + 64 * half, v[0]);
+            tmem_ld_32x32(trow + 64 * half + 32, v[1]);
+            tmem_ld_wait();
+            float mxa[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+            for (int j = 0; j < 64; ++j) {
+                if (j >= T) v[j >> 5][j & 31] = 0xff800000u;   // keys beyond T (zero rows of the K tile)
+                mxa[j & 3] = fmaxf(mxa[j & 3], __uint_as_float(v[j >> 5][j & 31]));
+            }
+            const float m = fmaxf(fmaxf(mxa[0], mxa[1]), fmaxf(mxa[2], mxa[3])) * sl2;
+            const float2 nm2 = make_float2(-m, -m), sc2 = make_float2(sl2, sl2);
+            float2 sum2 = make_float2(0.f, 0.f);
+            uint32_t pk[32];
+#pragma unroll
+            for (int j = 0; j < 64; j += 2) {
+                const float2 x = __ffma2_rn(make_float2(__uint_as_float(v[j >> 5][j & 31]), __uint_as_float(v[j >> 5][(j & 31) + 1])), sc2, nm2);
+                const float2 e = make_float2(ex2f(x.x), ex2f(x.y));
+                sum2 = __fadd2_rn(sum2, e);
+                pk[j >> 1] = pack_bf16x2(e.x, e.y);
+            }
+            {   // P: keys 0 .. 63 in packed columns 0 .. 31, keys 64 .. 127 in 32 .. 63; the other image's half is zero
+                uint32_t z[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) z[j] = 0u;
+                tmem_st_32x32(trow + 32 * half, pk);
+                tmem_st_32x32(trow + 32 * (1 - half), z);
+            }
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar(PB_P + wg));
+            // ---- O / l ----
+            mbar_wait_hot(bar(PB_O + wg), ph);
+            tc_fence_after();
+            uint32_t oa[2][32];
+            tmem_ld_32x32(trow + 128, oa[0]);
+            tmem_ld_32x32(trow + 160, oa[1]);
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar(PB_TFREE + wg));      // S / P / O of this item are in registers: the slot may take item + 2
+            const float inv = 1.0f / (sum2.x + sum2.y);
+            const float2 inv2 = make_float2(inv, inv);
+            uint8_t* stage = smem + stg * TP_STAGE_BYTES + r * 128;         // my row of the (dead) Q tile
+            if (t < T) {
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    float2 o2[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                        o2[e] = __fmul2_rn(make_float2(__uint_as_float(oa[c >> 2][8 * (c & 3) + 2 * e]),
+                                                       __uint_as_float(oa[c >> 2][8 * (c & 3) + 2 * e + 1])), inv2);
+                    *reinterpret_cast<uint4*>(stage + ((c ^ (r & 7)) << 4)) =
+                        make_uint4(pack_bf16x2(o2[0].x, o2[0].y), pack_bf16x2(o2[1].x, o2[1].y),
+                                   pack_bf16x2(o2[2].x, o2[2].y), pack_bf16x2(o2[3].x, o2[3].y));
+                }
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+                // 32-row slab of image 2 pair + half; tokens >= T and an image beyond the batch are clipped by the TMA unit
+                tma_store_3d(&tm_out, sbase + stg * TP_STAGE_BYTES + wq * 32 * 128, head * DH, (wq & 1) * 32, 2 * pair + half);
+                bulk_commit_group();
+                bulk_wait_group_read<0>();
+                mbar_arrive(bar(PB_FREE + stg));
+            }
+            __syncwarp();
+        }
+        if (lane == 0) bulk_wait_group<0>();
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == WP_MMA) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, ATC_TMEM_COLS);
+    }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -629,6 +830,30 @@ int attention_tc_launch(const void* qkv_bf16, int n_images, int tokens, int head
         for (int w = 0; w < 2; ++w) for (int i = 0; i < 7; ++i) printf("  wg%d %-10s %lld\n", w, names[i], h[w * 8 + i]);
     }
 #endif
+    return CLIPPPO_OK;
+}
+
+bool attention_tc_pair_supported(int tokens, bool causal) { return !causal && tokens >= 16 && tokens <= 64; }
+
+// T <= 64 (ViT-B/32: T = 50): two images per 128-row tensor-core tile
+int attention_tc_pair_launch(const void* qkv_bf16, int n_images, int tokens, int heads, void* out_bf16, cudaStream_t stream) {
+    if (!attention_tc_pair_supported(tokens, false)) return CLIPPPO_ERR_UNSUPPORTED;
+    const long long items = static_cast<long long>((n_images + 1) / 2) * heads;
+    if (items > 0x7fffffffLL) return CLIPPPO_ERR_BAD_SHAPE;
+    const int D = heads * DH;
+    CUtensorMap ti, to;
+    int st = make_seq_tmap(&ti, qkv_bf16, n_images, tokens, 3 * D, tokens);
+    if (!st) st = make_seq_tmap(&to, out_bf16, n_images, tokens, D, 32);
+    if (st) return st;
+    static DeviceOnce configured;
+    if (configured.first_use()) {
+        CLIPPPO_CUDA_TRY(cudaFuncSetAttribute(attention_tc_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TP_SMEM_BYTES));
+    }
+    static const uint32_t v_lbo = env_u32("CLIPPPO_ATC_V_LBO", 64), v_sbo = env_u32("CLIPPPO_ATC_V_SBO", 64),
+                          p_cols = env_u32("CLIPPPO_ATC_P_COLS", 8);
+    TpArgs g{static_cast<int>(items), tokens, heads, v_lbo, v_sbo, p_cols};
+    const int grid = static_cast<int>(items < kNumSMs ? items : kNumSMs);
+    CLIPPPO_CUDA_TRY(launch_pdl(attention_tc_pair_kernel, grid, TP_THREADS, TP_SMEM_BYTES, stream, 1, ti, to, g));
     return CLIPPPO_OK;
 }
 
