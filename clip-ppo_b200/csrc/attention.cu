@@ -475,13 +475,13 @@ int attention_launch(const void* qkv_bf16, int n_images, int tokens, int heads, 
         if (st == CLIPPPO_OK) prof_count_launch();
         return st;
     }
-    // T <= 64 without a mask (ViT-B/32: T = 50): two images per tcgen05 tile.  CLIPPPO_ATT_TC50=0 keeps the mma.sync kernel
-    // below (A/B measurements); read per call so that tests can switch it.
+    // T <= 64 (ViT-B/32: T = 50): two images per tcgen05 tile; causal T <= 128 (text tower: T = 77): one sequence per tile.
+    // CLIPPPO_ATT_TC50=0 keeps the mma.sync kernels below (A/B measurements); read per call so that tests can switch it.
     {
         const char* e = getenv("CLIPPPO_ATT_TC50");
         const bool on = use_tc && !(e && e[0] == '0');
         if (on && attention_tc_pair_supported(tokens, causal)) {
-            const int st = attention_tc_pair_launch(qkv_bf16, n_images, tokens, heads, out_bf16, stream);
+            const int st = attention_tc_pair_launch(qkv_bf16, n_images, tokens, heads, out_bf16, stream, causal);
             if (st == CLIPPPO_OK) prof_count_launch();
             return st;
         }

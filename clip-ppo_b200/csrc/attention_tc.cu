@@ -578,10 +578,13 @@ constexpr int TP_THREADS = 320;
 constexpr int TP_SLOT_COLS = 192;                               // per TMEM slot: S / P 128 columns, O 64 columns
 
 struct TpArgs {
-    int n_items, T, heads;
+    int n_items, T, heads, causal;
     uint32_t v_lbo, v_sbo, p_kstep_cols;
 };
 
+// PAIR = true: T <= 64, work item = (image pair, head).  PAIR = false: 64 < T <= 128, work item = (sequence, head) in rows
+// 0 .. T-1 of the tile - the text tower (T = 77) under its causal mask ([clip] build_attention_mask: query t sees keys 0 .. t).
+template <bool PAIR>
 __global__ void __launch_bounds__(TP_THREADS, 1)
 attention_tc_pair_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_out, const TpArgs g) {
     extern __shared__ uint8_t smem_raw[];
@@ -621,12 +624,17 @@ attention_tc_pair_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid
                 const int stg = it % TP_STAGES, use = it / TP_STAGES;
                 if (use > 0) mbar_wait_cold(bar(PB_FREE + stg), (use - 1) & 1);
                 const uint32_t base = sbase + stg * TP_STAGE_BYTES;
-                mbar_arrive_expect_tx(bar(PB_LOAD + stg), 6u * static_cast<uint32_t>(T) * 128u);
+                mbar_arrive_expect_tx(bar(PB_LOAD + stg), (PAIR ? 6u : 3u) * static_cast<uint32_t>(T) * 128u);
+                if constexpr (PAIR) {
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {                 // an image beyond the batch (odd n) is zero-filled by the TMA unit
+                    for (int h = 0; h < 2; ++h) {             // an image beyond the batch (odd n) is zero-filled by the TMA unit
 #pragma unroll
-                    for (int m = 0; m < 3; ++m)
-                        tma_load_3d(base + m * TILE_BYTES + h * 64 * 128, &tm_in, bar(PB_LOAD + stg), m * D + head * DH, 0, 2 * pair + h);
+                        for (int m = 0; m < 3; ++m)
+                            tma_load_3d(base + m * TILE_BYTES + h * 64 * 128, &tm_in, bar(PB_LOAD + stg), m * D + head * DH, 0, 2 * pair + h);
+                    }
+                } else {
+#pragma unroll
+                    for (int m = 0; m < 3; ++m) tma_load_3d(base + m * TILE_BYTES, &tm_in, bar(PB_LOAD + stg), m * D + head * DH, 0, pair);
                 }
             }
         }
@@ -664,7 +672,9 @@ attention_tc_pair_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid
         // ===================== softmax + epilogue: warpgroup wg owns TMEM slot wg, thread = row of the tile =====================
         const int wg = warp >> 2, wq = warp & 3;
         const int r = wq * 32 + lane;                           // tile row = TMEM lane
-        const int half = wq >> 1, t = r & 63;                   // which image of the pair, token
+        const int half = PAIR ? (wq >> 1) : 0;                  // which image of the pair
+        const int t0 = PAIR ? (r & 63) : r;                     // token of my row
+        const int t = t0;
         const uint32_t trow = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + TP_SLOT_COLS * wg;
         const float sl2 = 0.125f * 1.4426950408889634f;
         int it = 0;
@@ -675,33 +685,44 @@ attention_tc_pair_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid
             const uint32_t ph = (it >> 1) & 1;
             mbar_wait_hot(bar(PB_S + wg), ph);
             tc_fence_after();
-            uint32_t v[2][32];
-            tmem_ld_32x32(trow + 64 * half, v[0]);
-            tmem_ld_32x32(trow + 64 * half + 32, v[1]);
-            tmem_ld_wait();
-            float mxa[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+            // my keys: PAIR - the 64 columns of my image; else all 128.  Valid: the first T of them, under the causal mask the first t + 1.
+            constexpr int NCH = PAIR ? 2 : 4;
+            const uint32_t tkeys = trow + (PAIR ? 64 * half : 0);
+            const int nvalid = g.causal ? min(t0 + 1, T) : T;
+            float sum = 0.f;
+            uint32_t pk[16 * NCH];
+            {
+                uint32_t v[NCH][32];
 #pragma unroll
-            for (int j = 0; j < 64; ++j) {
-                if (j >= T) v[j >> 5][j & 31] = 0xff800000u;   // keys beyond T (zero rows of the K tile)
-                mxa[j & 3] = fmaxf(mxa[j & 3], __uint_as_float(v[j >> 5][j & 31]));
-            }
-            const float m = fmaxf(fmaxf(mxa[0], mxa[1]), fmaxf(mxa[2], mxa[3])) * sl2;
-            const float2 nm2 = make_float2(-m, -m), sc2 = make_float2(sl2, sl2);
-            float2 sum2 = make_float2(0.f, 0.f);
-            uint32_t pk[32];
+                for (int c = 0; c < NCH; ++c) tmem_ld_32x32(tkeys + 32 * c, v[c]);
+                tmem_ld_wait();
+                float mxa[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-            for (int j = 0; j < 64; j += 2) {
-                const float2 x = __ffma2_rn(make_float2(__uint_as_float(v[j >> 5][j & 31]), __uint_as_float(v[j >> 5][(j & 31) + 1])), sc2, nm2);
-                const float2 e = make_float2(ex2f(x.x), ex2f(x.y));
-                sum2 = __fadd2_rn(sum2, e);
-                pk[j >> 1] = pack_bf16x2(e.x, e.y);
+                for (int j = 0; j < 32 * NCH; ++j) {
+                    if (j >= nvalid) v[j >> 5][j & 31] = 0xff800000u;   // keys beyond T (zero rows of the K tile) / above the diagonal
+                    mxa[j & 3] = fmaxf(mxa[j & 3], __uint_as_float(v[j >> 5][j & 31]));
+                }
+                const float m = fmaxf(fmaxf(mxa[0], mxa[1]), fmaxf(mxa[2], mxa[3])) * sl2;
+                const float2 nm2 = make_float2(-m, -m), sc2 = make_float2(sl2, sl2);
+                float2 sum2 = make_float2(0.f, 0.f);
+#pragma unroll
+                for (int j = 0; j < 32 * NCH; j += 2) {
+                    const float2 x = __ffma2_rn(make_float2(__uint_as_float(v[j >> 5][j & 31]), __uint_as_float(v[j >> 5][(j & 31) + 1])), sc2, nm2);
+                    const float2 e = make_float2(ex2f(x.x), ex2f(x.y));
+                    sum2 = __fadd2_rn(sum2, e);
+                    pk[j >> 1] = pack_bf16x2(e.x, e.y);
+                }
+                sum = sum2.x + sum2.y;
             }
-            {   // P: keys 0 .. 63 in packed columns 0 .. 31, keys 64 .. 127 in 32 .. 63; the other image's half is zero
+            if constexpr (PAIR) {   // P: keys 0 .. 63 in packed columns 0 .. 31, keys 64 .. 127 in 32 .. 63; the other image's half is zero
                 uint32_t z[32];
 #pragma unroll
                 for (int j = 0; j < 32; ++j) z[j] = 0u;
-                tmem_st_32x32(trow + 32 * half, pk);
+                tmem_st_32x32(trow + 32 * half, *reinterpret_cast<uint32_t (*)[32]>(&pk[0]));
                 tmem_st_32x32(trow + 32 * (1 - half), z);
+            } else {
+                tmem_st_32x32(trow, *reinterpret_cast<uint32_t (*)[32]>(&pk[0]));
+                tmem_st_32x32(trow + 32, *reinterpret_cast<uint32_t (*)[32]>(&pk[32]));
             }
             tmem_st_wait();
             tc_fence_before();
@@ -717,7 +738,7 @@ attention_tc_pair_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar(PB_TFREE + wg));      // S / P / O of this item are in registers: the slot may take item + 2
-            const float inv = 1.0f / (sum2.x + sum2.y);
+            const float inv = 1.0f / sum;
             const float2 inv2 = make_float2(inv, inv);
             uint8_t* stage = smem + stg * TP_STAGE_BYTES + r * 128;         // my row of the (dead) Q tile
             if (t < T) {
@@ -737,7 +758,8 @@ attention_tc_pair_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid
             __syncwarp();
             if (lane == 0) {
                 // 32-row slab of image 2 pair + half; tokens >= T and an image beyond the batch are clipped by the TMA unit
-                tma_store_3d(&tm_out, sbase + stg * TP_STAGE_BYTES + wq * 32 * 128, head * DH, (wq & 1) * 32, 2 * pair + half);
+                tma_store_3d(&tm_out, sbase + stg * TP_STAGE_BYTES + wq * 32 * 128, head * DH, PAIR ? (wq & 1) * 32 : wq * 32,
+                             PAIR ? 2 * pair + half : pair);
                 bulk_commit_group();
                 bulk_wait_group_read<0>();
                 mbar_arrive(bar(PB_FREE + stg));
@@ -833,12 +855,15 @@ int attention_tc_launch(const void* qkv_bf16, int n_images, int tokens, int head
     return CLIPPPO_OK;
 }
 
-bool attention_tc_pair_supported(int tokens, bool causal) { return !causal && tokens >= 16 && tokens <= 64; }
+bool attention_tc_pair_supported(int tokens, bool causal) {
+    return tokens >= 16 && (causal ? tokens <= TILE : tokens <= 64);      // 64 < T <= 128 without a mask: attention_tc_kernel
+}
 
-// T <= 64 (ViT-B/32: T = 50): two images per 128-row tensor-core tile
-int attention_tc_pair_launch(const void* qkv_bf16, int n_images, int tokens, int heads, void* out_bf16, cudaStream_t stream) {
-    if (!attention_tc_pair_supported(tokens, false)) return CLIPPPO_ERR_UNSUPPORTED;
-    const long long items = static_cast<long long>((n_images + 1) / 2) * heads;
+// T <= 64 (ViT-B/32: T = 50): two images per 128-row tensor-core tile.  64 < T <= 128 causal (text tower: T = 77): one sequence per tile.
+int attention_tc_pair_launch(const void* qkv_bf16, int n_images, int tokens, int heads, void* out_bf16, cudaStream_t stream, bool causal) {
+    if (!attention_tc_pair_supported(tokens, causal)) return CLIPPPO_ERR_UNSUPPORTED;
+    const bool pair = tokens <= 64;
+    const long long items = static_cast<long long>(pair ? (n_images + 1) / 2 : n_images) * heads;
     if (items > 0x7fffffffLL) return CLIPPPO_ERR_BAD_SHAPE;
     const int D = heads * DH;
     CUtensorMap ti, to;
@@ -847,13 +872,15 @@ int attention_tc_pair_launch(const void* qkv_bf16, int n_images, int tokens, int
     if (st) return st;
     static DeviceOnce configured;
     if (configured.first_use()) {
-        CLIPPPO_CUDA_TRY(cudaFuncSetAttribute(attention_tc_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TP_SMEM_BYTES));
+        CLIPPPO_CUDA_TRY(cudaFuncSetAttribute(attention_tc_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TP_SMEM_BYTES));
+        CLIPPPO_CUDA_TRY(cudaFuncSetAttribute(attention_tc_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TP_SMEM_BYTES));
     }
     static const uint32_t v_lbo = env_u32("CLIPPPO_ATC_V_LBO", 64), v_sbo = env_u32("CLIPPPO_ATC_V_SBO", 64),
                           p_cols = env_u32("CLIPPPO_ATC_P_COLS", 8);
-    TpArgs g{static_cast<int>(items), tokens, heads, v_lbo, v_sbo, p_cols};
+    TpArgs g{static_cast<int>(items), tokens, heads, causal ? 1 : 0, v_lbo, v_sbo, p_cols};
     const int grid = static_cast<int>(items < kNumSMs ? items : kNumSMs);
-    CLIPPPO_CUDA_TRY(launch_pdl(attention_tc_pair_kernel, grid, TP_THREADS, TP_SMEM_BYTES, stream, 1, ti, to, g));
+    if (pair) CLIPPPO_CUDA_TRY(launch_pdl(attention_tc_pair_kernel<true>, grid, TP_THREADS, TP_SMEM_BYTES, stream, 1, ti, to, g));
+    else CLIPPPO_CUDA_TRY(launch_pdl(attention_tc_pair_kernel<false>, grid, TP_THREADS, TP_SMEM_BYTES, stream, 1, ti, to, g));
     return CLIPPPO_OK;
 }
 

@@ -35,8 +35,9 @@ int attention_launch(const void* qkv_bf16, int n_images, int tokens, int heads, 
 // tcgen05 / TMEM / TMA attention for 64 < T <= 257, no mask (attention_tc.cu)
 bool attention_tc_supported(int tokens, bool causal);
 int attention_tc_launch(const void* qkv_bf16, int n_images, int tokens, int heads, void* out_bf16, cudaStream_t stream);
-// the same machinery for T <= 64, two images per 128-row tile (ViT-B/32: T = 50)
+// the same machinery for T <= 64, two images per 128-row tile (ViT-B/32: T = 50), and for causal T <= 128 (text tower: T = 77)
 bool attention_tc_pair_supported(int tokens, bool causal);
-int attention_tc_pair_launch(const void* qkv_bf16, int n_images, int tokens, int heads, void* out_bf16, cudaStream_t stream);
+int attention_tc_pair_launch(const void* qkv_bf16, int n_images, int tokens, int heads, void* out_bf16, cudaStream_t stream,
+                             bool causal = false);
 
 }  // namespace clipppo

@@ -8,6 +8,7 @@ from collections import defaultdict
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+os.environ.setdefault("CLIPPPO_ALLOW_RANDOM_WEIGHTS", "1")
 import torch
 from torch.profiler import ProfilerActivity, profile
 
