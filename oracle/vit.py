@@ -7,7 +7,7 @@ functions over a state dict in openai key layout (``visual.conv1.weight`` ...), 
 reference-side preprocessing around it (``shared/clip_ppo_utils.py:141-164`` and
 ``:185-217``).
 
-Pinned by: ``tests/test_oracle.py::test_vit_matches_hf`` (transformers
+Pinned by: ``tests/test_oracle.py::test_vit_oracle_matches_hf_small`` (transformers
 CLIPVisionModelWithProjection with the same weights) and tests/golden/vit_*.npz.
 """
 from __future__ import annotations
