@@ -277,6 +277,47 @@ def test_attention_pair_kernel_vs_torch_and_vs_the_mma_sync_kernel(native, monke
     assert (out.float() - old.float()).abs().mean().item() <= 2e-3
 
 
+@pytest.mark.parametrize("kind,n,T,H", [("pair", 5, 50, 12), ("pair", 1, 50, 12), ("pair", 3, 17, 12), ("causal", 5, 77, 8), ("causal", 2, 128, 8),
+                                         ("long", 3, 257, 16)])
+def test_attention_kernels_write_nothing_outside_their_output(native, kind, n, T, H):
+    """The tcgen05 attention kernels store through TMA boxes that are larger than what they own (32-row slabs, a second image
+    that does not exist when n is odd): the TMA unit must clip them.  Guard rows around the output stay untouched."""
+    from clip_ppo_b200 import _native as Nn
+    D, G = H * 64, 40
+    gen = torch.Generator(device="cuda").manual_seed(n + T)
+    qkv = torch.randn(n * T, 3 * D, device="cuda", generator=gen).bfloat16()
+    buf = torch.full(((n * T + 2 * G), D), 7.5, device="cuda", dtype=torch.bfloat16)
+    out = buf[G:G + n * T]
+    fn = native.clipppo_attention_causal_bf16 if kind == "causal" else native.clipppo_attention_bf16
+    Nn.check(fn(qkv.data_ptr(), n, T, H, 64, out.data_ptr(), _stream()))
+    torch.cuda.synchronize()
+    assert (buf[:G] == 7.5).all() and (buf[G + n * T:] == 7.5).all()
+    assert torch.isfinite(out.float()).all() and not (out == 7.5).all(dim=1).any()       # every row was written
+
+
+@pytest.mark.parametrize("M,N,K", [(130, 768, 768), (50, 64, 64), (1000, 768, 3072), (257, 1024, 1024)])
+def test_gemm_resid_stats_writes_nothing_outside_its_rows(native, M, N, K):
+    """RESID_STATS loads and stores 32 x 64 boxes that overhang M: loads beyond M are zero-filled, stores clipped, and the partial
+    statistics are written for rows < M only."""
+    from clip_ppo_b200 import _native as Nn
+    gen = torch.Generator(device="cuda").manual_seed(M + N)
+    a = (torch.randn(M, K, device="cuda", generator=gen) * 0.5).bfloat16()
+    w = (torch.randn(N, K, device="cuda", generator=gen) * (K ** -0.5)).bfloat16()
+    bias = torch.randn(N, device="cuda", generator=gen) * 0.1
+    G, P = 200, (N + 127) // 128
+    xbuf = torch.full((M + G, N), 3.25, device="cuda", dtype=torch.bfloat16)
+    pbuf = torch.full((M + G, P, 2), -77.0, device="cuda")
+    x0 = torch.randn(M, N, device="cuda", generator=gen).bfloat16()
+    xbuf[:M] = x0
+    Nn.check(native.clipppo_gemm_bf16_resid_stats(a.data_ptr(), w.data_ptr(), M, N, K, bias.data_ptr(), xbuf.data_ptr(), N,
+                                                  pbuf.data_ptr(), _stream()))
+    torch.cuda.synchronize()
+    assert (xbuf[M:] == 3.25).all() and (pbuf[M:] == -77.0).all()
+    ref = (x0.float() + a.float() @ w.float().t() + bias)
+    assert (xbuf[:M].float() - ref).abs().max().item() <= 2 ** -6 * max(1.0, ref.abs().max().item())
+    assert (pbuf[:M] != -77.0).all()
+
+
 @pytest.mark.parametrize("n,T,H,skew", [(2, 257, 16, 1), (2, 257, 16, 2), (3, 200, 12, 1), (2, 129, 8, 2), (150, 257, 16, 0)])
 def test_attention_tc_running_shift(native, n, T, H, skew):
     """The tcgen05 kernel (64 < T <= 257) keeps ONE running softmax shift per row and only moves it when a later 32-key chunk
