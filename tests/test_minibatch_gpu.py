@@ -64,8 +64,9 @@ def _update(agent, r, mb, clip_embeddings, lam, detach_latents, gae_fn, cos_fn, 
     return out, clip_loss.detach(), {n: p.grad.detach().clone() for n, p in agent.named_parameters() if p.grad is not None}
 
 
+@pytest.mark.parametrize("native_encoder", [False, True], ids=["torch-encoder", "native-encoder"])
 @pytest.mark.parametrize("detach_latents", [True, False])
-def test_minibatch_update_matches_the_script_on_cpu(native, detach_latents):
+def test_minibatch_update_matches_the_script_on_cpu(native, detach_latents, native_encoder):
     import shared.clip_ppo_utils as U
     from clip_ppo_b200 import rollout
     T, E, mbsz = 8, 6, 24
@@ -83,13 +84,17 @@ def test_minibatch_update_matches_the_script_on_cpu(native, detach_latents):
 
     # ---- GPU: this repository ----
     tf32 = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
-    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False     # the agent itself is stock PyTorch
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False     # the stock-PyTorch agent (and the heads) in true fp32
     try:
         model = U.load_clip_model("ViT-B/32", "cuda")          # seeded-random weights == ov.random_state_dict(VIT_B32, 0)
         rg = {k: v.cuda() for k, v in r.items()}
         emb_gpu = U.generate_clip_embeddings(U.AblationMode.NONE, model, "image", T * E, "cuda",
                                              images=rg["obs"].permute(0, 3, 1, 2).contiguous())
         agent_gpu = Agent(seed=5).cuda()
+        if native_encoder:                                      # the NatureCNN on csrc/policy.cu, same parameter names
+            from clip_ppo_b200.policy import NatureCNN
+            rollout.use_native_encoder(agent_gpu)
+            assert isinstance(agent_gpu.network, NatureCNN)
         ppo_gpu = lambda nlp, ent, nv, olp, a, R, V, cl, l: rollout.ppo_minibatch_loss(nlp, ent, nv, olp, a, R, V, cl, l)
         out_g, cl_g, g_g = _update(agent_gpu, rg, mb.cuda(), emb_gpu, lam, detach_latents, rollout.compute_gae,
                                    U.compute_cosine_embedding_loss, ppo_gpu)
