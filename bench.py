@@ -650,6 +650,18 @@ def secondary_measurements(args, dev, pk, disturb_rows):
     out = {}
     out["disturb_hbm"] = {"bytes_per_element": 12, "peak_gb_per_s": pk["hbm"], "peak_source": pk["source"], "rows": disturb_rows,
                           "when": "first thing in the run (kernel timed alone, 10 launches after 3 warm-ups each)"}
+    # (1b) BASELINE configs[1]: the learner side of one MiniGrid CLIP-PPO iteration (E = 64 envs x 128 steps, MODERATE)
+    mg = minigrid_iteration(dev)
+    mg_ref = minigrid_iteration(dev, impl="reference")
+    out["minigrid_iteration"] = {
+        "config": "BASELINE configs[1]: the learner side of one MiniGrid CLIP-PPO iteration (everything but the environment): E = 64 envs x "
+                  "T = 128 steps of 84x84x3 uint8 frames, MODERATE disturbances at every env step, uint8 rollout store, 8192 CLIP "
+                  "embeddings per iteration, 4 epochs x 4 minibatches of 2048 (policy forward + backward on csrc/policy.cu, fused GAE / "
+                  "PPO-loss / alignment-loss kernels, Adam); synthetic frames stand in for the renderer",
+        **mg,
+        "reference_eager_same_gpu": {**mg_ref, "what": "the script's own statements over the reference's modules (oracle/_ref) on this GPU: "
+                                     "torchvision disturbances, fp32 store, nn.Sequential encoder with two forwards per CLIP minibatch, "
+                                     "the 128-step GAE loop, the PPO-loss expressions with their .item() sync, fp16 eager tower"}}
     # (2) BASELINE configs[3]: Atari stacks (84x84 gray x 4, HARD), one GPU's share of 256 envs x 128 steps over 8 GPUs
     model = U.load_clip_model("ViT-B/32", device=dev)
     stacks = 4096
@@ -693,6 +705,144 @@ def secondary_measurements(args, dev, pk, disturb_rows):
         del x8, nz, zz, xs, model
         torch.cuda.empty_cache()
     return out
+
+
+class MiniGridAgent(torch.nn.Module):
+    """The reference's MiniGrid Agent (clip_ppo_minigrid.py:213-271) with its encoder on the native kernels."""
+
+    def __init__(self, n_actions: int = 7):
+        super().__init__()
+        from clip_ppo_b200.policy import NatureCNN
+        self.network = NatureCNN(3)
+        self.actor = torch.nn.Linear(512, n_actions)
+        self.critic = torch.nn.Linear(512, 1)
+
+    def _pre(self, x):                       # [B,H,W,C] 0..255 -> the NCHW view the encoder reads (the / 255 is folded into its first kernel)
+        return x.permute(0, 3, 1, 2)
+
+    def _get_features(self, x):
+        return self.network(x, in_scale=1.0 / 255.0)
+
+
+def minigrid_iteration(dev, E: int = 64, T: int = 128, epochs: int = 4, minibatches: int = 4, impl: str = "b200"):
+    """Everything of one CLIP-PPO iteration except the environment itself (out of scope), at BASELINE configs[1]'s shape:
+    T env steps of [disturb the E frames -> store -> policy forward], GAE, the iteration's CLIP embeddings (84 -> 224), epochs x
+    minibatches updates [policy forward, latents, PPO loss, alignment loss on every CLIP_LOSS_FREQUENCY-th minibatch, backward,
+    clip_grad_norm_, Adam] (clip_ppo_minigrid.py:378-410, 437-450, 459-470, 486-564).  Synthetic uint8 frames stand in for the renderer.
+      impl "b200"       this repository's drop-in calls: disturb_minigrid_obs (one launch, uint8 out), uint8 store, native NatureCNN,
+                        one encoder forward per minibatch, fused GAE / PPO-loss / cosine-loss kernels, the sm_100a tower;
+      impl "reference"  the script's own statements over the reference's own modules (oracle/_ref) on the same GPU: torchvision
+                        disturbances, fp32 store, nn.Sequential encoder (two forwards per minibatch), the GAE loop, the PPO-loss
+                        expressions with their .item() sync, fp16 eager tower."""
+    from torch.distributions.categorical import Categorical
+    torch.manual_seed(11)
+    g = torch.Generator(device=dev).manual_seed(12)
+    frames = torch.randint(0, 256, (T, E, 84, 84, 3), device=dev, generator=g, dtype=torch.uint8)
+    rewards = (torch.rand(T, E, device=dev, generator=g) < 0.05).float()
+    dones = (torch.rand(T, E, device=dev, generator=g) < 0.02).float()
+    N_ = T * E
+    mbsz = N_ // minibatches
+    if impl == "b200":
+        import shared.clip_ppo_utils as U
+        from shared.disturbances_gpu import DisturbanceWrapperGPU
+        from shared.disturbance_types import DisturbanceSeverity
+        from clip_ppo_b200 import rollout as R
+        model = U.load_clip_model("ViT-B/32", device=dev)
+        agent = MiniGridAgent().to(dev)
+        w = DisturbanceWrapperGPU(device=dev, seed=5, severity=DisturbanceSeverity.MODERATE)
+        store = R.ObsStoreU8(T, E, (84, 84, 3), device=dev)
+    else:
+        from oracle import build_ref, losses as ol, vit as ov
+        if not build_ref.available():
+            return {"unavailable": "oracle/_ref not staged"}
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        from eager_tower import EagerCLIP
+        ref = build_ref.load(EagerCLIP(ov.random_state_dict(ov.VIT_B32, 0), dev))
+        U, DG, DT = ref.clip_ppo_utils, ref.disturbances_gpu, ref.disturbance_types
+        model = U.load_clip_model("ViT-B/32", dev)
+        nn = torch.nn
+        agent = nn.Module()
+        agent.network = nn.Sequential(nn.Conv2d(3, 32, 8, stride=4), nn.ReLU(), nn.Conv2d(32, 64, 4, stride=2), nn.ReLU(),
+                                      nn.Conv2d(64, 64, 3, stride=1), nn.ReLU(), nn.Flatten(), nn.Linear(64 * 7 * 7, 512), nn.ReLU())
+        agent.actor, agent.critic = nn.Linear(512, 7), nn.Linear(512, 1)
+        agent = agent.to(dev)
+        w = DG.DisturbanceWrapperGPU(device=dev, seed=5, severity=DT.DisturbanceSeverity.MODERATE)
+        store = torch.zeros((T, E, 84, 84, 3), device=dev)                                       # clip_ppo_minigrid.py:346
+        hidden = lambda x: agent.network(x.permute(0, 3, 1, 2) / 255.0)                          # :258-262
+    opt = torch.optim.Adam(agent.parameters(), lr=2.5e-4, eps=1e-5)
+    lam = U.get_clip_lambda_with_warmup(1e-5, 8, 16)
+
+    def iteration():
+        values = torch.empty(T, E, device=dev)
+        logprobs = torch.empty(T, E, device=dev)
+        actions = torch.empty(T, E, device=dev, dtype=torch.long)
+        for t in range(T):
+            if impl == "b200":
+                d = R.disturb_minigrid_obs(w, frames[t])                                         # clip_ppo_minigrid.py:381-388, one launch
+                store[t] = d
+                with torch.no_grad():
+                    a, lp, _, v, _ = R.action_value_and_latents(agent, d.float(), None)          # :395-399
+            else:
+                x = frames[t].float() / 255.0                                                    # :383-388, as written
+                x = w.apply_disturbances(x.permute(0, 3, 1, 2)).permute(0, 2, 3, 1)
+                d = (x * 255).byte().float()
+                store[t] = d
+                with torch.no_grad():
+                    h = hidden(d)
+                    probs = Categorical(logits=agent.actor(h))
+                    a = probs.sample()
+                    lp, v = probs.log_prob(a), agent.critic(h)
+            values[t], logprobs[t], actions[t] = v.flatten(), lp, a
+        with torch.no_grad():
+            if impl == "b200":
+                next_value = agent.critic(agent._get_features(agent._pre(frames[0].float()))).reshape(1, -1)
+                adv, ret = R.compute_gae(rewards, values, dones, next_value, dones[0], 0.99, 0.95)   # :437-450, one launch
+                emb = U.generate_clip_embeddings(U.AblationMode.NONE, model, "image", N_, dev,
+                                                 images=store.clip_images(torch.arange(N_, device=dev)))   # :459-470
+            else:
+                next_value = agent.critic(hidden(frames[0].float())).reshape(1, -1)
+                adv, ret = ol.gae(rewards, values, dones, next_value, dones[0], 0.99, 0.95)          # the script's T-step loop
+                b_obs = store.reshape((-1, 84, 84, 3))
+                emb = torch.cat([U.generate_clip_embeddings(U.AblationMode.NONE, model, "image", 2048, dev,
+                                                            images=b_obs[i:i + 2048].permute(0, 3, 1, 2))
+                                 for i in range(0, N_, 2048)])       # in minibatch-sized pieces: the stock path materialises fp32 224x224 frames
+        b_lp, b_adv, b_ret, b_val, b_act = logprobs.reshape(-1), adv.reshape(-1), ret.reshape(-1), values.reshape(-1), actions.reshape(-1)
+        counter = 0
+        loss = None
+        for _ in range(epochs):
+            perm = torch.randperm(N_, device=dev)
+            for i in range(minibatches):
+                mb = perm[i * mbsz:(i + 1) * mbsz]
+                do_clip = counter % U.CLIP_LOSS_FREQUENCY == 0
+                if impl == "b200":
+                    _, nlp, ent, nv, lat = R.action_value_and_latents(agent, store.policy_input(mb), b_act[mb])     # :498, :534 in one forward
+                    cl = U.compute_cosine_embedding_loss(lat, emb[mb]) if do_clip else None
+                    out = R.ppo_minibatch_loss(nlp, ent, nv.flatten(), b_lp[mb], b_adv[mb], b_ret[mb], b_val[mb], cl, lam)
+                else:
+                    obs_mb = store.reshape((-1, 84, 84, 3))[mb]
+                    h = hidden(obs_mb)                                                               # :498 get_action_and_value
+                    probs = Categorical(logits=agent.actor(h))
+                    nlp, ent, nv = probs.log_prob(b_act[mb]), probs.entropy(), agent.critic(h)
+                    cl = 0.0
+                    if do_clip:
+                        lat = hidden(obs_mb).detach()                                                # :534 get_latent_representation: a second forward
+                        cl = U.compute_cosine_embedding_loss(lat, emb[mb])
+                    out = ol.ppo_loss(nlp, ent, nv, b_lp[mb], b_adv[mb], b_ret[mb], b_val[mb], cl, lam)
+                    out["clipfrac"].item()                                                           # :505: the script's host sync
+                opt.zero_grad(set_to_none=True)
+                out["loss"].backward()
+                torch.nn.utils.clip_grad_norm_(agent.parameters(), 0.5)
+                opt.step()
+                counter += 1
+                loss = out["loss"]
+        return loss
+
+    iteration()
+    ms = event_ms(iteration, 2, warm=0)
+    res = {"ms_per_iteration": round(ms, 2), "env_frames_per_s": round(N_ / (ms * 1e-3), 1)}
+    del model, agent, frames, store
+    torch.cuda.empty_cache()
+    return res
 
 
 def eager_gpu_baseline(args, dev):

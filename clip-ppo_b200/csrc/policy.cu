@@ -89,7 +89,11 @@ template <int BN, int EPI, int GATHER, int RM = 8>
 __global__ void __launch_bounds__(256)
 sgemm_nt_kernel(const float* __restrict__ A, const __grid_constant__ Gather ga, const float* __restrict__ B, float* __restrict__ Cm,
                 const __grid_constant__ RowOut ro, long long M, int N, int K, float a_scale, const float* __restrict__ bias,
-                const float* __restrict__ mask) {
+                const float* __restrict__ mask, int ksteps = 0, float* __restrict__ part = nullptr) {
+    // ksteps > 0: the K loop is cut into canonical chunks of `ksteps` 16-wide k-steps whose sums are added in index order - the
+    // SAME arithmetic whether one CTA walks all chunks (part == null: large batches) or blockIdx.z owns one chunk and writes its
+    // raw partial tile to part[z][M][N] for splitk_finish_kernel to add (few output tiles: the env-step batches of the rollout,
+    // where the K = 3136 loop of 8 CTAs would be the whole latency).  A row's result is bitwise independent of the batch size.
     // 256 threads as TY x TX; a thread owns RM rows (groups of 4) x 4 consecutive columns:
     //   BN = 64: 16 x 16 threads, 128 x 64 tile (RM = 8) or 64 x 64 (RM = 4, small M: twice the CTAs);   BN = 32: 32 x 8 threads, 256 x 32 tile
     constexpr int TX = BN / 4, TY = 256 / TX, BM = TY * RM, BK = 16, HALF = BM / 2;
@@ -155,11 +159,20 @@ sgemm_nt_kernel(const float* __restrict__ A, const __grid_constant__ Gather ga, 
         }
         if (b_row < BN) { sb[buf][b_k4 + 0][b_row] = rb.x; sb[buf][b_k4 + 1][b_row] = rb.y; sb[buf][b_k4 + 2][b_row] = rb.z; sb[buf][b_k4 + 3][b_row] = rb.w; }
     };
-    const int nk = K / BK;
-    load_tiles(0);
-    store_tiles(0);
+    const int nk_all = K / BK;
+    const bool split = ksteps > 0 && part != nullptr;
+    const int kb0 = split ? static_cast<int>(blockIdx.z) * ksteps : 0;
+    const int nk = split ? min(nk_all, kb0 + ksteps) : nk_all;
+    float tot[RM][4];                                                  // chunk sums so far (chunked, unsplit walk only)
+#pragma unroll
+    for (int i = 0; i < RM; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) tot[i][j] = 0.f;
+    int left = ksteps;                                                 // k-steps left in the current chunk
+    load_tiles(kb0 * BK);
+    store_tiles(kb0 & 1);
     __syncthreads();
-    for (int kb = 0; kb < nk; ++kb) {
+    for (int kb = kb0; kb < nk; ++kb) {
         const int buf = kb & 1;
         if (kb + 1 < nk) load_tiles((kb + 1) * BK);                    // global loads in flight under the FMAs
 #pragma unroll
@@ -175,8 +188,32 @@ sgemm_nt_kernel(const float* __restrict__ A, const __grid_constant__ Gather ga, 
 #pragma unroll
                 for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
         }
+        if (ksteps > 0 && !split && (--left == 0 || kb + 1 == nk)) {  // chunk boundary: fold the chunk's sum in, start the next one at zero
+#pragma unroll
+            for (int i = 0; i < RM; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { tot[i][j] += acc[i][j]; acc[i][j] = 0.f; }
+            left = ksteps;
+        }
         if (kb + 1 < nk) store_tiles(buf ^ 1);
         __syncthreads();
+    }
+    if (ksteps > 0 && !split) {
+#pragma unroll
+        for (int i = 0; i < RM; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j] = tot[i][j];
+    }
+    if (split) {
+#pragma unroll
+        for (int i = 0; i < RM; ++i) {
+            const long long m = m0 + (i < 4 ? ty * 4 + i : HALF + ty * 4 + (i - 4));
+            const int n = n0 + tx * 4;
+            if (m < M && n < N)
+                *reinterpret_cast<float4*>(part + (static_cast<long long>(blockIdx.z) * M + m) * N + n) =
+                    make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+        }
+        return;
     }
 #pragma unroll
     for (int i = 0; i < RM; ++i) {
@@ -337,18 +374,79 @@ inline unsigned grid_for(long long n) {
     return static_cast<unsigned>(b < 148 * 16 ? (b > 0 ? b : 1) : 148 * 16);
 }
 
+// C = epi(a_scale * sum_z part[z]) for the split-K launches of sgemm_nt_kernel: splits added in index order (deterministic)
+template <int EPI, int GATHER>
+__global__ void __launch_bounds__(256)
+splitk_finish_kernel(const float* __restrict__ part, int splits, float* __restrict__ Cm, const __grid_constant__ RowOut ro,
+                     long long M, int N, float a_scale, const float* __restrict__ bias, const float* __restrict__ mask) {
+    const long long q = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;      // float4 index into [M, N]
+    const int n4 = N / 4;
+    if (q >= M * n4) return;
+    const long long m = q / n4;
+    const int n = static_cast<int>(q - m * n4) * 4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int z = 0; z < splits; ++z) {
+        const float4 pz = __ldg(reinterpret_cast<const float4*>(part + (static_cast<long long>(z) * M + m) * N + n));
+        v.x += pz.x; v.y += pz.y; v.z += pz.z; v.w += pz.w;
+    }
+    v = make_float4(v.x * a_scale, v.y * a_scale, v.z * a_scale, v.w * a_scale);
+    long long obase = m * N;
+    if (GATHER) {
+        const long long per = static_cast<long long>(ro.NI) * ro.NJ;
+        const long long img = m / per;
+        const int rem = static_cast<int>(m - img * per);
+        const int oi = rem / ro.NJ, oj = rem - oi * ro.NJ;
+        obase = ro.base + img * ro.sn + static_cast<long long>(oi) * ro.si + static_cast<long long>(oj) * ro.sj;
+    }
+    if (EPI == EPI_BIAS_RELU) {
+        const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + n));
+        v = make_float4(fmaxf(v.x + bb.x, 0.f), fmaxf(v.y + bb.y, 0.f), fmaxf(v.z + bb.z, 0.f), fmaxf(v.w + bb.w, 0.f));
+    }
+    if (EPI == EPI_MASK) {
+        const float4 mk = __ldg(reinterpret_cast<const float4*>(mask + obase + n));
+        v = make_float4(mk.x > 0.f ? v.x : 0.f, mk.y > 0.f ? v.y : 0.f, mk.z > 0.f ? v.z : 0.f, mk.w > 0.f ? v.w : 0.f);
+    }
+    *reinterpret_cast<float4*>(Cm + obase + n) = v;
+}
+
+// Canonical chunk length (k-steps) of a forward GEMM with `nk` k-steps: a function of K only, so that every batch size adds
+// the same chunk sums in the same order.  `*split` = launch one CTA per (tile, chunk): when the tiles alone leave most of the
+// part idle and the partial tiles fit the buffer.
+int plan_ksteps(long long ctas, int nk, long long M, int N, size_t part_floats, bool* split) {
+    *split = false;
+    if (nk < 8) return 0;
+    const int ksteps = max(4, (nk + 27) / 28);
+    const int splits = (nk + ksteps - 1) / ksteps;
+    *split = ctas < 148 && static_cast<size_t>(splits) * static_cast<size_t>(M) * N <= part_floats;
+    return ksteps;
+}
+
 const Gather kNoGather = {};
 const RowOut kNoRowOut = {};
 
 // C = epi(a_scale * A B^T) with a plain row-major A [M, K]
 template <int EPI>
-int launch_nt_plain(const float* A, const float* B, float* Cm, long long M, int N, int K, const float* bias, const float* mask, cudaStream_t st) {
+int launch_nt_plain(const float* A, const float* B, float* Cm, long long M, int N, int K, const float* bias, const float* mask, cudaStream_t st,
+                    float* part = nullptr, size_t part_floats = 0) {
     if (M * ((N + 63) / 64) <= 128LL * 148 * 2) {                     // few row tiles (the FC layer): 64-row tiles, twice the CTAs
         dim3 grid(static_cast<unsigned>((M + 63) / 64), (N + 63) / 64);
-        sgemm_nt_kernel<64, EPI, 0, 4><<<grid, 256, 0, st>>>(A, kNoGather, B, Cm, kNoRowOut, M, N, K, 1.0f, bias, mask);
+        bool split = false;
+        const int ksteps = part ? plan_ksteps(static_cast<long long>(grid.x) * grid.y, K / 16, M, N, part_floats, &split) : 0;
+        if (split) {                                                  // an env-step batch: the K = 3136 loop of 8 CTAs would be the whole latency
+            const int splits = (K / 16 + ksteps - 1) / ksteps;
+            grid.z = splits;
+            sgemm_nt_kernel<64, EPI, 0, 4><<<grid, 256, 0, st>>>(A, kNoGather, B, Cm, kNoRowOut, M, N, K, 1.0f, bias, mask, ksteps, part);
+            CLIPPPO_CHECK_LAUNCH();
+            splitk_finish_kernel<EPI, 0><<<static_cast<unsigned>((M * (N / 4) + 255) / 256), 256, 0, st>>>(part, splits, Cm, kNoRowOut, M, N, 1.0f, bias, mask);
+            CLIPPPO_CHECK_LAUNCH();
+            return CLIPPPO_OK;
+        }
+        sgemm_nt_kernel<64, EPI, 0, 4><<<grid, 256, 0, st>>>(A, kNoGather, B, Cm, kNoRowOut, M, N, K, 1.0f, bias, mask, ksteps, nullptr);
     } else {
         dim3 grid(static_cast<unsigned>((M + 127) / 128), (N + 63) / 64);
-        sgemm_nt_kernel<64, EPI, 0><<<grid, 256, 0, st>>>(A, kNoGather, B, Cm, kNoRowOut, M, N, K, 1.0f, bias, mask);
+        bool split = false;
+        const int ksteps = part ? plan_ksteps(1 << 20, K / 16, M, N, part_floats, &split) : 0;      // same chunks, never split
+        sgemm_nt_kernel<64, EPI, 0><<<grid, 256, 0, st>>>(A, kNoGather, B, Cm, kNoRowOut, M, N, K, 1.0f, bias, mask, ksteps, nullptr);
     }
     CLIPPPO_CHECK_LAUNCH();
     return CLIPPPO_OK;
@@ -356,7 +454,24 @@ int launch_nt_plain(const float* A, const float* B, float* Cm, long long M, int 
 // the same with A gathered through `ga` and the output rows placed through `ro`
 template <int EPI>
 int launch_nt_gather(const float* A, const Gather& ga, const float* B, float* Cm, const RowOut& ro, long long M, int N, int K,
-                     float a_scale, const float* bias, const float* mask, cudaStream_t st) {
+                     float a_scale, const float* bias, const float* mask, cudaStream_t st, float* part = nullptr, size_t part_floats = 0) {
+    if (part && N > 32) {
+        dim3 grid(static_cast<unsigned>((M + 127) / 128), (N + 63) / 64);
+        bool split = false;
+        const int ksteps = plan_ksteps(static_cast<long long>(grid.x) * grid.y, K / 16, M, N, part_floats, &split);
+        if (split) {
+            const int splits = (K / 16 + ksteps - 1) / ksteps;
+            grid.z = splits;
+            sgemm_nt_kernel<64, EPI, 1><<<grid, 256, 0, st>>>(A, ga, B, Cm, ro, M, N, K, a_scale, bias, mask, ksteps, part);
+            CLIPPPO_CHECK_LAUNCH();
+            splitk_finish_kernel<EPI, 1><<<static_cast<unsigned>((M * (N / 4) + 255) / 256), 256, 0, st>>>(part, splits, Cm, ro, M, N, a_scale, bias, mask);
+            CLIPPPO_CHECK_LAUNCH();
+            return CLIPPPO_OK;
+        }
+        sgemm_nt_kernel<64, EPI, 1><<<grid, 256, 0, st>>>(A, ga, B, Cm, ro, M, N, K, a_scale, bias, mask, ksteps, nullptr);   // same chunks, one CTA per tile
+        CLIPPPO_CHECK_LAUNCH();
+        return CLIPPPO_OK;
+    }
     if (N <= 32) {
         dim3 grid(static_cast<unsigned>((M + 255) / 256), 1);          // 256 x 32 tiles
         sgemm_nt_kernel<32, EPI, 1><<<grid, 256, 0, st>>>(A, ga, B, Cm, ro, M, N, K, a_scale, bias, mask);
@@ -538,9 +653,11 @@ extern "C" int clipppo_nature_forward(const float* obs, const int64_t obs_stride
     CLIPPPO_CHECK_LAUNCH();
     const RowOut r1{20, 20, 400LL * 32, 20 * 32, 32, 0}, r2{9, 9, 81LL * 64, 9 * 64, 64, 0}, r3{7, 7, 49LL * 64, 7 * 64, 64, 0};
     POL_TRY(launch_nt_gather<EPI_BIAS_RELU>(obs, g1, w1k, ws + p.act1, r1, p.M1, 32, p.K1, in_scale, b1, nullptr, st));
-    POL_TRY(launch_nt_gather<EPI_BIAS_RELU>(ws + p.act1, g2, ws + p.w2p, ws + p.act2, r2, p.M2, 64, p.K2, 1.0f, b2, nullptr, st));
-    POL_TRY(launch_nt_gather<EPI_BIAS_RELU>(ws + p.act2, g3, ws + p.w3p, ws + p.act3, r3, p.M3, 64, p.K3, 1.0f, b3, nullptr, st));
-    POL_TRY(launch_nt_plain<EPI_BIAS_RELU>(ws + p.act3, ws + p.wfp, hidden, mb, 512, p.KF, bfc, nullptr, st));
+    // env-step batches (tens of frames): conv2 / conv3 / FC are a handful of output tiles with a long K loop - split over K
+    // (partial sums in the backward's partial buffer, added in index order)
+    POL_TRY(launch_nt_gather<EPI_BIAS_RELU>(ws + p.act1, g2, ws + p.w2p, ws + p.act2, r2, p.M2, 64, p.K2, 1.0f, b2, nullptr, st, ws + p.part, kPartFloats));
+    POL_TRY(launch_nt_gather<EPI_BIAS_RELU>(ws + p.act2, g3, ws + p.w3p, ws + p.act3, r3, p.M3, 64, p.K3, 1.0f, b3, nullptr, st, ws + p.part, kPartFloats));
+    POL_TRY(launch_nt_plain<EPI_BIAS_RELU>(ws + p.act3, ws + p.wfp, hidden, mb, 512, p.KF, bfc, nullptr, st, ws + p.part, kPartFloats));
     return CLIPPPO_OK;
 }
 

@@ -42,7 +42,8 @@ def _native_activations(hidden, mb):
     return a1, a2, a3
 
 
-@pytest.mark.parametrize("mb,C,layout", [(256, 3, "nhwc"), (37, 4, "nchw"), (2048, 3, "nhwc"), (300, 4, "nchw"), (33, 3, "nchw")])
+@pytest.mark.parametrize("mb,C,layout", [(256, 3, "nhwc"), (37, 4, "nchw"), (2048, 3, "nhwc"), (300, 4, "nchw"), (33, 3, "nchw"),
+                                         (8, 3, "nhwc"), (64, 3, "nhwc"), (64, 4, "nchw"), (1, 3, "nchw")])      # env-step batches: split-K forward
 def test_nature_cnn_forward_backward_vs_torch(native, mb, C, layout):
     """Outputs and all eight gradients against torch.nn in fp32.  A ReLU whose pre-activation sits within rounding noise of zero
     is open in one fp32 implementation and closed in the other; the gradients then differ by that unit's whole contribution
@@ -91,6 +92,13 @@ def test_nature_cnn_is_deterministic_and_batch_invariant(native):
     a, b = net(x), net(x)
     assert torch.equal(a, b)
     assert torch.equal(net(x[:32]), a[:32])             # a row's features do not depend on the rest of the minibatch
+    # ... nor on whether the batch is small enough for the split-K forward (env-step batches) or not (minibatches): both add
+    # the same canonical K chunks in the same order
+    big = torch.rand(1500, 3, 84, 84, device="cuda")
+    big[100:164] = x[:64]
+    with torch.no_grad():
+        assert torch.equal(net(big)[100:164], net(x[:64]))
+        assert torch.equal(net(big[:600])[100:164], net(x[:64]))
     a.sum().backward()
     g1 = [p.grad.clone() for p in net.parameters()]
     net.zero_grad()
