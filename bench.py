@@ -245,6 +245,8 @@ def workload_config(args, per_gpu_batch, note=None):
            "parallelism": f"dp{args.gpus} by observation, frozen tower replicated, PPO-agent gradient all-reduce only"}
     if note:
         cfg["note"] = note
+        # the reference arm runs the reference's own call sequence
+        cfg["api"] = "apply_disturbances -> `* 255` -> generate_clip_embeddings(images=) -> compute_cosine_embedding_loss (the reference's own functions)"
     return cfg
 
 
