@@ -732,7 +732,8 @@ def minigrid_iteration(dev, E: int = 64, T: int = 128, epochs: int = 4, minibatc
     minibatches updates [policy forward, latents, PPO loss, alignment loss on every CLIP_LOSS_FREQUENCY-th minibatch, backward,
     clip_grad_norm_, Adam] (clip_ppo_minigrid.py:378-410, 437-450, 459-470, 486-564).  Synthetic uint8 frames stand in for the renderer.
       impl "b200"       this repository's drop-in calls: disturb_minigrid_obs (one launch, uint8 out), uint8 store, native NatureCNN,
-                        one encoder forward per minibatch, fused GAE / PPO-loss / cosine-loss kernels, the sm_100a tower;
+                        the env step's policy forward as a CUDA-graph replay (rollout.PolicyStepGraph), one encoder forward per
+                        minibatch, fused GAE / PPO-loss / cosine-loss kernels, the sm_100a tower;
       impl "reference"  the script's own statements over the reference's own modules (oracle/_ref) on the same GPU: torchvision
                         disturbances, fp32 store, nn.Sequential encoder (two forwards per minibatch), the GAE loop, the PPO-loss
                         expressions with their .item() sync, fp16 eager tower."""
@@ -774,6 +775,8 @@ def minigrid_iteration(dev, E: int = 64, T: int = 128, epochs: int = 4, minibatc
     opt = torch.optim.Adam(agent.parameters(), lr=2.5e-4, eps=1e-5)
     lam = U.get_clip_lambda_with_warmup(1e-5, 8, 16)
 
+    policy_step = R.PolicyStepGraph(agent, frames[0]) if impl == "b200" else None      # one graph launch per env step
+
     def iteration():
         values = torch.empty(T, E, device=dev)
         logprobs = torch.empty(T, E, device=dev)
@@ -782,8 +785,7 @@ def minigrid_iteration(dev, E: int = 64, T: int = 128, epochs: int = 4, minibatc
             if impl == "b200":
                 d = R.disturb_minigrid_obs(w, frames[t])                                         # clip_ppo_minigrid.py:381-388, one launch
                 store[t] = d
-                with torch.no_grad():
-                    a, lp, _, v, _ = R.action_value_and_latents(agent, d.float(), None)          # :395-399
+                a, lp, _, v = policy_step(d)                                                     # :395-399, graph replay
             else:
                 x = frames[t].float() / 255.0                                                    # :383-388, as written
                 x = w.apply_disturbances(x.permute(0, 3, 1, 2)).permute(0, 2, 3, 1)

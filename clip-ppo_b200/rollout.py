@@ -114,6 +114,48 @@ def action_value_and_latents(agent, obs: torch.Tensor, action: torch.Tensor):
     return action, probs.log_prob(action), probs.entropy(), agent.critic(hidden), hidden.detach()
 
 
+class PolicyStepGraph:
+    """The policy forward of one env step - ``agent.get_action_and_value(next_obs)`` under ``torch.no_grad()``
+    (clip_ppo_minigrid.py:395-399, clip_ppo_atari.py:590-594) - captured once as a CUDA graph and replayed.
+
+    At env-step batches (E = 8 ... 256 frames) the encoder is ~0.1 ms of device time while the ~25 small launches of the
+    heads, ``Categorical`` and the sampling cost ~0.5 ms of host time per step; a replay is one launch.  The agent's
+    parameters are read at replay time (optimizers update them in place), sampling draws from the device generator through
+    torch's graph-safe Philox offsets, so every replay samples fresh actions.  Returns ``(action, logprob, entropy, value)``
+    as views of the graph's static outputs: valid until the next call - copy what must survive (``actions[step] = action``
+    does).  ``obs`` must keep the shape / dtype of the example."""
+
+    def __init__(self, agent, example_obs: torch.Tensor):
+        self.agent = agent
+        self.static_obs = torch.empty_like(example_obs)
+        self.static_obs.copy_(example_obs)
+        dev = example_obs.device
+        cur = torch.cuda.current_stream(dev)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side), torch.no_grad():          # warm-up outside capture (lazy kernel attributes, cuBLAS handles)
+            for _ in range(2):
+                self._forward()
+        cur.wait_stream(side)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph), torch.no_grad():
+            self.out = self._forward()
+
+    def _forward(self):
+        # the statements of Agent.get_action_and_value; argument validation off: its `.all()` is a host sync, illegal in a capture
+        from torch.distributions.categorical import Categorical
+        agent = self.agent
+        hidden = agent._get_features(agent._pre(self.static_obs.float()))
+        probs = Categorical(logits=agent.actor(hidden), validate_args=False)
+        action = probs.sample()
+        return action, probs.log_prob(action), probs.entropy(), agent.critic(hidden)
+
+    def __call__(self, obs: torch.Tensor):
+        self.static_obs.copy_(obs)
+        self.graph.replay()
+        return self.out
+
+
 # ---- §8f-1: the PPO encoder on the native kernels ----------------------------------------------------
 def use_native_encoder(agent):
     """Swap the scripts' ``agent.network`` (``nn.Sequential`` NatureCNN, clip_ppo_minigrid.py:229-242 / clip_ppo_atari.py:196-209)

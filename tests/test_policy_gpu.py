@@ -166,3 +166,49 @@ def test_use_native_encoder_swaps_in_place(native):
     assert all(torch.equal(a.state_dict()[k], sd[k]) for k in sd)
     act, lp, ent, val, lat = rollout.action_value_and_latents(a, x, None)
     assert _rel(lat, want) <= 1e-4 and not lat.requires_grad
+
+
+def test_policy_step_graph_matches_eager_and_tracks_the_parameters(native):
+    """rollout.PolicyStepGraph: the env step's policy forward as one CUDA-graph replay - same logits / values as the eager
+    statements (given the sampled action), fresh samples on every replay, and parameter updates are seen without re-capture."""
+    import torch.nn as nn
+    from torch.distributions.categorical import Categorical
+    from clip_ppo_b200 import rollout
+    from clip_ppo_b200.policy import NatureCNN
+
+    class Agent(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.network = NatureCNN.from_sequential(_reference_network(3, seed=2))
+            self.actor, self.critic = nn.Linear(512, 7), nn.Linear(512, 1)
+
+        def _pre(self, x):
+            return x.permute(0, 3, 1, 2)
+
+        def _get_features(self, x):
+            return self.network(x, in_scale=1.0 / 255.0)
+
+    torch.manual_seed(0)
+    agent = Agent().cuda()
+    obs = torch.randint(0, 256, (64, 84, 84, 3), device="cuda", dtype=torch.uint8)
+    step = rollout.PolicyStepGraph(agent, obs)
+    acts = []
+    for trial in range(3):
+        a, lp, ent, v = step(obs)
+        with torch.no_grad():
+            h = agent._get_features(agent._pre(obs.float()))
+            probs = Categorical(logits=agent.actor(h))
+            assert torch.allclose(lp, probs.log_prob(a), atol=1e-6) and torch.allclose(ent, probs.entropy(), atol=1e-6)
+            assert torch.allclose(v, agent.critic(h), atol=1e-6)
+        acts.append(a.clone())
+        if trial == 1:                                  # an optimizer-style in-place update must be visible to the next replay
+            with torch.no_grad():
+                for p in agent.parameters():
+                    p.add_(0.01 * torch.randn_like(p))
+    assert not torch.equal(acts[0], acts[1])            # the device generator advances between replays
+    obs2 = torch.randint(0, 256, (64, 84, 84, 3), device="cuda", dtype=torch.uint8)
+    a2, lp2, _, v2 = step(obs2)
+    with torch.no_grad():
+        h2 = agent._get_features(agent._pre(obs2.float()))
+        assert torch.allclose(v2, agent.critic(h2), atol=1e-6)
+
