@@ -85,7 +85,7 @@ transpose_kernel(const float* __restrict__ src, float* __restrict__ dst, int row
 // scattered through `ro`.
 enum { EPI_NONE = 0, EPI_BIAS_RELU = 1, EPI_MASK = 2 };     // MASK: C = (mask[same address] > 0) ? acc : 0
 
-template <int BN, int EPI, int GATHER, int RM = 8>
+template <int BN, int EPI, int GATHER, int RM = 8, bool CHUNKED = false>
 __global__ void __launch_bounds__(256)
 sgemm_nt_kernel(const float* __restrict__ A, const __grid_constant__ Gather ga, const float* __restrict__ B, float* __restrict__ Cm,
                 const __grid_constant__ RowOut ro, long long M, int N, int K, float a_scale, const float* __restrict__ bias,
@@ -160,12 +160,13 @@ sgemm_nt_kernel(const float* __restrict__ A, const __grid_constant__ Gather ga, 
         if (b_row < BN) { sb[buf][b_k4 + 0][b_row] = rb.x; sb[buf][b_k4 + 1][b_row] = rb.y; sb[buf][b_k4 + 2][b_row] = rb.z; sb[buf][b_k4 + 3][b_row] = rb.w; }
     };
     const int nk_all = K / BK;
-    const bool split = ksteps > 0 && part != nullptr;
+    if constexpr (!CHUNKED) ksteps = 0;                               // the backward's GEMMs: one plain K walk, no second accumulator set
+    const bool split = CHUNKED && ksteps > 0 && part != nullptr;
     const int kb0 = split ? static_cast<int>(blockIdx.z) * ksteps : 0;
     const int nk = split ? min(nk_all, kb0 + ksteps) : nk_all;
-    float tot[RM][4];                                                  // chunk sums so far (chunked, unsplit walk only)
+    float tot[CHUNKED ? RM : 1][4];                                    // chunk sums so far (chunked, unsplit walk only)
 #pragma unroll
-    for (int i = 0; i < RM; ++i)
+    for (int i = 0; i < (CHUNKED ? RM : 1); ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) tot[i][j] = 0.f;
     int left = ksteps;                                                 // k-steps left in the current chunk
@@ -188,21 +189,25 @@ sgemm_nt_kernel(const float* __restrict__ A, const __grid_constant__ Gather ga, 
 #pragma unroll
                 for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
         }
-        if (ksteps > 0 && !split && (--left == 0 || kb + 1 == nk)) {  // chunk boundary: fold the chunk's sum in, start the next one at zero
+        if constexpr (CHUNKED) {
+            if (ksteps > 0 && !split && (--left == 0 || kb + 1 == nk)) {  // chunk boundary: fold the chunk's sum in, start the next one at zero
 #pragma unroll
-            for (int i = 0; i < RM; ++i)
+                for (int i = 0; i < RM; ++i)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) { tot[i][j] += acc[i][j]; acc[i][j] = 0.f; }
-            left = ksteps;
+                    for (int j = 0; j < 4; ++j) { tot[i][j] += acc[i][j]; acc[i][j] = 0.f; }
+                left = ksteps;
+            }
         }
         if (kb + 1 < nk) store_tiles(buf ^ 1);
         __syncthreads();
     }
-    if (ksteps > 0 && !split) {
+    if constexpr (CHUNKED) {
+        if (ksteps > 0 && !split) {
 #pragma unroll
-        for (int i = 0; i < RM; ++i)
+            for (int i = 0; i < RM; ++i)
 #pragma unroll
-            for (int j = 0; j < 4; ++j) acc[i][j] = tot[i][j];
+                for (int j = 0; j < 4; ++j) acc[i][j] = tot[i][j];
+        }
     }
     if (split) {
 #pragma unroll
@@ -435,18 +440,20 @@ int launch_nt_plain(const float* A, const float* B, float* Cm, long long M, int 
         if (split) {                                                  // an env-step batch: the K = 3136 loop of 8 CTAs would be the whole latency
             const int splits = (K / 16 + ksteps - 1) / ksteps;
             grid.z = splits;
-            sgemm_nt_kernel<64, EPI, 0, 4><<<grid, 256, 0, st>>>(A, kNoGather, B, Cm, kNoRowOut, M, N, K, 1.0f, bias, mask, ksteps, part);
+            sgemm_nt_kernel<64, EPI, 0, 4, true><<<grid, 256, 0, st>>>(A, kNoGather, B, Cm, kNoRowOut, M, N, K, 1.0f, bias, mask, ksteps, part);
             CLIPPPO_CHECK_LAUNCH();
             splitk_finish_kernel<EPI, 0><<<static_cast<unsigned>((M * (N / 4) + 255) / 256), 256, 0, st>>>(part, splits, Cm, kNoRowOut, M, N, 1.0f, bias, mask);
             CLIPPPO_CHECK_LAUNCH();
             return CLIPPPO_OK;
         }
-        sgemm_nt_kernel<64, EPI, 0, 4><<<grid, 256, 0, st>>>(A, kNoGather, B, Cm, kNoRowOut, M, N, K, 1.0f, bias, mask, ksteps, nullptr);
+        if (ksteps > 0) sgemm_nt_kernel<64, EPI, 0, 4, true><<<grid, 256, 0, st>>>(A, kNoGather, B, Cm, kNoRowOut, M, N, K, 1.0f, bias, mask, ksteps, nullptr);
+        else sgemm_nt_kernel<64, EPI, 0, 4><<<grid, 256, 0, st>>>(A, kNoGather, B, Cm, kNoRowOut, M, N, K, 1.0f, bias, mask);
     } else {
         dim3 grid(static_cast<unsigned>((M + 127) / 128), (N + 63) / 64);
         bool split = false;
         const int ksteps = part ? plan_ksteps(1 << 20, K / 16, M, N, part_floats, &split) : 0;      // same chunks, never split
-        sgemm_nt_kernel<64, EPI, 0><<<grid, 256, 0, st>>>(A, kNoGather, B, Cm, kNoRowOut, M, N, K, 1.0f, bias, mask, ksteps, nullptr);
+        if (ksteps > 0) sgemm_nt_kernel<64, EPI, 0, 8, true><<<grid, 256, 0, st>>>(A, kNoGather, B, Cm, kNoRowOut, M, N, K, 1.0f, bias, mask, ksteps, nullptr);
+        else sgemm_nt_kernel<64, EPI, 0><<<grid, 256, 0, st>>>(A, kNoGather, B, Cm, kNoRowOut, M, N, K, 1.0f, bias, mask);
     }
     CLIPPPO_CHECK_LAUNCH();
     return CLIPPPO_OK;
@@ -462,13 +469,13 @@ int launch_nt_gather(const float* A, const Gather& ga, const float* B, float* Cm
         if (split) {
             const int splits = (K / 16 + ksteps - 1) / ksteps;
             grid.z = splits;
-            sgemm_nt_kernel<64, EPI, 1><<<grid, 256, 0, st>>>(A, ga, B, Cm, ro, M, N, K, a_scale, bias, mask, ksteps, part);
+            sgemm_nt_kernel<64, EPI, 1, 8, true><<<grid, 256, 0, st>>>(A, ga, B, Cm, ro, M, N, K, a_scale, bias, mask, ksteps, part);
             CLIPPPO_CHECK_LAUNCH();
             splitk_finish_kernel<EPI, 1><<<static_cast<unsigned>((M * (N / 4) + 255) / 256), 256, 0, st>>>(part, splits, Cm, ro, M, N, a_scale, bias, mask);
             CLIPPPO_CHECK_LAUNCH();
             return CLIPPPO_OK;
         }
-        sgemm_nt_kernel<64, EPI, 1><<<grid, 256, 0, st>>>(A, ga, B, Cm, ro, M, N, K, a_scale, bias, mask, ksteps, nullptr);   // same chunks, one CTA per tile
+        sgemm_nt_kernel<64, EPI, 1, 8, true><<<grid, 256, 0, st>>>(A, ga, B, Cm, ro, M, N, K, a_scale, bias, mask, ksteps, nullptr);   // same chunks, one CTA per tile
         CLIPPPO_CHECK_LAUNCH();
         return CLIPPPO_OK;
     }
