@@ -1,6 +1,11 @@
 // V4 - multi-head self-attention core of one ResidualAttentionBlock: softmax(Q K^T / sqrt(d)) V,
 // no mask, eval mode.  Replaces the SDPA call inside [clip] nn.MultiheadAttention.
 //
+// Since round 2 every shape the towers produce runs on the tcgen05 / TMEM / TMA kernels of attention_tc.cu
+// (T <= 64: two images per tile; causal T <= 128: one sequence per tile; 64 < T <= 257 without a mask); the
+// mma.sync kernels of this file remain as the fallback for other shapes (T > 257, T < 16, unmasked 64 < T with
+// CLIPPPO_ATT_TC=0) and as the A/B reference (CLIPPPO_ATT_TC50=0).  attention_launch() below is the dispatcher.
+//
 // ViT-B/32 has T = 50 tokens and d_head = 64: ~1 % of the tower's FLOPs, bound by memory latency
 // and instruction issue rather than math.  Persistent CTAs (4 per SM) walk over (image, head)
 // items; the Q/K/V head slices of item i+1 stream into the second shared-memory buffer with

@@ -11,7 +11,12 @@
 // traffic per MMA (the limiter of the single-CTA 128x256 tile on Blackwell) and leaves room for a
 // 6-stage TMA ring.
 //   warps 0-7   epilogue (both CTAs): tcgen05.ld (thread = accumulator row) -> fused epilogue -> swizzled
-//               staging tile -> TMA store / TMA reduce-add (legacy fp32 epilogues: smem transpose -> stores)
+//               staging tile -> TMA store (legacy fp32 epilogues: smem transpose -> stores).  The residual
+//               epilogue (RESID_STATS) first TMA-LOADS the old rows of the residual stream into the same
+//               staging tile (one tile ahead), adds in fp32, rounds once, and leaves the row's partial
+//               (sum, sum of squares) - all that is left of the next LayerNorm - for the consuming GEMM;
+//               the round-1 variant (RESID_BF16: TMA reduce-add in L2, statistics by a separate pass) is kept
+//               for the split-K latency schedule and A/B measurements
 //   warp 8      TMA producer (both CTAs; bytes are counted on the LEADER's full barrier)
 //   warp 9      MMA issuer (leader CTA only): 4 x tcgen05.mma.cta_group::2 (256x256x16) per k-block;
 //               fp32 accumulators double-buffered in TMEM (2 x 256 columns per CTA)
