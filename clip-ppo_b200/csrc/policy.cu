@@ -103,11 +103,16 @@ sgemm_nt_kernel(const float* __restrict__ A, const __grid_constant__ Gather ga, 
     const int tid = threadIdx.x, tx = tid % TX, ty = tid / TX;
     const long long m0 = static_cast<long long>(blockIdx.x) * BM;
     const int n0 = blockIdx.y * BN;
-    float acc[RM][4];
+    // Accumulators as PACKED pairs of rows: acc2[ip][j] = (C[2 ip][j], C[2 ip + 1][j]).  On Blackwell a three-register FFMA issues
+    // every other cycle per scheduler; FFMA2 (two independent round-to-nearest FMAs on 64-bit register pairs, bit-identical
+    // to two FFMAs) is what reaches the fp32 pipe's full rate.  The a-fragment pairs are the aligned halves of the float4
+    // shared-memory loads; a b value is broadcast into a pair with one move.
+    constexpr int RP = RM / 2;
+    float2 acc2[RP][4];
 #pragma unroll
-    for (int i = 0; i < RM; ++i)
+    for (int i = 0; i < RP; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+        for (int j = 0; j < 4; ++j) acc2[i][j] = make_float2(0.f, 0.f);
     // loaders: A tile = BM rows x 16 k (A_F4 float4 per thread, rows a_row + 64 h); B tile = BN rows x 16 k
     const int a_row = tid >> 2, a_k4 = (tid & 3) * 4;
     const float* arow[A_F4];
@@ -164,11 +169,11 @@ sgemm_nt_kernel(const float* __restrict__ A, const __grid_constant__ Gather ga, 
     const bool split = CHUNKED && ksteps > 0 && part != nullptr;
     const int kb0 = split ? static_cast<int>(blockIdx.z) * ksteps : 0;
     const int nk = split ? min(nk_all, kb0 + ksteps) : nk_all;
-    float tot[CHUNKED ? RM : 1][4];                                    // chunk sums so far (chunked, unsplit walk only)
+    float2 tot2[CHUNKED ? RP : 1][4];                                  // chunk sums so far (chunked, unsplit walk only)
 #pragma unroll
-    for (int i = 0; i < (CHUNKED ? RM : 1); ++i)
+    for (int i = 0; i < (CHUNKED ? RP : 1); ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) tot[i][j] = 0.f;
+        for (int j = 0; j < 4; ++j) tot2[i][j] = make_float2(0.f, 0.f);
     int left = ksteps;                                                 // k-steps left in the current chunk
     load_tiles(kb0 * BK);
     store_tiles(kb0 & 1);
@@ -182,19 +187,19 @@ sgemm_nt_kernel(const float* __restrict__ A, const __grid_constant__ Gather ga, 
             float4 a1 = a0;
             if constexpr (RM == 8) a1 = *reinterpret_cast<const float4*>(&sa[buf][k][HALF + ty * 4]);
             const float4 b4 = *reinterpret_cast<const float4*>(&sb[buf][k][tx * 4]);
-            const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-            const float b[4] = {b4.x, b4.y, b4.z, b4.w};
+            const float2 ap[4] = {make_float2(a0.x, a0.y), make_float2(a0.z, a0.w), make_float2(a1.x, a1.y), make_float2(a1.z, a1.w)};
+            const float2 bb[4] = {make_float2(b4.x, b4.x), make_float2(b4.y, b4.y), make_float2(b4.z, b4.z), make_float2(b4.w, b4.w)};
 #pragma unroll
-            for (int i = 0; i < RM; ++i)
+            for (int i = 0; i < RP; ++i)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+                for (int j = 0; j < 4; ++j) acc2[i][j] = __ffma2_rn(ap[i], bb[j], acc2[i][j]);
         }
         if constexpr (CHUNKED) {
             if (ksteps > 0 && !split && (--left == 0 || kb + 1 == nk)) {  // chunk boundary: fold the chunk's sum in, start the next one at zero
 #pragma unroll
-                for (int i = 0; i < RM; ++i)
+                for (int i = 0; i < RP; ++i)
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) { tot[i][j] += acc[i][j]; acc[i][j] = 0.f; }
+                    for (int j = 0; j < 4; ++j) { tot2[i][j] = __fadd2_rn(tot2[i][j], acc2[i][j]); acc2[i][j] = make_float2(0.f, 0.f); }
                 left = ksteps;
             }
         }
@@ -204,11 +209,16 @@ sgemm_nt_kernel(const float* __restrict__ A, const __grid_constant__ Gather ga, 
     if constexpr (CHUNKED) {
         if (ksteps > 0 && !split) {
 #pragma unroll
-            for (int i = 0; i < RM; ++i)
+            for (int i = 0; i < RP; ++i)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) acc[i][j] = tot[i][j];
+                for (int j = 0; j < 4; ++j) acc2[i][j] = tot2[i][j];
         }
     }
+    float acc[RM][4];                                                  // unpack: the epilogues address single rows
+#pragma unroll
+    for (int i = 0; i < RP; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { acc[2 * i][j] = acc2[i][j].x; acc[2 * i + 1][j] = acc2[i][j].y; }
     if (split) {
 #pragma unroll
         for (int i = 0; i < RM; ++i) {
@@ -261,11 +271,12 @@ sgemm_tn_split_kernel(const float* __restrict__ A, const float* __restrict__ B, 
     const int p0 = blockIdx.y * BP, q0 = blockIdx.x * BQ;
     const long long r_begin = static_cast<long long>(blockIdx.z) * rows_per_split;
     const long long r_end = (r_begin + rows_per_split < R) ? r_begin + rows_per_split : R;
-    float acc[TP][TQ];
+    constexpr int TPP = TP / 2;                                        // packed pairs of output rows (FFMA2, see sgemm_nt_kernel)
+    float2 acc2[TPP][TQ];
 #pragma unroll
-    for (int i = 0; i < TP; ++i)
+    for (int i = 0; i < TPP; ++i)
 #pragma unroll
-        for (int j = 0; j < TQ; ++j) acc[i][j] = 0.f;
+        for (int j = 0; j < TQ; ++j) acc2[i][j] = make_float2(0.f, 0.f);
     const int lr = tid >> 4, lc = (tid & 15) * 4;                      // B: row lr, float4 groups lc + 64 g
     const int alr = (BP == 64) ? lr : (tid >> 3), alc = (BP == 64) ? lc : (tid & 7) * 4;     // A: 16 x BP (BP = 32: threads 0..127)
     const long long per = GATHER ? static_cast<long long>(gb.NI) * gb.NJ : 1;
@@ -301,25 +312,30 @@ sgemm_tn_split_kernel(const float* __restrict__ A, const float* __restrict__ B, 
         if (r0 + BR < r_end) load_step(r0 + BR);                       // next step's rows travel under this step's FMAs
 #pragma unroll
         for (int k = 0; k < BR; ++k) {
-            float av[4];
+            float2 ap[2];
             if constexpr (TP == 4) {
                 const float4 a = *reinterpret_cast<const float4*>(&sa[k][ty * 4]);
-                av[0] = a.x; av[1] = a.y; av[2] = a.z; av[3] = a.w;
+                ap[0] = make_float2(a.x, a.y); ap[1] = make_float2(a.z, a.w);
             } else {
-                const float2 a = *reinterpret_cast<const float2*>(&sa[k][ty * 2]);
-                av[0] = a.x; av[1] = a.y;
+                ap[0] = *reinterpret_cast<const float2*>(&sa[k][ty * 2]);
+                ap[1] = ap[0];
             }
 #pragma unroll
             for (int g = 0; g < QG; ++g) {
                 const float4 b = *reinterpret_cast<const float4*>(&sb[k][tx * 4 + 64 * g]);
-                const float bv[4] = {b.x, b.y, b.z, b.w};
+                const float2 bb[4] = {make_float2(b.x, b.x), make_float2(b.y, b.y), make_float2(b.z, b.z), make_float2(b.w, b.w)};
 #pragma unroll
-                for (int i = 0; i < TP; ++i)
+                for (int i = 0; i < TPP; ++i)
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) acc[i][4 * g + j] = fmaf(av[i], bv[j], acc[i][4 * g + j]);
+                    for (int j = 0; j < 4; ++j) acc2[i][4 * g + j] = __ffma2_rn(ap[i], bb[j], acc2[i][4 * g + j]);
             }
         }
     }
+    float acc[TP][TQ];
+#pragma unroll
+    for (int i = 0; i < TPP; ++i)
+#pragma unroll
+        for (int j = 0; j < TQ; ++j) { acc[2 * i][j] = acc2[i][j].x; acc[2 * i + 1][j] = acc2[i][j].y; }
     float* out = part + static_cast<long long>(blockIdx.z) * P * Q;
 #pragma unroll
     for (int i = 0; i < TP; ++i) {
