@@ -10,7 +10,8 @@ from clip_ppo_b200 import disturb as D
 from shared.disturbance_types import DisturbanceSeverity, SEVERITY_CONFIGS
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
-_row = SEVERITY_CONFIGS[DisturbanceSeverity.MODERATE]
+SEV = sys.argv[2] if len(sys.argv) > 2 else "MODERATE"
+_row = SEVERITY_CONFIGS[DisturbanceSeverity[SEV]]
 cfg = {"blur_sigma": _row["gaussian_blur_sigma"], "noise_sigma": _row["gaussian_noise_sigma"], "cutout": _row["cutout_ratio"]}
 x = torch.rand(B, 3, 224, 224, device="cuda")
 n = torch.randn(B, 3, 224, 224, device="cuda")
