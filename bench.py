@@ -21,7 +21,9 @@ inside the timed region, prefetched one step ahead on a copy stream), draws the 
 and reads the loss back to the host.  Extra keys of the JSON line:
     roofline      the tcgen05 GEMM (dominant kernel), CUDA-event timed inside a second pass of the same steps
     secondary     short CUDA-event measurements of the other BASELINE configs: disturbance HBM fractions (MODERATE / SEVERE
-                  224x224x3, HARD 84x84x1), the Atari 84 -> 224 path (configs[3], one GPU's share), ViT-L/14 (configs[4])
+                  224x224x3, HARD 84x84x1), the learner side of one MiniGrid iteration (configs[1]) next to the script's own
+                  statements over the reference's modules on the same GPU, the Atari 84 -> 224 path (configs[3], one GPU's share),
+                  ViT-L/14 (configs[4])
     eager_gpu_baseline   the reference's OWN functions (oracle/_ref, staged by oracle/build_ref.py) on the same GPU with an
                   fp16 eager tower (tools/eager_tower.py) - the library-dispatched path the reference runs on a GPU
     cpu_baseline  the reference's own functions on the host cores (fp32 tower restated in oracle/vit.py), bounded sample
