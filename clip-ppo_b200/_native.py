@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libclipppo_b200.so")
+# CLIPPPO_LIB=<path>: an experimental build of the same ABI (tools/build_variant.sh) instead of the in-tree library - A/B measurements only
+LIB_PATH = os.environ.get("CLIPPPO_LIB") or os.path.join(HERE, "libclipppo_b200.so")
 
 # status codes (include/clipppo_b200.h)
 OK = 0

@@ -430,19 +430,37 @@ disturb_fast_kernel(const __grid_constant__ DisturbParams p) {
             }
         } else if constexpr (K > 1) {
             const int nh4 = rows > 0 ? C * 2 * P * nq : 0;
-            for (int i = tid; i < nh4; i += nth) {
-                const int hr_c = div_nq(i), quad = i - hr_c * nq;
-                const int c_ = hr_c / (2 * P), hr = hr_c - c_ * (2 * P);     // compile-time divisor
-                const int lr = hr < P ? hr : rows + hr;                      // smem row: above the first / below the last own row
-                int ir = r0 - P + lr;                                        // image row before reflection
-                if (ir < 0) ir = -ir;
-                if (ir >= H) ir = 2 * (H - 1) - ir;
-                const int goff = c_ * HW + ir * W + 4 * quad;
-                const float4 xv = xu8 ? u8x4_over_255(ld_stream_u32(xb + goff)) : ld_stream_f4(xi + goff);
-                float4 nv = xv;
-                if constexpr (PHILOX) { if (do_noise) nv = philox_normal4(quad0 + static_cast<unsigned>(goff >> 2), p.philox_seed, p.philox_offset); }
-                else if (do_noise) nv = ld_stream_f4(ni + goff);
-                *reinterpret_cast<float4*>(tile + c_ * plane + lr * WP + kPad + 4 * quad) = noisy4(xv, nv);
+            // every load of UH positions is in flight before the first one is used: one round trip to L2 / HBM per UH * nth quads
+            constexpr int UH = 3;
+            for (int i0 = tid; i0 < nh4; i0 += nth * UH) {
+                float4 xv[UH], nv[UH];
+                int soff[UH], gq[UH];
+#pragma unroll
+                for (int u = 0; u < UH; ++u) {
+                    const int i = i0 + u * nth;
+                    if (i < nh4) {
+                        const int hr_c = div_nq(i), quad = i - hr_c * nq;
+                        const int c_ = hr_c / (2 * P), hr = hr_c - c_ * (2 * P);
+                        const int lr = hr < P ? hr : rows + hr;
+                        int ir = r0 - P + lr;
+                        if (ir < 0) ir = -ir;
+                        if (ir >= H) ir = 2 * (H - 1) - ir;
+                        const int goff = c_ * HW + ir * W + 4 * quad;
+                        soff[u] = c_ * plane + lr * WP + kPad + 4 * quad;
+                        gq[u] = goff >> 2;
+                        if constexpr (xu8) xv[u].x = __uint_as_float(ld_stream_u32(xb + goff)); else xv[u] = ld_stream_f4(xi + goff);
+                        if constexpr (!PHILOX) { if (do_noise) nv[u] = ld_stream_f4(ni + goff); }
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < UH; ++u) {
+                    const int i = i0 + u * nth;
+                    if (i < nh4) {
+                        if constexpr (xu8) xv[u] = u8x4_over_255(__float_as_uint(xv[u].x));
+                        if constexpr (PHILOX) { if (do_noise) nv[u] = philox_normal4(quad0 + static_cast<unsigned>(gq[u]), p.philox_seed, p.philox_offset); }
+                        *reinterpret_cast<float4*>(tile + soff[u]) = noisy4(xv[u], nv[u]);
+                    }
+                }
             }
         }
     };
@@ -552,8 +570,10 @@ disturb_fast_kernel(const __grid_constant__ DisturbParams p) {
     if (do_contrast) {
         tot = block_sum(g, red);
         if (exchange) {
-            if (tid == 0) *partial = tot;
-            asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+            // release of ONE shared-memory word: the writer fences, every thread arrives relaxed (an arrive.release is a
+            // MEMBAR.ALL.GPU in each of the CTA's threads)
+            if (tid == 0) { *partial = tot; asm volatile("fence.acq_rel.cluster;" ::: "memory"); }
+            asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
         }
     }
     load_halo();                                     // not part of the sum: rides between ARRIVE and WAIT
@@ -562,7 +582,11 @@ disturb_fast_kernel(const __grid_constant__ DisturbParams p) {
             asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
             tot = 0.0f;
             for (int q = 0; q < S; ++q) tot += *cluster.map_shared_rank(partial, q);
-            asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");     // my reads of the peers' sums are done
+            // "my reads of the peers' sums are done": relaxed - there is nothing to release, and an arrive.release is a MEMBAR in
+            // every thread.  The arrive must not overtake the loads, though: a (never taken) branch on their sum is a scoreboard
+            // wait for all of them, and instructions issue in order.
+            if (__float_as_uint(tot) == 0x7fc0deadu) asm volatile("nanosleep.u32 1;" ::: "memory");
+            asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
         }
         __syncthreads();
         contrast_image(tot);
