@@ -991,6 +991,8 @@ static int run_disturb(DisturbParams& p, const float* k1d_host, int k, cudaStrea
         int nthreads = (p.C * nq * nsplit + 31) / 32 * 32;
         if (nthreads > kFastMaxThreads) nthreads = kFastMaxThreads;
         if (nthreads < 64) nthreads = 64;
+        static const int env_nthreads = env_int("CLIPPPO_DISTURB_NTHREADS", 0);   // measurement knob: CTA size (multiple of 32, <= 384)
+        if (env_nthreads >= 64 && env_nthreads <= kFastMaxThreads && env_nthreads % 32 == 0) nthreads = env_nthreads;
         p.nthreads = nthreads;
         p.log2S = 0;
         while ((1 << p.log2S) < S) ++p.log2S;
