@@ -163,7 +163,9 @@ __global__ void __launch_bounds__(ATC_THREADS, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_tail,
                     const __grid_constant__ CUtensorMap tm_out, const AtcArgs g) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+        // 1024-byte alignment as an OFFSET from the __shared__ symbol: the pointer keeps its address space, so the staging-tile
+    // accesses are STS / LDS instead of generic ST.E / LD.E
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const uint32_t sbase = smem_u32(smem);
     auto bar = [&](int i) { return sbase + OFF_BAR + 8u * i; };
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_BAR + NUM_BARS * 8);
@@ -588,7 +590,9 @@ template <bool PAIR>
 __global__ void __launch_bounds__(TP_THREADS, 1)
 attention_tc_pair_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_out, const TpArgs g) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+        // 1024-byte alignment as an OFFSET from the __shared__ symbol: the pointer keeps its address space, so the staging-tile
+    // accesses are STS / LDS instead of generic ST.E / LD.E
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const uint32_t sbase = smem_u32(smem);
     auto bar = [&](int i) { return sbase + TP_OFF_BAR + 8u * i; };
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + TP_OFF_BAR + TP_NUM_BARS * 8);
