@@ -20,6 +20,12 @@
 //   warp 8      TMA producer (both CTAs; bytes are counted on the LEADER's full barrier)
 //   warp 9      MMA issuer (leader CTA only): 4 x tcgen05.mma.cta_group::2 (256x256x16) per k-block;
 //               fp32 accumulators double-buffered in TMEM (2 x 256 columns per CTA)
+//               Both issuer warps walk their schedule CONVERGED (all 32 lanes wait on the mbarriers and keep the loop
+//               state) and only the issue itself sits under elect.sync: the operands of UTCHMMA / UTMALDG live in uniform
+//               registers, so the four MMAs of a k-block are four consecutive instructions.  Issued from an
+//               `if (lane == 0)` region every operand was a per-thread value and each MMA cost an ELECT / 5 x R2UR /
+//               branch loop - 108 instructions per k-block against 57, and the tensor pipe waited for its issuer
+//               (QKV 549 -> 521 us, c_fc 750 -> 696 us at M = 204 800).
 //   warp 10     TMEM allocator
 // so the epilogue of tile i overlaps the MMAs of tile i+1.  MODE 1 (env CLIPPPO_GEMM_CLUSTER=1) is
 // the same kernel with one CTA per 128x256 tile and cta_group::1, kept for A/B measurements.
@@ -141,7 +147,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + C::OFF_BAR + C::NUM_BARS * 8);
 
     pdl_launch_dependents();                  // the next kernel may start its prologue under our tail
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // provably warp-uniform
     const int m_tiles = (g.M + BM - 1) / BM, n_tiles = (g.N + BN - 1) / BN;
     const int num_kb = g.K / BK;
     // work decomposition: unit = CTA (MODE 1) or CTA pair (MODE 2); a work item is CL stacked M-tiles
@@ -175,12 +181,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     tc_fence_before();
     if constexpr (CL == 2) cluster_sync_all(); else __syncthreads();   // peer barriers are initialised too
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
     pdl_wait();                               // everything above overlapped the previous kernel; its data is needed now
 
     if (warp == W_TMA) {
-        // ===================== TMA producer =====================
-        if (lane == 0) {
+        // ===================== TMA producer: the whole warp walks the schedule, one elected lane issues =====================
+        {
             int stage = 0; uint32_t phase = 0;
             for (int w = unit; w < num_work; w += num_units) {
                 const int t = w / ksplit, ks = w - t * ksplit;
@@ -189,26 +195,28 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     mbar_wait(empty_bar(stage), phase ^ 1);
                     const uint32_t sa = sbase + C::OFF_A + stage * C::A_STAGE_BYTES;
                     const uint32_t sb = sbase + C::OFF_B + stage * C::B_STAGE_BYTES;
-                    if constexpr ((DBG & 2) != 0) {
-                        if (rank == 0) mbar_arrive(full_bar(stage));
-                    } else if constexpr (CL == 2) {
-                        // the leader's barrier expects both CTAs' A tile and W half
-                        if (rank == 0) mbar_arrive_expect_tx(full_bar(stage), 2 * (C::A_STAGE_BYTES + C::B_STAGE_BYTES));
-                        tma_load_2d_2sm(sa, &tmap_a, full_bar(stage), kb * BK, m_blk * BM);
-                        tma_load_2d_2sm(sb, &tmap_b, full_bar(stage), kb * BK, n_blk * BN + rank * (BN / 2));
-                    } else {
-                        mbar_arrive_expect_tx(full_bar(stage), C::A_STAGE_BYTES + C::B_STAGE_BYTES);
-                        tma_load_2d(sa, &tmap_a, full_bar(stage), kb * BK, m_blk * BM);
-                        tma_load_2d(sb, &tmap_b, full_bar(stage), kb * BK, n_blk * BN);
-                        tma_load_2d(sb + C::B_STAGE_BYTES / 2, &tmap_b, full_bar(stage), kb * BK, n_blk * BN + BN / 2);
+                    if (elect_one_sync()) {
+                        if constexpr ((DBG & 2) != 0) {
+                            if (rank == 0) mbar_arrive(full_bar(stage));
+                        } else if constexpr (CL == 2) {
+                            if (rank == 0) mbar_arrive_expect_tx(full_bar(stage), 2 * (C::A_STAGE_BYTES + C::B_STAGE_BYTES));
+                            tma_load_2d_2sm(sa, &tmap_a, full_bar(stage), kb * BK, m_blk * BM);
+                            tma_load_2d_2sm(sb, &tmap_b, full_bar(stage), kb * BK, n_blk * BN + rank * (BN / 2));
+                        } else {
+                            mbar_arrive_expect_tx(full_bar(stage), C::A_STAGE_BYTES + C::B_STAGE_BYTES);
+                            tma_load_2d(sa, &tmap_a, full_bar(stage), kb * BK, m_blk * BM);
+                            tma_load_2d(sb, &tmap_b, full_bar(stage), kb * BK, n_blk * BN);
+                            tma_load_2d(sb + C::B_STAGE_BYTES / 2, &tmap_b, full_bar(stage), kb * BK, n_blk * BN + BN / 2);
+                        }
                     }
+                    __syncwarp();
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == W_MMA) {
-        // ===================== MMA issuer (leader CTA of the pair) =====================
-        if (lane == 0 && rank == 0) {
+        // ===================== MMA issuer (leader CTA of the pair): converged warp, elected lane issues =====================
+        if (rank == 0) {
             constexpr uint32_t idesc = make_idesc_bf16(BM * CL, BN);
             int stage = 0; uint32_t phase = 0;
             int as = 0; uint32_t aphase = 0;
@@ -222,18 +230,21 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     tc_fence_after();
                     const uint64_t da = make_kmajor_sw128_desc(sbase + C::OFF_A + stage * C::A_STAGE_BYTES);
                     const uint64_t db = make_kmajor_sw128_desc(sbase + C::OFF_B + stage * C::B_STAGE_BYTES);
+                    if (elect_one_sync()) {
 #pragma unroll
-                    for (int k = 0; k < BK / UMMA_K; ++k) {
-                        // +32 bytes per 16-element k-step inside the 128-byte swizzle atom
-                        if constexpr (CL == 2) umma_bf16_2sm(tmem_d, da + 2 * k, db + 2 * k, idesc, ((kb - kb0) | k) != 0);
-                        else umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, ((kb - kb0) | k) != 0);
+                        for (int k = 0; k < BK / UMMA_K; ++k) {
+                            if constexpr (CL == 2) umma_bf16_2sm(tmem_d, da + 2 * k, db + 2 * k, idesc, ((kb - kb0) | k) != 0);
+                            else umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, ((kb - kb0) | k) != 0);
+                        }
+                        if constexpr (CL == 2) umma_commit_2sm(empty_bar(stage), 0x3); else umma_commit(empty_bar(stage));
+                        // accumulator complete after the tile's last k-block: wake the epilogue warps of both CTAs
+                        if (kb + 1 == kbe) {
+                            if constexpr (CL == 2) umma_commit_2sm(tfull_bar(as), 0x3); else umma_commit(tfull_bar(as));
+                        }
                     }
-                    // smem slot free (in both CTAs) once these MMAs retire
-                    if constexpr (CL == 2) umma_commit_2sm(empty_bar(stage), 0x3); else umma_commit(empty_bar(stage));
+                    __syncwarp();
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
-                // accumulator complete: wake the epilogue warps of both CTAs
-                if constexpr (CL == 2) umma_commit_2sm(tfull_bar(as), 0x3); else umma_commit(tfull_bar(as));
                 if (++as == ACC_STAGES) { as = 0; aphase ^= 1; }
             }
         }

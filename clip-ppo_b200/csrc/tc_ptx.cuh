@@ -89,6 +89,21 @@ __device__ __forceinline__ void bulk_wait_group_read() { asm volatile("cp.async.
 template <int N>
 __device__ __forceinline__ void bulk_wait_group() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
 
+// ---- warp-uniform issue ----------------------------------------------------------------------
+// One lane of a CONVERGED warp (all 32 lanes must execute this).  The single-thread instructions (tcgen05.mma, TMA) take their
+// operands from uniform registers: issued from a warp whose control flow the compiler can prove uniform, with only the issue
+// itself under elect.sync, they cost one instruction each - issued from an `if (lane == 0)` region every operand is a per-thread
+// value that has to be moved into a uniform register by an ELECT / R2UR / branch loop of ~10 instructions.
+__device__ __forceinline__ bool elect_one_sync() {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+        "elect.sync rx|px, %1;\n\t"
+        "@px mov.s32 %0, 1;\n\t}"
+        : "+r"(pred) : "r"(0xffffffffu));
+    return pred != 0;
+}
+
 // ---- clusters -------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;
