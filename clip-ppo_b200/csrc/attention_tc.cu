@@ -11,11 +11,12 @@
 //               the first 64 columns of S; per item: read the tile's two output accumulators, merge, normalise,
 //               stage in the (dead) Q tile under the TMA swizzle, TMA store.
 //   warp 8      TMEM allocation (all 512 columns: S of both tiles 2 x 128, four 64-column output accumulators);
-//               lane 0 issues every tcgen05.mma:  S_w = Q_w K_kb^T  (A, B from shared memory, both K-major
+//               the warp walks the schedule converged and one elected lane issues every tcgen05.mma (operands in uniform
+//               registers: no R2UR loops between the hand-offs, 749 -> 654 us at 1024 images x 16 heads):  S_w = Q_w K_kb^T  (A, B from shared memory, both K-major
 //               SWIZZLE_128B);  O_w,kb = P_w V_kb  (A = P from TMEM, B = V from shared memory, MN-major: V stays
 //               [key][d] exactly as the TMA box wrote it - no transpose anywhere).  While warpgroup 0 exponentiates
 //               block (0, kb) the tensor core computes S of tile 1, and so on.
-//   warp 9      lane 0 issues the TMA loads, up to two items ahead.
+//   warp 9      issues the TMA loads (same converged / elected scheme), up to two items ahead.
 //   warps 10-11 the "tail" query row (below), one key block each, on the CUDA cores.
 // T = 257 = 2 x 128 + 1: the 256 x 256 part of the problem maps onto M = N = 128 tensor-core tiles without
 // padding; the 257th token would cost a third, almost empty, 128-row tile and a third key block.  Instead its
@@ -169,7 +170,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
     const uint32_t sbase = smem_u32(smem);
     auto bar = [&](int i) { return sbase + OFF_BAR + 8u * i; };
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_BAR + NUM_BARS * 8);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // provably warp-uniform
 
     pdl_launch_dependents();
     const int T = g.T, heads = g.heads, D = heads * DH;
@@ -199,20 +200,23 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
     pdl_wait();
 
     const float sl2 = 0.125f * 1.4426950408889634f;               // 1/sqrt(64) * log2(e)
 
     if (warp == W_TMA) {
         // ===================== TMA producer: two items ahead of the consumers =====================
-        if (lane == 0) {
+        // (this warp and the MMA warp walk their schedules converged; only the issue sits under elect.sync, so the operands of
+        // the single-thread instructions stay in uniform registers - see elect_one_sync() in tc_ptx.cuh)
+        {
             int it = 0;
             for (int item = blockIdx.x; item < g.n_items; item += gridDim.x, ++it) {
                 const int img = item / heads, head = item - img * heads;
                 const int st = it & 1, use = it >> 1;
                 const uint32_t base = sbase + st * STAGE_BYTES;
                 if (use > 0) mbar_wait_cold(bar(B_FREE + st), (use - 1) & 1);     // every reader of the stage's previous item is done
+                if (elect_one_sync()) {
                 mbar_arrive_expect_tx(bar(B_QK + st), 2u * n_tiles * TILE_BYTES + (tail ? 3 * 1024 : 0));
                 for (int t = 0; t < n_tiles; ++t) {
                     tma_load_3d(base + OFF_Q + t * TILE_BYTES, &tm_qkv, bar(B_QK + st), head * DH, t * TILE, img);
@@ -226,11 +230,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
                 mbar_arrive_expect_tx(bar(B_V + st), static_cast<uint32_t>(n_tiles) * TILE_BYTES);
                 for (int t = 0; t < n_tiles; ++t)
                     tma_load_3d(base + OFF_V + t * TILE_BYTES, &tm_qkv, bar(B_V + st), 2 * D + head * DH, t * TILE, img);
+                }
+                __syncwarp();
             }
         }
     } else if (warp == W_MMA) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
+        {
             const uint32_t idesc_pv = make_idesc_bf16(TILE, DH) | (1u << 16);     // B (= V) is MN-major
             uint32_t ph_p0 = 0, ph_p1 = 0;
             int it = 0;
@@ -248,6 +254,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
                 };
                 mbar_wait_cold(bar(B_QK + st), use & 1);
                 tc_fence_after();
+                if (elect_one_sync()) {
                 for (int w = 0; w < n_tiles; ++w) issue_s(w, 0);
                 if (tail) {
                     // the tail key's score for all 256 query rows: Q_w x (k_tail box)^T, N = 16 (row 0 of the box is the key, rows 1-7
@@ -261,6 +268,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
                         for (int k = 0; k < DH / 16; ++k) umma_bf16(tmem_base + 384 + 16 * w, dq + 2 * k, dkt + 2 * k, idesc_t, k != 0);
                     }
                 }
+                }
+                __syncwarp();
                 mbar_wait_cold(bar(B_V + st), use & 1);
                 tc_fence_after();
                 for (int kb = 0; kb < n_tiles; ++kb) {
@@ -271,6 +280,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
                         if (w) ph_p1 ^= 1; else ph_p0 ^= 1;
                         tc_fence_after();
                         const uint32_t v_addr = base + OFF_V + kb * TILE_BYTES;
+                        if (elect_one_sync()) {
                         for (int k = 0; k < nk / 16; ++k)                       // O_w (+)= P_w V_kb: one accumulator for both key blocks
                             umma_bf16_ts(tmem_base + 256 + 64 * w, tmem_base + 128 * w + g.p_kstep_cols * k,
                                          make_mnmajor_sw128_desc(v_addr + k * 2048, g.v_lbo, g.v_sbo), idesc_pv, (kb | k) != 0);
@@ -281,6 +291,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
                                              make_mnmajor_sw128_desc(base + OFF_TAIL + 2048, g.v_lbo, 0), idesc_pv, 1);
                             umma_commit(bar(B_O + w));
                         }
+                        }
+                        __syncwarp();
                     }
                 }
             }
@@ -596,7 +608,7 @@ attention_tc_pair_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid
     const uint32_t sbase = smem_u32(smem);
     auto bar = [&](int i) { return sbase + TP_OFF_BAR + 8u * i; };
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + TP_OFF_BAR + TP_NUM_BARS * 8);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // provably warp-uniform
     constexpr int WP_MMA = 8, WP_TMA = 9;
 
     pdl_launch_dependents();
@@ -617,17 +629,18 @@ attention_tc_pair_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
     pdl_wait();
 
     if (warp == WP_TMA) {
-        if (lane == 0) {
+        {
             int it = 0;
             for (int item = blockIdx.x; item < g.n_items; item += gridDim.x, ++it) {
                 const int pair = item / heads, head = item - pair * heads;
                 const int stg = it % TP_STAGES, use = it / TP_STAGES;
                 if (use > 0) mbar_wait_cold(bar(PB_FREE + stg), (use - 1) & 1);
                 const uint32_t base = sbase + stg * TP_STAGE_BYTES;
+                if (elect_one_sync()) {
                 mbar_arrive_expect_tx(bar(PB_LOAD + stg), (PAIR ? 6u : 3u) * static_cast<uint32_t>(T) * 128u);
                 if constexpr (PAIR) {
 #pragma unroll
@@ -640,10 +653,12 @@ attention_tc_pair_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid
 #pragma unroll
                     for (int m = 0; m < 3; ++m) tma_load_3d(base + m * TILE_BYTES, &tm_in, bar(PB_LOAD + stg), m * D + head * DH, 0, pair);
                 }
+                }
+                __syncwarp();
             }
         }
     } else if (warp == WP_MMA) {
-        if (lane == 0) {
+        {
             constexpr uint32_t idesc_s = make_idesc_bf16(TILE, TILE);
             const uint32_t idesc_pv = make_idesc_bf16(TILE, DH) | (1u << 16);     // B (= V) is MN-major
             auto issue_pv = [&](int j) {                       // O_j = P_j V_j over all 128 key rows of the tile
@@ -652,10 +667,13 @@ attention_tc_pair_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid
                 tc_fence_after();
                 const uint32_t v_addr = sbase + stg * TP_STAGE_BYTES + 2 * TILE_BYTES;
                 const uint32_t ts = tmem_base + TP_SLOT_COLS * slot;
+                if (elect_one_sync()) {
 #pragma unroll
-                for (int k = 0; k < TILE / 16; ++k)
-                    umma_bf16_ts(ts + 128, ts + g.p_kstep_cols * k, make_mnmajor_sw128_desc(v_addr + k * 2048, g.v_lbo, g.v_sbo), idesc_pv, k != 0);
-                umma_commit(bar(PB_O + slot));
+                    for (int k = 0; k < TILE / 16; ++k)
+                        umma_bf16_ts(ts + 128, ts + g.p_kstep_cols * k, make_mnmajor_sw128_desc(v_addr + k * 2048, g.v_lbo, g.v_sbo), idesc_pv, k != 0);
+                    umma_commit(bar(PB_O + slot));
+                }
+                __syncwarp();
             };
             int it = 0;
             for (int item = blockIdx.x; item < g.n_items; item += gridDim.x, ++it) {
@@ -665,9 +683,12 @@ attention_tc_pair_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid
                 tc_fence_after();
                 const uint32_t base = sbase + stg * TP_STAGE_BYTES;
                 const uint64_t dq = make_kmajor_sw128_desc(base), dk = make_kmajor_sw128_desc(base + TILE_BYTES);
+                if (elect_one_sync()) {
 #pragma unroll
-                for (int k = 0; k < DH / 16; ++k) umma_bf16(tmem_base + TP_SLOT_COLS * slot, dq + 2 * k, dk + 2 * k, idesc_s, k != 0);
-                umma_commit(bar(PB_S + slot));
+                    for (int k = 0; k < DH / 16; ++k) umma_bf16(tmem_base + TP_SLOT_COLS * slot, dq + 2 * k, dk + 2 * k, idesc_s, k != 0);
+                    umma_commit(bar(PB_S + slot));
+                }
+                __syncwarp();
                 if (it >= 1) issue_pv(it - 1);
             }
             if (it >= 1) issue_pv(it - 1);
