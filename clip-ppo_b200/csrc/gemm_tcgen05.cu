@@ -69,7 +69,10 @@ struct Cfg {
     static constexpr int CL = MODE;                                   // CTAs per cluster
     // the TMA reduce-add epilogue double-buffers its staging tile (the store engine reads smem
     // asynchronously) and pays for it with one pipeline stage
-    static constexpr int EPI_BUFS = (EPI == EPI_RESID_TMA || is_bf16_tma(EPI)) ? 2 : 1;
+    // row-affine epilogues (QKV, c_fc): ONE staging tile per warp buys a sixth TMA stage; the residual epilogues keep two (their
+    // x_old boxes land in both, one tile ahead)
+    static constexpr int EPI_BUFS = (EPI == CLIPPPO_EPI_ROWAFFINE_BF16 || EPI == CLIPPPO_EPI_ROWAFFINE_GELU_BF16) ? 1
+                                    : ((EPI == EPI_RESID_TMA || is_bf16_tma(EPI)) ? 2 : 1);
     static constexpr int STAGES = (MODE == 2) ? (EPI_BUFS == 2 ? 5 : 6) : (EPI_BUFS == 2 ? 3 : 4);
     static constexpr int A_STAGE_BYTES = BM * BK * 2;                 // 16 KB: my 128 rows of A
     static constexpr int B_STAGE_BYTES = (MODE == 2 ? BN / 2 : BN) * BK * 2;   // 16 KB (my W half) / 32 KB
@@ -329,11 +332,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     }
                     const int col0 = n_blk * BN + hh * 128 + ch * 64;
                     if (col0 < g.N) {
-                        uint8_t* buf = stg0 + (ch & 1) * EPI_STAGE_BYTES;
+                        uint8_t* buf = stg0 + (C::EPI_BUFS == 2 ? (ch & 1) : 0) * EPI_STAGE_BYTES;
                         if constexpr (is_resid_stats(EPI)) {
                             mbar_wait(xbar(ch), xphase);                // the x_old box of this chunk has landed in buf
                         } else {
-                            if (lane == 0) bulk_wait_group_read<1>();      // the box issued two chunks ago has left buf
+                            // the box that last left from buf (two chunks ago / with one staging tile: the previous chunk) has been read
+                            if (lane == 0) { if constexpr (C::EPI_BUFS == 2) bulk_wait_group_read<1>(); else bulk_wait_group_read<0>(); }
                             __syncwarp();
                         }
 #pragma unroll
