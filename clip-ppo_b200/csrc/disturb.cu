@@ -971,6 +971,15 @@ static int run_disturb(DisturbParams& p, const float* k1d_host, int k, cudaStrea
         }
         if (!S) return CLIPPPO_ERR_UNSUPPORTED;
         S = widen_for_small_batches(S, p.B, p.H, P, max_cluster, kNumSMs);
+        // k = 7 on a small RGB frame that one CTA could hold (84 x 84 x 3 SEVERE): the 7-tap filter phase is long and the kernel
+        // needs 80 registers, so one CTA per frame leaves an SM with two CTAs of 8 - 10 warps.  Two stripes per frame with row
+        // splits for 256 threads (two load trips instead of three or four, three CTAs per SM) reach 82 % of the HBM copy peak
+        // where one CTA per frame reaches 67 % (profiles/r02_disturb_smem_sweep84.txt) - affordable since the cluster barrier
+        // lost its memory barriers.  k <= 5 and C = 1 are faster with the whole frame in one CTA (83 - 87 %).
+        static const int env_two = env_int("CLIPPPO_DISTURB_TWO_STRIPES", 1);
+        const bool two_stripes = env_two && K == 7 && p.C == 3 && S == 1 && max_cluster >= 2 && env_budget == 113 && p.H >= 8 * P &&
+                                 tile_bytes(2) + hdr <= 75 * 1024;
+        if (two_stripes) S = 2;
         p.S = S;
         p.R = (p.H + S - 1) / S;
         // Blur tasks = C x nsplit x (W/4) column quads, one per thread.  A split costs 2P extra
@@ -985,6 +994,7 @@ static int run_disturb(DisturbParams& p, const float* k1d_host, int k, cudaStrea
             // gave 81-84 %; k = 7: 4 splits 67 %, 6 splits 62-64 %.
             auto min_rows = [&](int n) { return n >= 2 && 6 * P > 12 ? 6 * P : 12; };
             while (p.C * nq * nsplit < 300 && p.R / (nsplit + 1) >= min_rows(nsplit)) ++nsplit;
+            if (two_stripes) nsplit = (256 + p.C * nq / 2) / (p.C * nq) > 0 ? (256 + p.C * nq / 2) / (p.C * nq) : 1;   // ~256 tasks
         }
         if (nsplit > p.R) nsplit = p.R;
         p.nsplit = nsplit;

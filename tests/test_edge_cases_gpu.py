@@ -49,14 +49,16 @@ def test_ragged_batches_are_rows_of_a_larger_batch(native, n):
 @pytest.mark.parametrize("B", [1, 2, 7, 37])
 def test_disturbing_a_ragged_batch_equals_the_rows_of_a_larger_one(native, B):
     """Per-image work only (the contrast mean is per image, c / cutout are shared scalars): the first B frames of a batch
-    of 64 give the same result alone, bit for bit, with the same supplied randomness."""
+    of 64 give the same result alone with the same supplied randomness - up to the last bit of the per-image gray mean,
+    whose summation order follows the number of stripes a frame is cut into (which depends on the batch size below 148
+    frames: csrc/disturb.cu widen_for_small_batches)."""
     w = _wrapper("SEVERE")
     g = torch.Generator(device="cuda").manual_seed(11)
     x = torch.rand(64, 3, 84, 84, device="cuda", generator=g)
     noise = torch.randn(64, 3, 84, 84, device="cuda", generator=g)
     ref = w.apply_disturbances(x, noise=noise, contrast_factor=1.23, cutout_start=(5, 9))
     out = w.apply_disturbances(x[:B], noise=noise[:B], contrast_factor=1.23, cutout_start=(5, 9))
-    assert torch.equal(out, ref[:B])
+    assert (out - ref[:B]).abs().max().item() <= 1e-6
 
 
 def test_losses_on_the_smallest_inputs(native):
