@@ -668,6 +668,33 @@ def secondary_measurements(args, dev, pk, disturb_rows):
                                      "the 128-step GAE loop, the PPO-loss expressions with their .item() sync, fp16 eager tower"}}
     # (2) BASELINE configs[3]: Atari stacks (84x84 gray x 4, HARD), one GPU's share of 256 envs x 128 steps over 8 GPUs
     model = U.load_clip_model("ViT-B/32", device=dev)
+    # (1c) the headline step with the opt-in exact shortcut CLIPPPO_VIT_CLS_LAST_BLOCK=1 (NOT the headline: the headline pass runs
+    # every token through every block, as SURVEY.md section 8d counts its FLOPs)
+    if args.model == "ViT-B/32":
+        nB = args.batch
+        x8, nz, zz = seeded_inputs(dev, 0, nB, 224, 512)
+        xs = x8.float() / 255.0
+        wm = DisturbanceWrapperGPU(device=dev, seed=3, severity=DisturbanceSeverity.MODERATE)
+
+        def b32():
+            d = wm.apply_disturbances(xs, noise=nz, contrast_factor=1.1, cutout_start=(44, 56), out_scale=255.0)
+            e = U.generate_clip_embeddings(U.AblationMode.NONE, model, "image", nB, dev, images=d)
+            return U.compute_cosine_embedding_loss(zz, e)
+        t_full, t_cls = [], []
+        for _ in range(3):                                      # interleaved: the part drifts with temperature under its power cap
+            os.environ.pop("CLIPPPO_VIT_CLS_LAST_BLOCK", None)
+            t_full.append(event_ms(b32, 3, warm=1))
+            os.environ["CLIPPPO_VIT_CLS_LAST_BLOCK"] = "1"
+            t_cls.append(event_ms(b32, 3, warm=1))
+        os.environ.pop("CLIPPPO_VIT_CLS_LAST_BLOCK", None)
+        ms_full, ms_cls = statistics.median(t_full), statistics.median(t_cls)
+        out["cls_rows_only_in_last_block"] = {
+            "what": "opt-in, exact: after the last block's attention only the class-token rows go through out_proj / c_fc / c_proj "
+                    "(VisionTransformer.forward reads x[:, 0, :] only; embeddings bitwise equal, tests/test_edge_cases_gpu.py); "
+                    "the same public calls, same box, three interleaved rounds of three steps each, medians",
+            "frames": nB, "ms_full": round(ms_full, 2), "ms": round(ms_cls, 2),
+            "frames_per_s_full": round(nB / (ms_full * 1e-3), 1), "frames_per_s": round(nB / (ms_cls * 1e-3), 1)}
+        del x8, nz, zz, xs
     stacks = 4096
     g = torch.Generator(device=dev).manual_seed(6)
     obs = torch.randint(0, 256, (stacks, 4, 84, 84), device=dev, generator=g).float()
@@ -706,6 +733,10 @@ def secondary_measurements(args, dev, pk, disturb_rows):
                                     "MODERATE, same public calls", "frames": nL, "ms": round(ms, 2),
                           "frames_per_s": round(nL / (ms * 1e-3), 1),
                           "tower_tflops_incl_all_kernels": round(nL * FLOPS_PER_IMAGE_BY_MODEL["ViT-L/14"] / (ms * 1e-3) / 1e12, 1)}
+        os.environ["CLIPPPO_VIT_CLS_LAST_BLOCK"] = "1"
+        ms_c = event_ms(l14, 3)
+        os.environ.pop("CLIPPPO_VIT_CLS_LAST_BLOCK", None)
+        out["vit_l14"]["cls_rows_only_in_last_block"] = {"ms": round(ms_c, 2), "frames_per_s": round(nL / (ms_c * 1e-3), 1)}
         del x8, nz, zz, xs, model
         torch.cuda.empty_cache()
     return out

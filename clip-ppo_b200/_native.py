@@ -19,7 +19,7 @@ ERR_WORKSPACE, ERR_UNSUPPORTED, ERR_ALIGN, ERR_CUDA, ERR_DIM_MISMATCH = -5, -6, 
 
 STAGE_NOISE, STAGE_CONTRAST, STAGE_BLUR, STAGE_CUTOUT, STAGE_ALL = 1, 2, 4, 8, 15
 IMG_F32, IMG_U8 = 0, 1
-VIT_L2NORM, VIT_PRENORMALIZED = 1, 2
+VIT_L2NORM, VIT_PRENORMALIZED, VIT_CLS_LAST_BLOCK = 1, 2, 4
 EPI_ROWAFFINE_BF16, EPI_ROWAFFINE_GELU_BF16, EPI_RESID_BF16, EPI_RESID_STATS_BF16 = 6, 7, 8, 9
 EPI_BIAS_BF16, EPI_BIAS_GELU_BF16, EPI_BIAS_RESID_F32, EPI_PATCH_F32, EPI_F32 = 0, 1, 2, 3, 4
 

@@ -169,8 +169,11 @@ bool fused_stats() {                                   // read per tower pass (t
 // L x [ x += out_proj(attn(ln_1(x)));  x += c_proj(QuickGELU(c_fc(ln_2(x)))) ] on the bf16 residual stream X [rows, D]
 // fused = true: `stats` arrives holding the partial sums of the rows of X (written by ln_pre / rowstats) and every
 // residual GEMM refreshes them.
+// cls_last (image tower, fused schedule only): the last block's out_proj / c_fc / c_proj run on the n class-token rows alone -
+// row 0 of every image, addressed through tensor maps with a row stride of T * D - because ln_post reads nothing else.
 int run_blocks(const std::vector<clipppo_tower_layer>& layers, int n, int T, int D, int heads, bool causal,
-               __nv_bfloat16* X, float* stats, __nv_bfloat16* Y, __nv_bfloat16* H, cudaStream_t stream, bool fused) {
+               __nv_bfloat16* X, float* stats, __nv_bfloat16* Y, __nv_bfloat16* H, cudaStream_t stream, bool fused,
+               bool cls_last = false) {
     const int rows = n * T;
     CUtensorMap tmX, tmY, tmH;
     VIT_TRY(make_bf16_kmajor_tmap(&tmX, X, rows, D, D, gemm_a_box_rows()));
@@ -178,10 +181,28 @@ int run_blocks(const std::vector<clipppo_tower_layer>& layers, int n, int T, int
     VIT_TRY(make_bf16_kmajor_tmap(&tmH, H, rows, 4 * D, 4 * D, gemm_a_box_rows()));
     if (fused) {
         const int P = D / 128;
-        for (const clipppo_tower_layer& w : layers) {
+        for (size_t li = 0; li < layers.size(); ++li) {
+            const clipppo_tower_layer& w = layers[li];
             VIT_TRY(gemm_bf16_launch(tmX, w.tm_qkv, rows, 3 * D, D, CLIPPPO_EPI_ROWAFFINE_BF16, w.b_qkv, nullptr, 0,
                                      H, 3 * D, stream, stats, w.s_qkv, P));
             VIT_TRY(attention_launch(H, n, T, heads, D / heads, Y, stream, causal));
+            if (cls_last && li + 1 == layers.size()) {
+                // every key / value of the block was needed (attention above), but only the class token's query row is read
+                // from here on: M = n rows with a row stride of T * D; H (the QKV matrix, consumed) takes the [n, 4 D] hidden rows;
+                // the statistics of the n rows use the first n entries of `stats`
+                const long long ldx = static_cast<long long>(T) * D;
+                CUtensorMap tmYc, tmXc, tmHc;
+                VIT_TRY(make_bf16_kmajor_tmap(&tmYc, Y, n, D, ldx, gemm_a_box_rows()));
+                VIT_TRY(make_bf16_kmajor_tmap(&tmXc, X, n, D, ldx, gemm_a_box_rows()));
+                VIT_TRY(make_bf16_kmajor_tmap(&tmHc, H, n, 4 * D, 4 * D, gemm_a_box_rows()));
+                VIT_TRY(gemm_bf16_launch(tmYc, w.tm_out, n, D, D, CLIPPPO_EPI_RESID_STATS_BF16, w.b_out, nullptr, 0, X, ldx, stream,
+                                         nullptr, nullptr, 0, stats));
+                VIT_TRY(gemm_bf16_launch(tmXc, w.tm_fc, n, 4 * D, D, CLIPPPO_EPI_ROWAFFINE_GELU_BF16, w.b_fc, nullptr, 0,
+                                         H, 4 * D, stream, stats, w.s_fc, P));
+                VIT_TRY(gemm_bf16_launch(tmHc, w.tm_proj, n, D, 4 * D, CLIPPPO_EPI_RESID_STATS_BF16, w.b_proj, nullptr, 0, X, ldx, stream,
+                                         nullptr, nullptr, 0, stats));
+                break;
+            }
             VIT_TRY(gemm_bf16_launch(tmY, w.tm_out, rows, D, D, CLIPPPO_EPI_RESID_STATS_BF16, w.b_out, nullptr, 0, X, D, stream,
                                      nullptr, nullptr, 0, stats));
             VIT_TRY(gemm_bf16_launch(tmX, w.tm_fc, rows, 4 * D, D, CLIPPPO_EPI_ROWAFFINE_GELU_BF16, w.b_fc, nullptr, 0,
@@ -307,7 +328,8 @@ int encode_chunk(const clipppo_vit_s* h, const void* images, int img_dtype, cons
     const bool fused = fused_stats();
     VIT_TRY(layernorm_launch(ws.X0, h->ln_pre_g, h->ln_pre_b, rows, D, D, ws.X, stream,                // ln_pre -> bf16 residual
                              fused ? ws.stats : nullptr, D / 128));                                   //  (+ the statistics block 0's ln_1 needs)
-    VIT_TRY(run_blocks(h->layers, n, T, D, h->cfg.heads, false, ws.X, ws.stats, ws.Y, ws.H, stream, fused));
+    VIT_TRY(run_blocks(h->layers, n, T, D, h->cfg.heads, false, ws.X, ws.stats, ws.Y, ws.H, stream, fused,
+                       fused && (flags & CLIPPPO_VIT_CLS_LAST_BLOCK) != 0));
     VIT_TRY(layernorm_bf16in_launch(ws.X, h->ln_post_g, h->ln_post_b, n, D, static_cast<long long>(T) * D, ws.Ycls, stream));
     VIT_TRY(gemm_bf16_launch(tmC, h->tm_head, n, O, D, CLIPPPO_EPI_F32, nullptr, nullptr, 0, out, O, stream));
     if (flags & CLIPPPO_VIT_L2NORM) {

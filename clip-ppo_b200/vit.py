@@ -11,6 +11,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 from dataclasses import dataclass
 from typing import Dict, Optional
 
@@ -45,6 +46,13 @@ def config_from_state_dict(sd: Dict[str, torch.Tensor], prefix: str = "visual.")
     blocks = {k[len(prefix):].split(".")[2] for k in sd if k.startswith(prefix + "transformer.resblocks.")}
     return TowerConfig(width=D, layers=len(blocks), heads=D // 64, patch=P, image=G * P,
                        out_dim=int(sd[prefix + "proj"].shape[1]))
+
+
+def _cls_last_flag() -> int:
+    """CLIPPPO_VIT_CLS_LAST_BLOCK=1 (opt-in, read per call): after the last block's attention only the class-token rows go
+    through out_proj / c_fc / c_proj.  Exact - ``VisionTransformer.forward`` reads ``x[:, 0, :]`` only, embeddings are bitwise
+    equal - and 6 % fewer FLOPs on ViT-B/32.  Off by default: the default pass runs every token through every block."""
+    return N.VIT_CLS_LAST_BLOCK if os.environ.get("CLIPPPO_VIT_CLS_LAST_BLOCK", "") not in ("", "0") else 0
 
 
 class VitEngine:
@@ -137,7 +145,7 @@ class VitEngine:
             raise ValueError(f"expected [N,C,h,w], got {tuple(images.shape)}")
         if images.dtype not in (torch.float32, torch.uint8):
             images = images.float()
-        key = (tuple(images.shape), images.dtype, float(pre_scale), bool(l2norm), bool(prenormalized))
+        key = (tuple(images.shape), images.dtype, float(pre_scale), bool(l2norm), bool(prenormalized), _cls_last_flag())
         ent = self._graphs.pop(key, None)                 # re-inserted below: the dict is kept in least-recently-used order
         if ent is None:
             while len(self._graphs) >= self.GRAPH_CACHE_ENTRIES:       # each entry owns an input, an output and a full workspace
@@ -172,7 +180,7 @@ class VitEngine:
             st = N.lib().clipppo_vit_encode(
                 self._handle, images.data_ptr(), N.IMG_U8 if images.dtype == torch.uint8 else N.IMG_F32,
                 N.strides4(images), n, c, h, w, float(pre_scale),
-                (N.VIT_L2NORM if l2norm else 0) | (N.VIT_PRENORMALIZED if prenormalized else 0), out.data_ptr(),
+                (N.VIT_L2NORM if l2norm else 0) | (N.VIT_PRENORMALIZED if prenormalized else 0) | _cls_last_flag(), out.data_ptr(),
                 ws.data_ptr(), ws.numel(), torch.cuda.current_stream(self.device).cuda_stream)
         N.check(st, "clipppo_vit_encode")
 
@@ -212,7 +220,7 @@ class VitEngine:
             st = N.lib().clipppo_vit_encode(
                 self._handle, images.data_ptr(), N.IMG_U8 if images.dtype == torch.uint8 else N.IMG_F32,
                 N.strides4(images), n, c, h, w, float(pre_scale),
-                (N.VIT_L2NORM if l2norm else 0) | (N.VIT_PRENORMALIZED if prenormalized else 0), out.data_ptr(),
+                (N.VIT_L2NORM if l2norm else 0) | (N.VIT_PRENORMALIZED if prenormalized else 0) | _cls_last_flag(), out.data_ptr(),
                 ws.data_ptr(), ws.numel(), torch.cuda.current_stream(self.device).cuda_stream)
         N.check(st, "clipppo_vit_encode")
         return out

@@ -217,6 +217,10 @@ int clipppo_vit_workspace_bytes(clipppo_vit_t handle, int n_images, size_t* byte
 #define CLIPPPO_IMG_U8  1
 #define CLIPPPO_VIT_L2NORM        1   /* L2-normalise the output rows (generate_clip_embeddings)      */
 #define CLIPPPO_VIT_PRENORMALIZED 2   /* input already (u - mean)/std: skip the normalise step        */
+#define CLIPPPO_VIT_CLS_LAST_BLOCK 4  /* opt-in, exact: after the last block's attention only the class-token rows go through
+                                        out_proj / c_fc / c_proj - VisionTransformer.forward reads x[:, 0, :] only, the other
+                                        tokens' outputs of that block are never used (embeddings bitwise equal; 6 % fewer FLOPs
+                                        on ViT-B/32).  Off by default: the default pass runs every token through every block.  */
 /*   images : [N,C,h,w] with element strides; C == 3, or C == 1 (gray broadcast to RGB, the
  *            Atari path clip_ppo_atari.py:249-269).  pre_scale multiplies the raw pixel before
  *            resize (1/255 for generate_clip_embeddings, 1/255^2 for the Atari double divide,

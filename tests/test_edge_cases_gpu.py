@@ -77,3 +77,23 @@ def test_losses_on_the_smallest_inputs(native):
     r = torch.tensor([[1.0]], device="cuda"); d = torch.zeros(1, 1, device="cuda"); v = torch.tensor([[0.5]], device="cuda")
     adv, ret = Ls.gae(r, v, d, torch.tensor([[0.25]], device="cuda"), torch.zeros(1, device="cuda"), 0.99, 0.95)
     assert abs(adv.item() - (1.0 + 0.99 * 0.25 - 0.5)) <= 1e-7 and abs(ret.item() - (adv.item() + 0.5)) <= 1e-7
+
+
+@pytest.mark.parametrize("name,n,hw", [("ViT-B/32", 1, 84), ("ViT-B/32", 37, 84), ("ViT-B/32", 300, 224), ("ViT-L/14", 9, 224)])
+def test_cls_only_last_block_is_bitwise_the_full_pass(native, monkeypatch, name, n, hw):
+    """CLIPPPO_VIT_CLS_LAST_BLOCK=1 (opt-in): the last block's out_proj / c_fc / c_proj on the class-token rows alone.
+    VisionTransformer.forward reads x[:, 0, :] only, and a row of the GEMM does not depend on the other rows of its tile, so the
+    embeddings are bitwise those of the default pass (every token through every block) - eager and graph replay."""
+    from clip_ppo_b200.clip_compat.model import random_visual_state_dict
+    from clip_ppo_b200.vit import VitEngine
+    eng = VitEngine(random_visual_state_dict(name, 0), device="cuda")
+    g = torch.Generator(device="cuda").manual_seed(3)
+    x = torch.rand(n, 3, hw, hw, device="cuda", generator=g) * 255.0
+    monkeypatch.delenv("CLIPPPO_VIT_CLS_LAST_BLOCK", raising=False)
+    full = eng.encode(x, pre_scale=1.0 / 255.0, l2norm=True)
+    full_raw = eng.encode(x, pre_scale=1.0 / 255.0, l2norm=False)
+    monkeypatch.setenv("CLIPPPO_VIT_CLS_LAST_BLOCK", "1")
+    assert torch.equal(eng.encode(x, pre_scale=1.0 / 255.0, l2norm=True), full)
+    assert torch.equal(eng.encode(x, pre_scale=1.0 / 255.0, l2norm=False), full_raw)
+    if n <= 512:
+        assert torch.equal(eng.encode_graphed(x, pre_scale=1.0 / 255.0, l2norm=True), full)
