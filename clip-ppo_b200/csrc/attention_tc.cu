@@ -164,7 +164,7 @@ __global__ void __launch_bounds__(ATC_THREADS, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_tail,
                     const __grid_constant__ CUtensorMap tm_out, const AtcArgs g) {
     extern __shared__ uint8_t smem_raw[];
-        // 1024-byte alignment as an OFFSET from the __shared__ symbol: the pointer keeps its address space, so the staging-tile
+    // 1024-byte alignment as an OFFSET from the __shared__ symbol: the pointer keeps its address space, so the staging-tile
     // accesses are STS / LDS instead of generic ST.E / LD.E
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const uint32_t sbase = smem_u32(smem);
@@ -217,19 +217,19 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
                 const uint32_t base = sbase + st * STAGE_BYTES;
                 if (use > 0) mbar_wait_cold(bar(B_FREE + st), (use - 1) & 1);     // every reader of the stage's previous item is done
                 if (elect_one_sync()) {
-                mbar_arrive_expect_tx(bar(B_QK + st), 2u * n_tiles * TILE_BYTES + (tail ? 3 * 1024 : 0));
-                for (int t = 0; t < n_tiles; ++t) {
-                    tma_load_3d(base + OFF_Q + t * TILE_BYTES, &tm_qkv, bar(B_QK + st), head * DH, t * TILE, img);
-                    tma_load_3d(base + OFF_K + t * TILE_BYTES, &tm_qkv, bar(B_QK + st), D + head * DH, t * TILE, img);
-                }
-                if (tail) {
-                    tma_load_3d(base + OFF_TAIL, &tm_tail, bar(B_QK + st), head * DH, 2 * TILE, img);
-                    tma_load_3d(base + OFF_TAIL + 1024, &tm_tail, bar(B_QK + st), D + head * DH, 2 * TILE, img);
-                    tma_load_3d(base + OFF_TAIL + 2048, &tm_tail, bar(B_QK + st), 2 * D + head * DH, 2 * TILE, img);
-                }
-                mbar_arrive_expect_tx(bar(B_V + st), static_cast<uint32_t>(n_tiles) * TILE_BYTES);
-                for (int t = 0; t < n_tiles; ++t)
-                    tma_load_3d(base + OFF_V + t * TILE_BYTES, &tm_qkv, bar(B_V + st), 2 * D + head * DH, t * TILE, img);
+                    mbar_arrive_expect_tx(bar(B_QK + st), 2u * n_tiles * TILE_BYTES + (tail ? 3 * 1024 : 0));
+                    for (int t = 0; t < n_tiles; ++t) {
+                        tma_load_3d(base + OFF_Q + t * TILE_BYTES, &tm_qkv, bar(B_QK + st), head * DH, t * TILE, img);
+                        tma_load_3d(base + OFF_K + t * TILE_BYTES, &tm_qkv, bar(B_QK + st), D + head * DH, t * TILE, img);
+                    }
+                    if (tail) {
+                        tma_load_3d(base + OFF_TAIL, &tm_tail, bar(B_QK + st), head * DH, 2 * TILE, img);
+                        tma_load_3d(base + OFF_TAIL + 1024, &tm_tail, bar(B_QK + st), D + head * DH, 2 * TILE, img);
+                        tma_load_3d(base + OFF_TAIL + 2048, &tm_tail, bar(B_QK + st), 2 * D + head * DH, 2 * TILE, img);
+                    }
+                    mbar_arrive_expect_tx(bar(B_V + st), static_cast<uint32_t>(n_tiles) * TILE_BYTES);
+                    for (int t = 0; t < n_tiles; ++t)
+                        tma_load_3d(base + OFF_V + t * TILE_BYTES, &tm_qkv, bar(B_V + st), 2 * D + head * DH, t * TILE, img);
                 }
                 __syncwarp();
             }
@@ -255,19 +255,19 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
                 mbar_wait_cold(bar(B_QK + st), use & 1);
                 tc_fence_after();
                 if (elect_one_sync()) {
-                for (int w = 0; w < n_tiles; ++w) issue_s(w, 0);
-                if (tail) {
-                    // the tail key's score for all 256 query rows: Q_w x (k_tail box)^T, N = 16 (row 0 of the box is the key, rows 1-7
-                    // are zero-filled, the second 8-row group aliases the first), into 16 spare TMEM columns per tile.  Complete
-                    // before the softmax asks for it: every later commit on B_S covers these MMAs.
-                    const uint64_t dkt = make_kmajor_sw128_desc(base + OFF_TAIL + 1024) & ~(static_cast<uint64_t>(0x3FFF) << 32);   // SBO = 0
-                    const uint32_t idesc_t = make_idesc_bf16(TILE, 16);
-                    for (int w = 0; w < 2; ++w) {
-                        const uint64_t dq = make_kmajor_sw128_desc(base + OFF_Q + w * TILE_BYTES);
+                    for (int w = 0; w < n_tiles; ++w) issue_s(w, 0);
+                    if (tail) {
+                        // the tail key's score for all 256 query rows: Q_w x (k_tail box)^T, N = 16 (row 0 of the box is the key, rows 1-7
+                        // are zero-filled, the second 8-row group aliases the first), into 16 spare TMEM columns per tile.  Complete
+                        // before the softmax asks for it: every later commit on B_S covers these MMAs.
+                        const uint64_t dkt = make_kmajor_sw128_desc(base + OFF_TAIL + 1024) & ~(static_cast<uint64_t>(0x3FFF) << 32);   // SBO = 0
+                        const uint32_t idesc_t = make_idesc_bf16(TILE, 16);
+                        for (int w = 0; w < 2; ++w) {
+                            const uint64_t dq = make_kmajor_sw128_desc(base + OFF_Q + w * TILE_BYTES);
 #pragma unroll
-                        for (int k = 0; k < DH / 16; ++k) umma_bf16(tmem_base + 384 + 16 * w, dq + 2 * k, dkt + 2 * k, idesc_t, k != 0);
+                            for (int k = 0; k < DH / 16; ++k) umma_bf16(tmem_base + 384 + 16 * w, dq + 2 * k, dkt + 2 * k, idesc_t, k != 0);
+                        }
                     }
-                }
                 }
                 __syncwarp();
                 mbar_wait_cold(bar(B_V + st), use & 1);
@@ -281,16 +281,16 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
                         tc_fence_after();
                         const uint32_t v_addr = base + OFF_V + kb * TILE_BYTES;
                         if (elect_one_sync()) {
-                        for (int k = 0; k < nk / 16; ++k)                       // O_w (+)= P_w V_kb: one accumulator for both key blocks
-                            umma_bf16_ts(tmem_base + 256 + 64 * w, tmem_base + 128 * w + g.p_kstep_cols * k,
-                                         make_mnmajor_sw128_desc(v_addr + k * 2048, g.v_lbo, g.v_sbo), idesc_pv, (kb | k) != 0);
-                        if (kb + 1 < n_tiles) issue_s(w, kb + 1);          // in order behind the MMAs that read P_w
-                        else {
-                            if (tail)      // + p_t v_tail: A = the (p_t, 0, ...) columns, B = the v_tail box (row 0; both 8-row groups alias it)
-                                umma_bf16_ts(tmem_base + 256 + 64 * w, tmem_base + 128 * w + 64,
-                                             make_mnmajor_sw128_desc(base + OFF_TAIL + 2048, g.v_lbo, 0), idesc_pv, 1);
-                            umma_commit(bar(B_O + w));
-                        }
+                            for (int k = 0; k < nk / 16; ++k)                       // O_w (+)= P_w V_kb: one accumulator for both key blocks
+                                umma_bf16_ts(tmem_base + 256 + 64 * w, tmem_base + 128 * w + g.p_kstep_cols * k,
+                                             make_mnmajor_sw128_desc(v_addr + k * 2048, g.v_lbo, g.v_sbo), idesc_pv, (kb | k) != 0);
+                            if (kb + 1 < n_tiles) issue_s(w, kb + 1);          // in order behind the MMAs that read P_w
+                            else {
+                                if (tail)      // + p_t v_tail: A = the (p_t, 0, ...) columns, B = the v_tail box (row 0; both 8-row groups alias it)
+                                    umma_bf16_ts(tmem_base + 256 + 64 * w, tmem_base + 128 * w + 64,
+                                                 make_mnmajor_sw128_desc(base + OFF_TAIL + 2048, g.v_lbo, 0), idesc_pv, 1);
+                                umma_commit(bar(B_O + w));
+                            }
                         }
                         __syncwarp();
                     }
@@ -602,7 +602,7 @@ template <bool PAIR>
 __global__ void __launch_bounds__(TP_THREADS, 1)
 attention_tc_pair_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_out, const TpArgs g) {
     extern __shared__ uint8_t smem_raw[];
-        // 1024-byte alignment as an OFFSET from the __shared__ symbol: the pointer keeps its address space, so the staging-tile
+    // 1024-byte alignment as an OFFSET from the __shared__ symbol: the pointer keeps its address space, so the staging-tile
     // accesses are STS / LDS instead of generic ST.E / LD.E
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const uint32_t sbase = smem_u32(smem);
@@ -641,18 +641,18 @@ attention_tc_pair_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid
                 if (use > 0) mbar_wait_cold(bar(PB_FREE + stg), (use - 1) & 1);
                 const uint32_t base = sbase + stg * TP_STAGE_BYTES;
                 if (elect_one_sync()) {
-                mbar_arrive_expect_tx(bar(PB_LOAD + stg), (PAIR ? 6u : 3u) * static_cast<uint32_t>(T) * 128u);
-                if constexpr (PAIR) {
+                    mbar_arrive_expect_tx(bar(PB_LOAD + stg), (PAIR ? 6u : 3u) * static_cast<uint32_t>(T) * 128u);
+                    if constexpr (PAIR) {
 #pragma unroll
-                    for (int h = 0; h < 2; ++h) {             // an image beyond the batch (odd n) is zero-filled by the TMA unit
+                        for (int h = 0; h < 2; ++h) {             // an image beyond the batch (odd n) is zero-filled by the TMA unit
 #pragma unroll
-                        for (int m = 0; m < 3; ++m)
-                            tma_load_3d(base + m * TILE_BYTES + h * 64 * 128, &tm_in, bar(PB_LOAD + stg), m * D + head * DH, 0, 2 * pair + h);
+                            for (int m = 0; m < 3; ++m)
+                                tma_load_3d(base + m * TILE_BYTES + h * 64 * 128, &tm_in, bar(PB_LOAD + stg), m * D + head * DH, 0, 2 * pair + h);
+                        }
+                    } else {
+#pragma unroll
+                        for (int m = 0; m < 3; ++m) tma_load_3d(base + m * TILE_BYTES, &tm_in, bar(PB_LOAD + stg), m * D + head * DH, 0, pair);
                     }
-                } else {
-#pragma unroll
-                    for (int m = 0; m < 3; ++m) tma_load_3d(base + m * TILE_BYTES, &tm_in, bar(PB_LOAD + stg), m * D + head * DH, 0, pair);
-                }
                 }
                 __syncwarp();
             }

@@ -138,7 +138,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     using C = Cfg<MODE, EPI>;
     constexpr int CL = C::CL, STAGES = C::STAGES;
     extern __shared__ uint8_t smem_raw[];
-        // 1024-byte alignment as an OFFSET from the __shared__ symbol: the pointer keeps its address space, so the staging-tile
+    // 1024-byte alignment as an OFFSET from the __shared__ symbol: the pointer keeps its address space, so the staging-tile
     // accesses are STS / LDS instead of generic ST.E / LD.E
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const uint32_t sbase = smem_u32(smem);
